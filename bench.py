@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the MinGraph-UNet graph block on B200 (driver contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg1]
+
+One "step" = one pass of the hot path over one batch of synthetic images:
+  per-pixel feature map (B,20,H,W) -> patch-mean pool -> 4-connected patch grid -> patch GAT ->
+  predictor GAT -> softmax/argmax -> N-cut loss -> region mean-pool -> region GAT -> nearest
+  un-pool written straight into the channel slice [32:96] of a (B,96,H,W) fusion buffer.
+Workload at every N: BASELINE.json configs[1] per GPU (512x512, batch 16 per GPU, bf16 storage,
+fp32 math), i.e. weak scaling by image; ranks exchange only the small per-image outputs
+(loss, region features, labels) with one NCCL all-gather per step.
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU oracle port of the reference
+(oracle/restate.py; the reference itself is pure Python and does not travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (H, W, images per GPU, storage dtype)
+    "cfg1": (256, 256, 1, "float32"),      # BASELINE configs[0]: the reference's CPU-runnable case
+    "cfg2": (512, 512, 16, "bfloat16"),    # BASELINE configs[1]: headline single-GPU config
+    "cfg3": (1024, 1024, 8, "bfloat16"),   # BASELINE configs[2] shard: 64 images over 8 GPUs
+}
+IN_DIM, D_OUT, HEADS, K_SEG, PATCH, C_UNET = 20, 64, 4, 2, 16, 32
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
+    ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_config(name, n_gpus):
+    H, W, B, dt = WORKLOADS[name]
+    nph, npw = -(-H // PATCH), -(-W // PATCH)
+    N = nph * npw
+    E = 2 * (nph * (npw - 1) + npw * (nph - 1))
+    return dict(workload=f"{name}: {H}x{W} images, batch {B}/GPU, {dt} storage + fp32 math, graph block "
+                         f"(pool->grid graph->patch GAT->N-cut->region GAT->un-pool into fusion buffer)",
+                H=H, W=W, images_per_gpu=B, global_batch=B * n_gpus, nodes_per_image=N, edges_per_image=E,
+                node_feature_dim=IN_DIM, gat_out=D_OUT, heads=HEADS, num_segments=K_SEG, patch_size=PATCH,
+                parallelism=f"shard-by-image x{n_gpus}",
+                l2="working set per step (pool read + un-pool write) exceeds the 126 MB L2; no explicit flush")
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------
+def cpu_block_images(name, n_images, seed=0):
+    """Run the oracle port of the reference's per-image loop on ``n_images`` synthetic images of the
+    workload; returns seconds.  Same stage order as the GPU step, fp32 (the reference is fp32-only)."""
+    import torch
+    from oracle import restate as O
+    H, W, _, _ = WORKLOADS[name]
+    params = O.init_block_params(IN_DIM, D_OUT, HEADS, K_SEG, seed=1234)
+    gen = torch.Generator().manual_seed(seed)
+    fms = [torch.randn(IN_DIM, H, W, generator=gen) for _ in range(n_images)]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for fm in fms:
+            x = O.patch_mean_pool(fm, PATCH)
+            O.graph_block_image(x, H, W, params, K=K_SEG, want_dense=True)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.cpu_sample_images or 2
+    for _ in range(max(args.warmup, 1)):
+        cpu_block_images(args.workload, 1)
+    times = [cpu_block_images(args.workload, sample, seed=s) for s in range(args.steps)]
+    total = sum(times)
+    value = sample * args.steps / total
+    cfg = workload_config(args.workload, args.gpus)
+    line = {
+        "impl": "reference", "metric": "graph_block_images_per_s", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sample} images of the workload per step through oracle/restate.py "
+                                   f"(CPU restatement of the reference's per-image loop, fp32)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """NVML sampling thread (SM clock + clock-event reasons) running during the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self, note):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0,
+                    "note": "NVML unavailable"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "note": note}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mingraph_unet_b200 as mg
+    from mingraph_unet_b200 import _lib
+    from oracle import restate as O          # only for the reference weight init + the cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N>1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    H, W, B, dtname = WORKLOADS[args.workload]
+    dtype = getattr(torch, dtname)
+    cfg = workload_config(args.workload, world)
+    N, E = cfg["nodes_per_image"], cfg["edges_per_image"]
+    nph, npw = -(-H // PATCH), -(-W // PATCH)
+
+    # model: reference init (xavier_uniform gain 1.414) under seed 1234, loaded through state_dict
+    params = O.init_block_params(IN_DIM, D_OUT, HEADS, K_SEG, seed=1234)
+    blk = mg.GraphBlock(node_feature_dim=IN_DIM, num_segments=K_SEG)
+    for name, net in (("patch", blk.patch_gat_model), ("pred", blk.segment_predictor.gnn_predictor),
+                      ("region", blk.region_gat_model)):
+        sd = {}
+        for h in range(params[f"{name}_W"].shape[0]):
+            sd[f"gat_layers.0.heads.{h}.W.weight"] = params[f"{name}_W"][h].clone()
+            sd[f"gat_layers.0.heads.{h}.a.weight"] = params[f"{name}_a"][h].reshape(1, -1).clone()
+        net.load_state_dict(sd)
+    blk = blk.to(dev).eval()
+
+    gen = torch.Generator().manual_seed(1000 + rank)
+    fm_host = torch.randn(B, IN_DIM, H, W, generator=gen).to(dtype).pin_memory()
+    fm_dev = fm_host.to(dev)
+    fusion = torch.zeros(B, C_UNET + D_OUT, H, W, dtype=dtype, device=dev)     # [0:32] decoder features, [32:96] F_g
+    f_g_slice = fusion[:, C_UNET:]
+    small_f = torch.empty(B * (1 + K_SEG * D_OUT), dtype=torch.float32, device=dev)
+    small_i = torch.empty(B * N, dtype=torch.int32, device=dev)
+    gath_f = torch.empty(world * small_f.numel(), dtype=torch.float32, device=dev) if world > 1 else None
+    gath_i = torch.empty(world * small_i.numel(), dtype=torch.int32, device=dev) if world > 1 else None
+    host_f = torch.empty(small_f.numel(), dtype=torch.float32).pin_memory()
+    host_i = torch.empty(small_i.numel(), dtype=torch.int32).pin_memory()
+
+    unpool_ev = []
+
+    def step(x_dev, time_unpool=False):
+        with torch.no_grad():
+            out = blk(feature_map=x_dev, image_size=(H, W), want_dense=False)
+            if time_unpool:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            mg.ops.unpool_nearest(out.region_features, out.hard_labels, nph, npw, H, W, out=f_g_slice)
+            if time_unpool:
+                e1.record()
+                unpool_ev.append((e0, e1))
+            small_f[:B].copy_(out.l_partition)
+            small_f[B:].copy_(out.region_features.reshape(-1))
+            small_i.copy_(out.hard_labels.reshape(-1))
+            if world > 1:
+                dist.all_gather_into_tensor(gath_f, small_f)
+                dist.all_gather_into_tensor(gath_i, small_i)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(fm_dev)
+    sampler = ClockSampler(local)
+    barrier()
+    launches0 = _lib.launch_count()
+    sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        step(fm_dev, time_unpool=True)
+    t_end.record()
+    barrier()
+    sampler.stop()
+    launches = _lib.launch_count() - launches0
+    ms_total = t_start.elapsed_time(t_end)
+    note = "sampled during the timed region"
+    if len(sampler.samples) < 5:        # very short timed region: keep the same load running while sampling
+        sampler.start()
+        t_until = time.time() + 1.0
+        while time.time() < t_until:
+            for _ in range(20):
+                step(fm_dev)
+            torch.cuda.synchronize()
+        sampler.stop()
+        note = "timed region shorter than the NVML sampling period; sampled under the same load right after it"
+    unpool_ms = statistics.mean(a.elapsed_time(b) for a, b in unpool_ev)
+
+    # ---- end-to-end through the public API with host buffers (e2e) ---------------------------
+    def e2e_step():
+        x = fm_host.to(dev, non_blocking=True)
+        step(x)
+        host_f.copy_(small_f, non_blocking=True)
+        host_i.copy_(small_i, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_steps = max(10, min(args.steps, 50))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # ---- max over ranks ------------------------------------------------------------------------
+    tm = torch.tensor([ms_total, e2e_ms, unpool_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, unpool_ms = (float(v) for v in tm.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        b = 2 if dtype == torch.bfloat16 else 4
+        unpool_bytes = B * (D_OUT * H * W * b + 4 * N + K_SEG * D_OUT * 4)
+        pool_bytes = B * (IN_DIM * H * W * b + N * IN_DIM * b)
+        achieved = unpool_bytes / (unpool_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get("unpool_dram_bytes_per_launch")
+        except Exception:
+            pass
+        ms_step = ms_total / args.steps
+        line = {
+            "metric": "graph_block_images_per_s", "value": B * world * args.steps / (ms_total * 1e-3),
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if dtype == torch.float32 else "bf16 storage / f32 math", "data": "synthetic", "config": cfg,
+            "edges_per_s": B * world * E * args.steps / (ms_total * 1e-3),
+            "step_hbm_gbs": (unpool_bytes + pool_bytes) / (ms_step * 1e-3) / 1e9,
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "unpool_vec_kernel (K7 nearest un-pool)", "bound": "hbm", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": unpool_bytes,
+                         "kernel_ms": unpool_ms, "frac_of_nominal_8TBs": achieved / 8000.0},
+            "e2e": {"value": B * world * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": fm_host.numel() * fm_host.element_size(),
+                    "d2h_bytes_per_step": host_f.numel() * 4 + host_i.numel() * 4, "steps": e2e_steps,
+                    "api": "GraphBlock.forward(feature_map=pinned host tensor -> device) + D2H of loss/region/labels"},
+            "clocks": sampler.summary(note),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cpu_block_images(args.workload, 1)
+            n_img = args.cpu_sample_images or (8 if H >= 512 else 32)
+            secs = cpu_block_images(args.workload, n_img)
+            line["cpu_baseline"] = {"value": n_img / secs, "unit": "images/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "sample": f"{n_img} images of the workload, oracle/restate.py fp32, "
+                                                              f"{secs:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

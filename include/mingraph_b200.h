@@ -1,0 +1,138 @@
+/*
+ * libmingraph_b200 — C ABI of the B200 (sm_100a) graph block of MinGraph-UNet.
+ *
+ * The reference (agent-charon/MinGraph-UNet) has no FFI: its boundary is the
+ * Python nn.Module contract of the classes cited below (paths relative to the
+ * reference root).  This header is what a binding of those classes needs: plain
+ * device pointers, explicit sizes, a dtype enum and the caller's cudaStream_t.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - nothing here allocates, synchronises or touches the default stream:
+ *     work is enqueued on `stream` (a cudaStream_t passed as void*), so calls are
+ *     CUDA-graph capturable;
+ *   - return value 0 = enqueued; <0 = error (MG_ERR_*), text via mg_last_error();
+ *   - node features are row-major (N, D); graphs are CSR over int32:
+ *       "in"  CSR: rowptr[j]..rowptr[j+1] lists the SOURCES of edges into j,
+ *       "out" CSR: rowptr[i]..rowptr[i+1] lists the TARGETS of edges out of i,
+ *     both in ascending COO edge id (the order torch's CPU scatter_add_ visits
+ *     them), so segment sums round like the reference's;
+ *   - batched calls are block-diagonal: image b owns nodes [b*N, (b+1)*N).
+ */
+#ifndef MINGRAPH_B200_H_
+#define MINGRAPH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MG_API __attribute__((visibility("default")))
+#else
+#define MG_API
+#endif
+
+#define MG_VERSION 100            /* 0.1.0 */
+
+#define MG_OK 0
+#define MG_ERR_INVALID (-1)       /* bad argument / unsupported shape */
+#define MG_ERR_CUDA (-2)          /* launch failed (sticky CUDA error text in mg_last_error) */
+#define MG_ERR_UNSUPPORTED (-3)
+
+#define MG_F32 0
+#define MG_BF16 1
+
+typedef void* mg_stream_t;        /* cudaStream_t */
+
+MG_API int mg_version(void);
+MG_API const char* mg_last_error(void);
+/* Number of kernels this library has launched from the calling process (for bench.py's
+ * gpu_launches claim). */
+MG_API int64_t mg_launch_count(void);
+
+/* ---- graph construction --------------------------------------------------------------
+ * PatchGraphConstructor.construct_patch_graph — preprocessing/graph_construction/
+ * patch_graph_construction.py:49-102.  4-connected patch grid, both directions, the
+ * reference's emission order (per node, row-major: right pair then down pair). */
+MG_API int64_t mg_grid_num_edges(int Hp, int Wp);      /* 2*(Hp*(Wp-1)+Wp*(Hp-1)) */
+/* edge_index (2, B*E) int64: row 0 sources, row 1 targets; image b's ids are offset by
+ * b*Hp*Wp when offset_nodes != 0 (B=1 reproduces the reference tensor bit for bit). */
+MG_API int mg_grid_edge_index(int Hp, int Wp, int B, int offset_nodes, int64_t* edge_index, mg_stream_t stream);
+/* Closed-form CSR of the same graph (block-diagonal over B images).  The grid is
+ * symmetric, so the arrays serve as both the "in" and the "out" CSR; neighbour order is
+ * up, left, right, down = ascending COO edge id in both views.  eid_in/eid_out (nullable)
+ * receive the per-image COO edge id of each slot in the in/out view. */
+MG_API int mg_grid_csr(int Hp, int Wp, int B, int32_t* rowptr, int32_t* col, int32_t* eid_in, int32_t* eid_out,
+                mg_stream_t stream);
+/* Complete digraph on K regions per image — scripts/train_end_to_end.py:376-380
+ * (triu pairs (s,t) then the reversed pairs). */
+MG_API int mg_complete_edge_index(int K, int B, int offset_nodes, int64_t* edge_index, mg_stream_t stream);
+MG_API int mg_complete_csr(int K, int B, int32_t* rowptr, int32_t* col, mg_stream_t stream);
+/* Arbitrary caller-supplied edge_index (2,E) int64 -> stable CSR by target (by_target=1)
+ * or by source (0).  work: at least mg_csr_work_bytes(N,E) bytes.  status (1 int, nullable):
+ * set non-zero if an index is outside [0,N) (the reference raises IndexError). */
+MG_API int64_t mg_csr_work_bytes(int N, int64_t E);
+MG_API int mg_csr_from_coo(const int64_t* edge_index, int64_t E, int N, int by_target, int32_t* rowptr, int32_t* col,
+                    int32_t* eid, void* work, int32_t* status, mg_stream_t stream);
+
+/* ---- pooling ---------------------------------------------------------------------------
+ * Patch mean pooling (B,C,Hf,Wf) -> (B, Hp*Wp, C): the documented intent of
+ * PatchGraphConstructor.get_patch_features_from_unet_encoder (patch_graph_construction.py:
+ * 104-136, raises NotImplementedError) expressed as image_to_patches(x).mean((2,3))
+ * (:27-47; scripts/graph_refinement.py:78,98,103).  Right/bottom zero padding counts in the
+ * mean: the divisor is always ph*pw. */
+MG_API int mg_pool_patches(const void* x, int x_dtype, int B, int C, int Hf, int Wf, int ph, int pw, void* out,
+                    int out_dtype, mg_stream_t stream);
+/* Region mean pool — train_end_to_end.py:368-373: out[b,k,:] = mean(h[b, labels[b]==k, :]),
+ * zero for empty regions.  h (B,N,D) f32, labels (B,N) int32, out (B,K,D) f32,
+ * counts (B,K) int32 (nullable). */
+MG_API int mg_segment_mean(const float* h, const int32_t* labels, int B, int N, int D, int K, float* out,
+                    int32_t* counts, mg_stream_t stream);
+
+/* ---- graph attention ---------------------------------------------------------------------
+ * MultiHeadGATLayer.forward (eval) — model/gat/graph_attention.py:40-118,150-160.
+ *   x (N,in) f32|bf16; W (heads,F,in) f32 = heads.{h}.W.weight; a (heads,2F) f32 = heads.{h}.a.weight
+ *   out (N, concat ? heads*F : F) f32|bf16
+ *   nodes_per_graph > 0: the batch holds N/nodes_per_graph independent graphs and the softmax
+ *   shift (torch.max(e), :86) is taken per graph; 0 = one graph.
+ *   work: mg_gat_work_bytes() bytes of scratch (scores, per-graph max, spill of the
+ *   aggregated features when the weights do not fit in shared memory).
+ *   save_den (N,heads) f32 and save_z (N,heads,in) f32 are optional (nullable) outputs kept
+ *   for mg_gat_backward.
+ * Empty graphs (E == 0) are rejected with MG_ERR_INVALID like the reference's RuntimeError. */
+MG_API int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int num_graphs);
+MG_API int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, int64_t E,
+                   const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
+                   int nodes_per_graph, void* out, int out_dtype, void* work, float* save_den, float* save_z,
+                   mg_stream_t stream);
+
+/* Row softmax + argmax of the predictor logits — mincut_refinement.py:193 and
+ * train_end_to_end.py:356.  logits (N,K) f32 -> S (N,K) f32, labels (N) int32 (first max). */
+MG_API int mg_softmax_argmax(const float* logits, int N, int K, float* S, int32_t* labels, mg_stream_t stream);
+
+/* ---- normalized cut ------------------------------------------------------------------------
+ * MinCutRefinement.compute_edge_weights_for_ncut — mincut_refinement.py:30-52: w (E) f32 in
+ * COO order for an int64 edge_index. */
+MG_API int mg_ncut_edge_weights(const float* h, int N, int D, const int64_t* edge_index, int64_t E, float* w,
+                         mg_stream_t stream);
+/* MinCutRefinement.normalized_cut_loss — :55-160, per graph.  Uses the OUT CSR (degree is
+ * summed by source, :96).  loss (G) f32; work: mg_ncut_work_bytes(). */
+MG_API int64_t mg_ncut_work_bytes(int N, int K, int num_graphs);
+MG_API int mg_ncut_loss(const float* h, const float* S, const int32_t* rowptr_out, const int32_t* col_out, int N, int D,
+                 int K, int nodes_per_graph, float* loss, void* work, mg_stream_t stream);
+
+/* ---- un-pool ---------------------------------------------------------------------------------
+ * train_end_to_end.py:403-421: f_patch = table[labels]; (N,D)->(D,Hp,Wp); nearest up-sampling to
+ * (D,H,W) with torch's index rule.  table (B,K,D) f32; labels (B,Hp*Wp) int32 or NULL (then
+ * K == Hp*Wp and the table is the per-patch feature matrix).  out[b] starts at
+ * out + b*out_batch_stride elements and holds (D,H,W) contiguous, so the result can be written
+ * straight into a channel slice of a fusion buffer. */
+MG_API int mg_unpool_nearest(const float* table, const int32_t* labels, int B, int K, int D, int Hp, int Wp, int H, int W,
+                      void* out, int out_dtype, int64_t out_batch_stride, mg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINGRAPH_B200_H_ */

@@ -1,0 +1,125 @@
+"""Batched graph block: the per-image loop of scripts/train_end_to_end.py:300-425 for all ``B``
+images at once (block-diagonal graphs, O(10) kernel launches per batch, no host syncs).
+
+Stage order (reference lines in parentheses):
+  node features  — patch-mean pool of a feature map (patch_graph_construction.py:104-109 intent;
+                   graph_refinement.py:78,98,103 idiom) or given ``(B,N,in)`` (:326 placeholder)
+  patch graph    — 4-connected grid (:329)
+  patch GAT      — ``patch_gat_model`` (:332)
+  min-cut        — predictor GAT -> softmax -> N-cut loss (:348; mincut_refinement.py:192-196)
+  hard labels    — argmax (:356)
+  region pool    — per-label mean, zeros for empty regions (:368-373)
+  region GAT     — complete digraph over K regions (:376-389)
+  un-pool        — gather by label, nearest up-sampling to (D,H,W) (:403-421), stacked (B,D,H,W) (:432)
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .autograd import gat_layer_apply
+from .graph import Graph
+from .modules import GATNetwork, MinCutRefinement, PatchGraphConstructor, PatchSegmentPredictor, _layer_forward
+
+
+class GraphBlockOutput(NamedTuple):
+    f_g: Optional[torch.Tensor]          # (B, D, H, W) dense graph features (train_end_to_end.py:432)
+    l_partition: torch.Tensor            # (B,) per-image N-cut loss (the reference averages them, :428)
+    soft_assignments: torch.Tensor       # (B, N, K)
+    hard_labels: torch.Tensor            # (B, N) int32
+    patch_features: torch.Tensor         # (B, N, D) patch-GAT output h
+    region_features: torch.Tensor        # (B, K, D) region-GAT output
+    grid: Tuple[int, int]                # (nph, npw)
+
+
+class GraphBlock(nn.Module):
+    """Sub-module names follow the reference's variables (train_end_to_end.py:144-178) so their
+    state_dicts map one to one: ``patch_gat_model``, ``segment_predictor``, ``mincut_module``,
+    ``region_gat_model``."""
+
+    def __init__(self, node_feature_dim: int = 20, gat_hidden_dim: int = 128, gat_output_dim: int = 64,
+                 num_heads: int = 4, num_segments: int = 2, patch_size: int = 16, dropout_rate: float = 0.1,
+                 alpha: float = 0.2):
+        super().__init__()
+        self.patch_size = patch_size
+        self.num_segments = num_segments
+        self.gat_output_dim = gat_output_dim
+        self.patch_graph_constructor = PatchGraphConstructor(patch_size)
+        self.patch_gat_model = GATNetwork(node_feature_dim, gat_hidden_dim, gat_output_dim, num_heads, 1,
+                                          dropout_rate, alpha)
+        self.segment_predictor = PatchSegmentPredictor(gat_output_dim, num_segments, hidden_dim=gat_output_dim // 2,
+                                                       use_gnn=True, num_gnn_layers=1, num_heads=max(1, num_heads // 2))
+        self.mincut_module = MinCutRefinement()
+        self.region_gat_model = GATNetwork(gat_output_dim, gat_hidden_dim, gat_output_dim, num_heads, 1,
+                                           dropout_rate, alpha)
+
+    def forward(self, node_features: Optional[torch.Tensor] = None, image_size: Optional[Tuple[int, int]] = None,
+                feature_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                out_dtype: Optional[torch.dtype] = None, want_dense: bool = True) -> GraphBlockOutput:
+        """Either ``node_features (B,N,in)`` + ``image_size (H,W)`` or a per-pixel ``feature_map
+        (B,in,H,W)`` (patch-mean pooled to node features).  ``out`` may be a channel slice of a fusion
+        buffer ``(B,Ctot,H,W)[:, c0:c0+D]``; the dense map is written there directly."""
+        if (node_features is None) == (feature_map is None):
+            raise ValueError("pass exactly one of node_features / feature_map")
+        if feature_map is not None:
+            if image_size is None:
+                image_size = tuple(feature_map.shape[-2:])
+            fh, fw = feature_map.shape[-2:]
+            H, W = image_size
+            nph, npw = self.patch_graph_constructor.grid_dims(H, W)
+            # pooling window in feature-map pixels (patch_size / stride of the feature map)
+            if H % fh or W % fw or self.patch_size % (H // fh) or self.patch_size % (W // fw):
+                raise ValueError("feature_map resolution must divide the image size and the patch size")
+            ph, pw = self.patch_size // (H // fh), self.patch_size // (W // fw)
+            node_features = ops.pool_patches(feature_map, ph, pw)
+            if node_features.shape[1] != nph * npw:
+                raise ValueError("pooled patch count does not match the patch grid")
+        if image_size is None:
+            raise ValueError("image_size=(H, W) is required with node_features")
+        H, W = image_size
+        if node_features.dim() != 3:
+            raise ValueError("node_features must be (B, N, in)")
+        B, N, _ = node_features.shape
+        nph, npw = self.patch_graph_constructor.grid_dims(H, W)
+        if N != nph * npw:                                            # patch_graph_construction.py:71-74
+            raise ValueError(f"Number of patch features ({N}) does not match expected number of patches "
+                             f"({nph * npw}) for image {H}x{W} and patch size {self.patch_size}.")
+        dev = node_features.device
+        K, D = self.num_segments, self.gat_output_dim
+        g = Graph.grid(nph, npw, dev, B)
+        if g.E == 0:
+            raise RuntimeError("max(): Expected reduction dim to be specified for input.numel() == 0 "
+                               "(a 1x1 patch grid has no edges)")
+        x = node_features.reshape(B * N, -1)
+        patch_layer = self.patch_gat_model.gat_layers[0]
+        h = _batched_layer(patch_layer, x, g, torch.float32)                       # :332
+        pred_layer = self.segment_predictor.gnn_predictor.gat_layers[0]
+        logits = _batched_layer(pred_layer, h, g, torch.float32)                   # mincut_refinement.py:192
+        S, labels = ops.softmax_argmax(logits)                                     # :193, train_end_to_end.py:356
+        loss = ops.ncut_loss(h, S, g.rowptr_out, g.col_out, g.nodes_per_graph if B > 1 else 0)   # :196
+        R = ops.segment_mean(h.view(B, N, D), labels.view(B, N), K)                # :368-373
+        if K > 1:                                                                  # :383-389
+            rg = Graph.complete(K, dev, B)
+            G = _batched_layer(self.region_gat_model.gat_layers[0], R.view(B * K, D), rg, torch.float32).view(B, K, D)
+        else:
+            G = R
+        f_g = None
+        if want_dense:                                                             # :403-421
+            f_g = ops.unpool_nearest(G, labels.view(B, N), nph, npw, H, W, out=out,
+                                     out_dtype=out_dtype if out_dtype is not None else node_features.dtype)
+        return GraphBlockOutput(f_g, loss, S.view(B, N, K), labels.view(B, N), h.view(B, N, D), G, (nph, npw))
+
+
+def _batched_layer(layer, x: torch.Tensor, g: Graph, out_dtype: torch.dtype) -> torch.Tensor:
+    """Eval-mode multi-head layer on a block-diagonal batch (dropout is identity in eval; the
+    training path goes through ``modules._layer_forward``)."""
+    if layer.training and layer.dropout_rate > 0:
+        return layer(x, g)
+    heads = list(layer.heads)
+    W = torch.stack([hd.W.weight for hd in heads], 0).detach()
+    a = torch.stack([hd.a.weight.view(-1) for hd in heads], 0).detach()
+    return ops.gat_forward(x, g.rowptr_in, g.col_in, W, a, concat=layer.concat, slope=layer.alpha,
+                           nodes_per_graph=g.nodes_per_graph, out_dtype=out_dtype)

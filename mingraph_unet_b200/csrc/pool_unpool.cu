@@ -1,0 +1,341 @@
+// K1 patch mean pooling, region mean pooling (a11) and K7 nearest un-pool (a13).
+// All three are HBM-streaming kernels: K1 reads the feature map once with 16-byte loads,
+// K7 writes the dense (B,D,H,W) map once with 16-byte streaming stores.
+#include "common.cuh"
+
+namespace mg {
+
+// ------------------------------------------------------------------------------------------
+// K1: (B,C,Hf,Wf) -> (B, Hp*Wp, C), mean over ph x pw windows, zero padded right/bottom
+// oracle: image_to_patches(x).mean((2,3))  (patch_graph_construction.py:27-47)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ float sum(const float* p) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return (v.x + v.y) + (v.z + v.w);
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ float sum(const __nv_bfloat16* p) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    float s = 0.f;
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += __uint_as_float(w[i] << 16) + __uint_as_float(w[i] & 0xffff0000u);
+    return s;
+  }
+};
+
+constexpr int kPoolCC = 32;   // channels per block
+
+// fast path: pw % VEC == 0, Wf % VEC == 0, (pw/VEC) power of two <= 32
+template <typename TX, typename TO>
+__global__ void __launch_bounds__(256) pool_patches_vec_kernel(const TX* __restrict__ x, int C, int Hf, int Wf, int ph,
+                                                               int pw, int Hp, int Wp, TO* __restrict__ out) {
+  constexpr int VEC = Vec16<TX>::N;
+  extern __shared__ float tile[];   // [Wp][kPoolCC+1]
+  const int b = blockIdx.z, py = blockIdx.y, c0 = blockIdx.x * kPoolCC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpp = pw / VEC;                               // lanes per patch
+  const int y0 = py * ph, y1 = min(Hf, y0 + ph);
+  const float inv = 1.f / (float)(ph * pw);
+  const int nvec = Wf / VEC;
+  for (int cc = warp; cc < kPoolCC; cc += 8) {
+    const int c = c0 + cc;
+    if (c >= C) break;
+    const TX* plane = x + ((size_t)b * C + c) * Hf * Wf;
+    for (int xv0 = 0; xv0 < nvec; xv0 += 32) {
+      const int xv = xv0 + lane;
+      float acc = 0.f;
+      if (xv < nvec) {
+        const TX* p = plane + (size_t)y0 * Wf + (size_t)xv * VEC;
+        int y = y0;
+        for (; y + 3 < y1; y += 4) {                      // 4 independent 16-byte loads in flight
+          const float s0 = Vec16<TX>::sum(p), s1 = Vec16<TX>::sum(p + Wf), s2 = Vec16<TX>::sum(p + 2 * (size_t)Wf),
+                      s3 = Vec16<TX>::sum(p + 3 * (size_t)Wf);
+          acc += (s0 + s1) + (s2 + s3);
+          p += 4 * (size_t)Wf;
+        }
+        for (; y < y1; ++y) { acc += Vec16<TX>::sum(p); p += Wf; }
+      }
+      for (int o = 1; o < lpp; o <<= 1) acc += __shfl_xor_sync(kFull, acc, o);
+      if (xv < nvec && (lane & (lpp - 1)) == 0) tile[(xv / lpp) * (kPoolCC + 1) + cc] = acc * inv;
+    }
+  }
+  __syncthreads();
+  const int ncc = min(kPoolCC, C - c0);
+  for (int idx = threadIdx.x; idx < Wp * kPoolCC; idx += blockDim.x) {
+    const int px = idx / kPoolCC, cc = idx - px * kPoolCC;
+    if (cc < ncc) out[((size_t)b * Hp * Wp + (size_t)py * Wp + px) * C + c0 + cc] = from_f32<TO>(tile[px * (kPoolCC + 1) + cc]);
+  }
+}
+
+// generic path: any window; one thread per output element (px fastest so window reads share lines)
+template <typename TX, typename TO>
+__global__ void pool_patches_generic_kernel(const TX* __restrict__ x, int B, int C, int Hf, int Wf, int ph, int pw,
+                                            int Hp, int Wp, TO* __restrict__ out) {
+  const int64_t total = (int64_t)B * C * Hp * Wp;
+  const float inv = 1.f / (float)(ph * pw);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int px = (int)(t % Wp);
+    const int py = (int)((t / Wp) % Hp);
+    const int c = (int)((t / ((int64_t)Wp * Hp)) % C);
+    const int b = (int)(t / ((int64_t)Wp * Hp * C));
+    const TX* plane = x + ((size_t)b * C + c) * Hf * Wf;
+    const int y1 = min(Hf, (py + 1) * ph), x1 = min(Wf, (px + 1) * pw);
+    float acc = 0.f;
+    for (int y = py * ph; y < y1; ++y)
+      for (int xx = px * pw; xx < x1; ++xx) acc += to_f32<TX>(plane[(size_t)y * Wf + xx]);
+    out[((size_t)b * Hp * Wp + (size_t)py * Wp + px) * C + c] = from_f32<TO>(acc * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a11: region mean pool.  One block per image; warp-private shared accumulators, fixed
+// reduction order (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ h, const int32_t* __restrict__ labels,
+                                                           int N, int D, int K, float* __restrict__ out,
+                                                           int32_t* __restrict__ counts) {
+  extern __shared__ float acc[];                       // [8][K][D] then int cnt[8][K]
+  int* cnt = reinterpret_cast<int*>(acc + (size_t)8 * K * D);
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 8 * K * D; i += blockDim.x) acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  float* mine = acc + (size_t)warp * K * D;
+  for (int n = warp; n < N; n += 8) {
+    const int k = __ldg(labels + (size_t)b * N + n);
+    if (k < 0 || k >= K) continue;
+    const float* row = h + ((size_t)b * N + n) * D;
+    for (int d = lane; d < D; d += 32) mine[k * D + d] += __ldg(row + d);
+    if (lane == 0) cnt[warp * K + k] += 1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+    const int k = i / D;
+    float s = 0.f;
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s += acc[(size_t)w * K * D + i]; c += cnt[w * K + k]; }
+    out[(size_t)b * K * D + i] = c > 0 ? s / (float)c : 0.f;       // train_end_to_end.py:372-373
+    if (counts && (i % D) == 0) counts[b * K + k] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: nearest un-pool.  out[b,d,y,x] = table[b, label[b, iy(y)*Wp + ix(x)], d]
+// index rule = torch CPU upsample_nearest ('nearest'): identity, >>1, else
+// min(floor(dst * float(in/out)), in-1) in fp32.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size, float scale) {
+  if (out_size == in_size) return dst;
+  if (out_size == 2 * in_size) return dst >> 1;
+  const int s = (int)floorf(__fmul_rn((float)dst, scale));
+  return min(s, in_size - 1);
+}
+
+template <typename TO>
+struct Pack;
+template <>
+struct Pack<float> {
+  static constexpr int VEC = 4;
+  static __device__ __forceinline__ uint4 make(const float* v) {
+    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+  }
+};
+template <>
+struct Pack<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  static __device__ __forceinline__ uint4 make(const float* v) {
+    uint4 r;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]),
+                   c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    r.x = *reinterpret_cast<unsigned*>(&a); r.y = *reinterpret_cast<unsigned*>(&b);
+    r.z = *reinterpret_cast<unsigned*>(&c); r.w = *reinterpret_cast<unsigned*>(&d);
+    return r;
+  }
+};
+
+constexpr int kUnTX = 64, kUnTY = 4, kUnRY = 16, kUnDC = 8;
+
+// vector path (W % VEC == 0, 16-byte aligned rows): grid (xblocks, yblocks, B * dchunks)
+template <typename TO>
+__global__ void __launch_bounds__(kUnTX* kUnTY) unpool_vec_kernel(const float* __restrict__ table,
+                                                                 const int32_t* __restrict__ labels, int K, int D,
+                                                                 int Hp, int Wp, int H, int W, TO* __restrict__ out,
+                                                                 int64_t out_batch_stride, float sy, float sx) {
+  constexpr int VEC = Pack<TO>::VEC;
+  const int dchunks = ceil_div(D, kUnDC);
+  const int b = blockIdx.z / dchunks, d0 = (blockIdx.z - b * dchunks) * kUnDC;
+  const int nd = min(kUnDC, D - d0);
+  const int xv = blockIdx.x * kUnTX + threadIdx.x;
+  if (xv * VEC >= W) return;
+  int px[VEC];
+  bool same = true;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    px[v] = nearest_src(xv * VEC + v, Wp, W, sx);
+    same = same && (px[v] == px[0]);
+  }
+  const int yend = min(H, (int)(blockIdx.y + 1) * kUnRY);
+  const float* tb = table + (size_t)b * K * D;
+  const int32_t* lb = labels ? labels + (size_t)b * Hp * Wp : nullptr;
+  TO* ob = out + (size_t)b * out_batch_stride;
+  int prev_py = -1;
+  int lab[VEC];
+  for (int y = blockIdx.y * kUnRY + threadIdx.y; y < yend; y += kUnTY) {
+    const int py = nearest_src(y, Hp, H, sy);
+    if (py != prev_py) {
+      prev_py = py;
+      if (same) {
+        const int n = py * Wp + px[0];
+        const int l = lb ? __ldg(lb + n) : n;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) lab[v] = l;
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int n = py * Wp + px[v];
+          lab[v] = lb ? __ldg(lb + n) : n;
+        }
+      }
+    }
+    TO* orow = ob + ((size_t)d0 * H + y) * W + (size_t)xv * VEC;
+    if (same) {
+      const float* tp = tb + (size_t)lab[0] * D + d0;
+#pragma unroll
+      for (int d = 0; d < kUnDC; ++d) {
+        if (d < nd) {
+          const float t = __ldg(tp + d);
+          float vals[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) vals[v] = t;
+          st_cs_v4(orow + (size_t)d * H * W, Pack<TO>::make(vals));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < kUnDC; ++d) {
+        if (d < nd) {
+          float vals[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) vals[v] = __ldg(tb + (size_t)lab[v] * D + d0 + d);
+          st_cs_v4(orow + (size_t)d * H * W, Pack<TO>::make(vals));
+        }
+      }
+    }
+  }
+}
+
+// scalar path: any W / alignment
+template <typename TO>
+__global__ void unpool_scalar_kernel(const float* __restrict__ table, const int32_t* __restrict__ labels, int B, int K,
+                                     int D, int Hp, int Wp, int H, int W, TO* __restrict__ out,
+                                     int64_t out_batch_stride, float sy, float sx) {
+  const int64_t total = (int64_t)B * D * H * W;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(t % W);
+    const int y = (int)((t / W) % H);
+    const int d = (int)((t / ((int64_t)W * H)) % D);
+    const int b = (int)(t / ((int64_t)W * H * D));
+    const int n = nearest_src(y, Hp, H, sy) * Wp + nearest_src(xx, Wp, W, sx);
+    const int l = labels ? __ldg(labels + (size_t)b * Hp * Wp + n) : n;
+    out[(size_t)b * out_batch_stride + ((size_t)d * H + y) * W + xx] = from_f32<TO>(__ldg(table + ((size_t)b * K + l) * D + d));
+  }
+}
+
+template <typename TX, typename TO>
+static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int pw, void* out, cudaStream_t st) {
+  constexpr int VEC = Vec16<TX>::N;
+  const int Hp = ceil_div(Hf, ph), Wp = ceil_div(Wf, pw);
+  const int lpp = pw / VEC;
+  const bool fast = (pw % VEC == 0) && (Wf % VEC == 0) && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 &&
+                    ((uintptr_t)x % 16 == 0) && (size_t)Wp * (kPoolCC + 1) * 4 <= 160 * 1024;
+  if (fast) {
+    const size_t smem = (size_t)Wp * (kPoolCC + 1) * 4;
+    auto k = pool_patches_vec_kernel<TX, TO>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    dim3 grid(ceil_div(C, kPoolCC), Hp, B);
+    k<<<grid, 256, smem, st>>>(reinterpret_cast<const TX*>(x), C, Hf, Wf, ph, pw, Hp, Wp, reinterpret_cast<TO*>(out));
+    return check_launch("pool_patches_vec_kernel");
+  }
+  const int64_t total = (int64_t)B * C * Hp * Wp;
+  const int grid = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
+  pool_patches_generic_kernel<TX, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TX*>(x), B, C, Hf, Wf, ph, pw, Hp, Wp,
+                                                           reinterpret_cast<TO*>(out));
+  return check_launch("pool_patches_generic_kernel");
+}
+
+template <typename TO>
+static int launch_unpool(const float* table, const int32_t* labels, int B, int K, int D, int Hp, int Wp, int H, int W,
+                         void* out, int64_t stride, cudaStream_t st) {
+  constexpr int VEC = Pack<TO>::VEC;
+  // torch: scale = float(in) / float(out)
+  const float sy = (float)Hp / (float)H, sx = (float)Wp / (float)W;
+  const bool vec_ok = (W % VEC == 0) && ((uintptr_t)out % 16 == 0) && ((stride * (int64_t)sizeof(TO)) % 16 == 0);
+  if (vec_ok) {
+    dim3 block(kUnTX, kUnTY);
+    dim3 grid(ceil_div(W / VEC, kUnTX), ceil_div(H, kUnRY), B * ceil_div(D, kUnDC));
+    MG_REQUIRE(grid.z <= 65535 && grid.y <= 65535, MG_ERR_INVALID, "mg_unpool_nearest: grid too large");
+    unpool_vec_kernel<TO><<<grid, block, 0, st>>>(table, labels, K, D, Hp, Wp, H, W, reinterpret_cast<TO*>(out), stride, sy, sx);
+    return check_launch("unpool_vec_kernel");
+  }
+  const int64_t total = (int64_t)B * D * H * W;
+  const int grid = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 32);
+  unpool_scalar_kernel<TO><<<grid, 256, 0, st>>>(table, labels, B, K, D, Hp, Wp, H, W, reinterpret_cast<TO*>(out), stride, sy, sx);
+  return check_launch("unpool_scalar_kernel");
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" {
+
+int mg_pool_patches(const void* x, int x_dtype, int B, int C, int Hf, int Wf, int ph, int pw, void* out, int out_dtype,
+                    mg_stream_t stream) {
+  MG_REQUIRE(x && out && B > 0 && C > 0 && Hf > 0 && Wf > 0 && ph > 0 && pw > 0, MG_ERR_INVALID,
+             "mg_pool_patches: bad arguments");
+  MG_REQUIRE(B <= 65535 && ceil_div(Hf, ph) <= 65535, MG_ERR_INVALID, "mg_pool_patches: grid too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == MG_F32 && out_dtype == MG_F32) return launch_pool<float, float>(x, B, C, Hf, Wf, ph, pw, out, st);
+  if (x_dtype == MG_BF16 && out_dtype == MG_BF16)
+    return launch_pool<__nv_bfloat16, __nv_bfloat16>(x, B, C, Hf, Wf, ph, pw, out, st);
+  if (x_dtype == MG_BF16 && out_dtype == MG_F32) return launch_pool<__nv_bfloat16, float>(x, B, C, Hf, Wf, ph, pw, out, st);
+  if (x_dtype == MG_F32 && out_dtype == MG_BF16) return launch_pool<float, __nv_bfloat16>(x, B, C, Hf, Wf, ph, pw, out, st);
+  set_error("mg_pool_patches: unsupported dtypes %d -> %d", x_dtype, out_dtype);
+  return MG_ERR_INVALID;
+}
+
+int mg_segment_mean(const float* h, const int32_t* labels, int B, int N, int D, int K, float* out, int32_t* counts,
+                    mg_stream_t stream) {
+  MG_REQUIRE(h && labels && out && B > 0 && N > 0 && D > 0 && K > 0, MG_ERR_INVALID, "mg_segment_mean: bad arguments");
+  const size_t smem = (size_t)8 * K * D * 4 + (size_t)8 * K * 4;
+  MG_REQUIRE(smem <= 200 * 1024, MG_ERR_UNSUPPORTED, "mg_segment_mean: K*D=%d too large for shared accumulators", K * D);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(segment_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  segment_mean_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(h, labels, N, D, K, out, counts);
+  return check_launch("segment_mean_kernel");
+}
+
+int mg_unpool_nearest(const float* table, const int32_t* labels, int B, int K, int D, int Hp, int Wp, int H, int W,
+                      void* out, int out_dtype, int64_t out_batch_stride, mg_stream_t stream) {
+  MG_REQUIRE(table && out && B > 0 && K > 0 && D > 0 && Hp > 0 && Wp > 0 && H > 0 && W > 0, MG_ERR_INVALID,
+             "mg_unpool_nearest: bad arguments");
+  MG_REQUIRE(labels || K == Hp * Wp, MG_ERR_INVALID, "mg_unpool_nearest: labels==NULL requires K == Hp*Wp");
+  MG_REQUIRE(out_batch_stride >= (int64_t)D * H * W, MG_ERR_INVALID, "mg_unpool_nearest: batch stride smaller than D*H*W");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == MG_F32) return launch_unpool<float>(table, labels, B, K, D, Hp, Wp, H, W, out, out_batch_stride, st);
+  if (out_dtype == MG_BF16)
+    return launch_unpool<__nv_bfloat16>(table, labels, B, K, D, Hp, Wp, H, W, out, out_batch_stride, st);
+  set_error("mg_unpool_nearest: unsupported out dtype %d", out_dtype);
+  return MG_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+"""Drop-in ``nn.Module`` mirror of the reference's graph-block classes, executing on the sm_100a
+kernels of ``libmingraph_b200.so``.
+
+Constructor arguments, ``forward`` signatures, tensor layouts, parameter names / shapes
+(``state_dict`` keys) and error behaviour follow the reference (paths relative to the
+reference root):
+
+* ``GraphAttentionLayer``   — model/gat/graph_attention.py:5-118
+* ``MultiHeadGATLayer``     — model/gat/graph_attention.py:120-160
+* ``GATNetwork``            — model/gat/graph_attention.py:162-192
+* ``PatchGraphConstructor`` — preprocessing/graph_construction/patch_graph_construction.py:5-136
+* ``MinCutRefinement``      — model/graph_partition/mincut_refinement.py:5-205
+* ``PatchSegmentPredictor`` — scripts/train_end_to_end.py:40-70
+
+so a reference checkpoint loads with ``load_state_dict`` unchanged and the classes can replace
+the reference's at its two call sites (scripts/train_end_to_end.py:318-421,
+scripts/graph_refinement.py:70-152).  ``GraphBlock`` (block.py) is the batched form of that
+per-image loop.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .autograd import gat_layer_apply, ncut_loss_apply, softmax_rows
+from .graph import Graph, register
+
+
+def _pad_in_dim(x: torch.Tensor, W: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Kernels take in<=32, even in<=64 or in%4==0 (<=512).  Other widths are zero padded
+    (exact: the padded columns contribute 0 to every dot product)."""
+    in_dim = x.shape[1]
+    if in_dim <= 32 or (in_dim <= 64 and in_dim % 2 == 0) or (in_dim % 4 == 0 and in_dim <= 512):
+        return x, W
+    if in_dim > 512:
+        raise RuntimeError(f"node feature width {in_dim} > 512 is not supported by the GAT kernels")
+    pad = (-in_dim) % 4
+    return F.pad(x, (0, pad)), F.pad(W, (0, pad))
+
+
+class GraphAttentionLayer(nn.Module):
+    """One attention head (graph_attention.py:5-118).  Parameters: ``W.weight (F,in)``,
+    ``a.weight (1,2F)``, xavier-uniform with gain 1.414 (:36-37)."""
+
+    def __init__(self, in_features, out_features, dropout_rate, alpha, concat=True):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.dropout_rate = dropout_rate
+        self.alpha = alpha
+        self.concat = concat
+        self.W = nn.Linear(in_features, out_features, bias=False)
+        self.a = nn.Linear(2 * out_features, 1, bias=False)
+        self.leakyrelu = nn.LeakyReLU(self.alpha)
+        self.dropout = nn.Dropout(self.dropout_rate)
+        nn.init.xavier_uniform_(self.W.weight, gain=1.414)
+        nn.init.xavier_uniform_(self.a.weight, gain=1.414)
+
+    def forward(self, node_features, edge_index):
+        return _layer_forward([self], node_features, edge_index, concat=True, alpha=self.alpha,
+                              att_dropout=self.dropout_rate if self.training else 0.0)
+
+
+def _layer_forward(heads: List[GraphAttentionLayer], x: torch.Tensor, edge_index, concat: bool, alpha: float,
+                   att_dropout: float) -> torch.Tensor:
+    if isinstance(edge_index, Graph):
+        g = edge_index
+    else:
+        g = Graph.from_edge_index(edge_index, x.shape[0])
+    if g.E == 0:
+        # graph_attention.py:86 — torch.max over an empty edge tensor raises RuntimeError
+        raise RuntimeError("max(): Expected reduction dim to be specified for input.numel() == 0 "
+                           "(edge_index is empty)")
+    if x.dim() != 2 or x.shape[1] != heads[0].in_features:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x.shape[0]}x{x.shape[-1]} and "
+                           f"{heads[0].in_features}x{heads[0].out_features})")
+    if len(heads) == 1:
+        W = heads[0].W.weight.unsqueeze(0)
+        a = heads[0].a.weight.view(1, -1)
+    else:
+        W = torch.stack([h.W.weight for h in heads], 0)
+        a = torch.stack([h.a.weight.view(-1) for h in heads], 0)
+    xp, Wp = _pad_in_dim(x, W)
+    return gat_layer_apply(xp, g, Wp, a, concat, alpha, att_dropout)
+
+
+class MultiHeadGATLayer(nn.Module):
+    """``num_heads`` independent heads, concatenated or averaged, then dropout
+    (graph_attention.py:120-160).  All heads run in ONE fused kernel sequence."""
+
+    def __init__(self, in_features, out_features, num_heads, dropout_rate, alpha, concat=True):
+        super().__init__()
+        self.num_heads = num_heads
+        self.concat = concat
+        if concat:
+            assert out_features % num_heads == 0, "out_features must be divisible by num_heads if concatenating"
+            self.head_out_features = out_features // num_heads
+        else:
+            self.head_out_features = out_features
+        self.heads = nn.ModuleList()
+        for _ in range(num_heads):
+            self.heads.append(GraphAttentionLayer(in_features, self.head_out_features, dropout_rate, alpha))
+        self.dropout = nn.Dropout(dropout_rate)
+        self.alpha = alpha
+        self.dropout_rate = dropout_rate
+
+    def forward(self, node_features, edge_index):
+        out = _layer_forward(list(self.heads), node_features, edge_index, self.concat, self.alpha,
+                             att_dropout=self.dropout_rate if self.training else 0.0)
+        return self.dropout(out)
+
+
+class GATNetwork(nn.Module):
+    """Layer stack (graph_attention.py:162-192).  One layer = a single averaging multi-head layer
+    (``hidden_dim`` unused).  Two or more layers are CONSTRUCTED exactly like the reference (same
+    state_dict shapes), which means they inherit its width mismatch (:176-186: the next layer
+    expects ``hidden_dim*num_heads`` inputs but the concatenating layer emits ``hidden_dim``) and
+    raise the same RuntimeError at forward."""
+
+    def __init__(self, node_feature_dim, hidden_dim, output_dim, num_heads, num_gat_layers=1, dropout_rate=0.1,
+                 alpha=0.2):
+        super().__init__()
+        self.num_gat_layers = num_gat_layers
+        self.gat_layers = nn.ModuleList()
+        if num_gat_layers == 1:
+            self.gat_layers.append(
+                MultiHeadGATLayer(node_feature_dim, output_dim, num_heads, dropout_rate, alpha, concat=False))
+        else:
+            self.gat_layers.append(
+                MultiHeadGATLayer(node_feature_dim, hidden_dim, num_heads, dropout_rate, alpha, concat=True))
+            for _ in range(num_gat_layers - 2):
+                self.gat_layers.append(
+                    MultiHeadGATLayer(hidden_dim * num_heads, hidden_dim, num_heads, dropout_rate, alpha, concat=True))
+            self.gat_layers.append(
+                MultiHeadGATLayer(hidden_dim * num_heads, output_dim, num_heads, dropout_rate, alpha, concat=False))
+
+    def forward(self, node_features, edge_index):
+        h = node_features
+        if not isinstance(edge_index, Graph):
+            edge_index = Graph.from_edge_index(edge_index, h.shape[0])
+        for layer in self.gat_layers:
+            h = layer(h, edge_index)
+        return h
+
+
+class PatchGraphConstructor:
+    """Patch extraction and the 4-connected patch-grid graph (patch_graph_construction.py:5-136)."""
+
+    def __init__(self, patch_size=16):
+        self.patch_size = patch_size
+
+    def grid_dims(self, H: int, W: int) -> Tuple[int, int]:
+        p = self.patch_size
+        return (H + p - 1) // p, (W + p - 1) // p
+
+    def image_to_patches(self, image_tensor_chw):
+        """``(C,H,W) -> (N,C,P,P), (nph,npw)`` (:15-47).  A strided copy; stock torch view ops,
+        only needed by callers that want the raw patches (the block itself pools with
+        ``get_patch_features``)."""
+        C, H, W = image_tensor_chw.shape
+        p = self.patch_size
+        if H % p != 0 or W % p != 0:
+            image_tensor_chw = F.pad(image_tensor_chw, (0, (p - W % p) % p, 0, (p - H % p) % p))
+        patches = image_tensor_chw.unfold(1, p, p).unfold(2, p, p)
+        nph, npw = patches.shape[1], patches.shape[2]
+        patches = patches.permute(1, 2, 0, 3, 4).contiguous().view(-1, C, p, p)
+        return patches, (nph, npw)
+
+    def construct_patch_graph(self, image_tensor_chw, patch_features_flat):
+        """Returns ``(patch_features_flat, edge_index (2,E) int64)`` (:49-102); the feature tensor is
+        returned as the same object, the edge list is generated on the GPU in the reference's order."""
+        _, H, W = image_tensor_chw.shape
+        nph, npw = self.grid_dims(H, W)
+        n = nph * npw
+        if patch_features_flat.shape[0] != n:
+            raise ValueError(f"Number of patch features ({patch_features_flat.shape[0]}) "
+                             f"does not match expected number of patches ({n}) "
+                             f"for image {H}x{W} and patch size {self.patch_size}.")
+        dev = patch_features_flat.device
+        if dev.type != "cuda":
+            raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        edge_index = ops.grid_edge_index(nph, npw, dev)
+        if edge_index.shape[1] > 0:
+            register(edge_index, Graph.grid(nph, npw, dev))
+        return patch_features_flat, edge_index
+
+    def get_patch_features(self, feature_map: torch.Tensor, patch: Optional[Tuple[int, int]] = None,
+                           out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """Per-channel patch mean ``(C,Hf,Wf) -> (N,C)`` or ``(B,C,Hf,Wf) -> (B,N,C)``: the pooling
+        ``get_patch_features_from_unet_encoder`` documents (:104-109, unimplemented there) as
+        ``image_to_patches(fm)[0].mean((2,3))``."""
+        ph, pw = patch if patch is not None else (self.patch_size, self.patch_size)
+        single = feature_map.dim() == 3
+        out = ops.pool_patches(feature_map.unsqueeze(0) if single else feature_map, ph, pw, out_dtype)
+        return out[0] if single else out
+
+    def get_patch_features_from_unet_encoder(self, unet_encoder_features, patches_coords_info):
+        """The reference raises NotImplementedError here (:104-136); same contract.  Use
+        :meth:`get_patch_features`."""
+        raise NotImplementedError("Feature extraction from U-Net for specific patches is complex and "
+                                  "depends on U-Net architecture. Use get_patch_features(feature_map).")
+
+
+class MinCutRefinement(nn.Module):
+    """Soft normalized-cut loss + soft segment assignment (mincut_refinement.py:5-205)."""
+
+    def __init__(self, gamma_unet_priors=0.5, sigma_intensity=10.0, sigma_features=1.0):
+        super().__init__()
+        self.gamma_unet_priors = gamma_unet_priors
+        self.sigma_intensity = sigma_intensity
+        self.sigma_features = sigma_features
+
+    def compute_edge_weights_for_ncut(self, node_features, edge_index):
+        """``exp(-|f_src - f_tgt|^2 / 2)`` per edge (:30-52; sigma hard-coded to 1.0 at :50)."""
+        return ops.ncut_edge_weights(node_features.float(), edge_index)
+
+    def normalized_cut_loss(self, node_features, edge_index, segment_assignments_soft, num_segments_k):
+        """(:55-160).  Returns a 0-dim tensor; where the reference returns the Python float ``0.0``
+        (no segment with association > 1e-8) this returns a tensor holding 0.0, without a device
+        sync."""
+        N = node_features.size(0)
+        if tuple(segment_assignments_soft.shape) != (N, num_segments_k):
+            raise ValueError("segment_assignments_soft shape mismatch.")
+        g = edge_index if isinstance(edge_index, Graph) else Graph.from_edge_index(edge_index, N)
+        return ncut_loss_apply(node_features.float(), segment_assignments_soft.float(), g).sum()
+
+    def forward(self, gat_refined_patch_features, patch_graph_edge_index, num_expected_segments,
+                segment_predictor_network=None):
+        if segment_predictor_network is None:
+            raise ValueError("segment_predictor_network is required to get segment assignments for Ncut loss.")
+        logits = segment_predictor_network(gat_refined_patch_features, patch_graph_edge_index)
+        S = softmax_rows(logits.float())
+        loss = self.normalized_cut_loss(gat_refined_patch_features, patch_graph_edge_index, S, num_expected_segments)
+        return loss, S
+
+
+class PatchSegmentPredictor(nn.Module):
+    """Segment-logit predictor (train_end_to_end.py:40-70): a 1-layer ``GATNetwork`` when
+    ``use_gnn`` else a 2-layer MLP (stock torch, not on the hot path)."""
+
+    def __init__(self, in_dim, num_segments, hidden_dim=None, use_gnn=False, num_gnn_layers=1, num_heads=1):
+        super().__init__()
+        self.use_gnn = use_gnn
+        if use_gnn:
+            self.gnn_predictor = GATNetwork(node_feature_dim=in_dim, hidden_dim=hidden_dim if hidden_dim else in_dim,
+                                            output_dim=num_segments, num_heads=num_heads,
+                                            num_gat_layers=num_gnn_layers, dropout_rate=0.1, alpha=0.2)
+        else:
+            if hidden_dim is None:
+                hidden_dim = in_dim * 2
+            self.mlp_predictor = nn.Sequential(nn.Linear(in_dim, hidden_dim), nn.ReLU(),
+                                               nn.Linear(hidden_dim, num_segments))
+
+    def forward(self, x, edge_index=None):
+        if self.use_gnn:
+            if edge_index is None:
+                raise ValueError("edge_index must be provided for GNN-based segment predictor.")
+            return self.gnn_predictor(x, edge_index)
+        return self.mlp_predictor(x)

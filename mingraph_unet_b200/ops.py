@@ -1,0 +1,262 @@
+"""Tensor-level wrappers over the C ABI (``include/mingraph_b200.h``).
+
+PyTorch is used here only as the owner of device memory and of the current CUDA stream;
+all arithmetic happens in ``libmingraph_b200.so``.  Every function requires CUDA tensors and
+raises otherwise (no CPU fallback).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MG_BF16, MG_F32, call
+
+_DT = {torch.float32: MG_F32, torch.bfloat16: MG_BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts: torch.Tensor) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        if dev is not None and t.device != dev:
+            raise RuntimeError("tensors live on different devices")
+        dev = t.device
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise RuntimeError(f"unsupported dtype {dt}: the graph block handles float32 and bfloat16") from None
+
+
+# ---------------------------------------------------------------------------------------------
+# graph construction
+# ---------------------------------------------------------------------------------------------
+def grid_num_edges(Hp: int, Wp: int) -> int:
+    return int(_lib.load().mg_grid_num_edges(Hp, Wp))
+
+
+def grid_edge_index(Hp: int, Wp: int, device, B: int = 1, offset_nodes: bool = False) -> torch.Tensor:
+    """``(2, B*E)`` int64 COO of the 4-connected patch grid in the reference's edge order
+    (patch_graph_construction.py:78-97)."""
+    E = grid_num_edges(Hp, Wp)
+    ei = torch.empty((2, B * E), dtype=torch.int64, device=device)
+    with torch.cuda.device(ei.device):
+        call("mg_grid_edge_index", Hp, Wp, B, int(offset_nodes), ei.data_ptr(), _stream())
+    return ei
+
+
+def grid_csr(Hp: int, Wp: int, device, B: int = 1, with_eid: bool = False):
+    """Closed-form block-diagonal CSR of ``B`` grid graphs: ``rowptr (B*N+1)``, ``col (B*E)`` int32."""
+    N, E = Hp * Wp, grid_num_edges(Hp, Wp)
+    rowptr = torch.empty(B * N + 1, dtype=torch.int32, device=device)
+    col = torch.empty(max(B * E, 1), dtype=torch.int32, device=device)
+    eid_in = torch.empty_like(col) if with_eid else None
+    eid_out = torch.empty_like(col) if with_eid else None
+    with torch.cuda.device(rowptr.device):
+        call("mg_grid_csr", Hp, Wp, B, rowptr.data_ptr(), col.data_ptr(), _ptr(eid_in), _ptr(eid_out), _stream())
+    col = col[: B * E]
+    if with_eid:
+        return rowptr, col, eid_in[: B * E], eid_out[: B * E]
+    return rowptr, col
+
+
+def complete_edge_index(K: int, device, B: int = 1, offset_nodes: bool = False) -> torch.Tensor:
+    """Complete digraph on K regions, ``triu`` pairs then reversed (train_end_to_end.py:376-380)."""
+    E = K * (K - 1)
+    ei = torch.empty((2, B * E), dtype=torch.int64, device=device)
+    if E > 0:
+        with torch.cuda.device(ei.device):
+            call("mg_complete_edge_index", K, B, int(offset_nodes), ei.data_ptr(), _stream())
+    return ei
+
+
+def complete_csr(K: int, device, B: int = 1):
+    rowptr = torch.empty(B * K + 1, dtype=torch.int32, device=device)
+    col = torch.empty(max(B * K * (K - 1), 1), dtype=torch.int32, device=device)
+    with torch.cuda.device(rowptr.device):
+        call("mg_complete_csr", K, B, rowptr.data_ptr(), col.data_ptr(), _stream())
+    return rowptr, col[: B * K * (K - 1)]
+
+
+def csr_from_coo(edge_index: torch.Tensor, N: int, by_target: bool = True, check: bool = False):
+    """Stable CSR of a caller-supplied ``(2,E)`` int64 ``edge_index`` (ascending COO id inside each
+    row).  Returns ``rowptr, col, eid``.  ``check=True`` synchronises and raises ``IndexError`` if an
+    index is outside ``[0,N)`` like the reference's indexing would."""
+    _need_cuda(edge_index)
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_index must have shape (2, E)")
+    if edge_index.dtype != torch.int64:
+        edge_index = edge_index.long()
+    edge_index = edge_index.contiguous()
+    E = edge_index.shape[1]
+    dev = edge_index.device
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    work = torch.empty(int(_lib.load().mg_csr_work_bytes(N, E)), dtype=torch.uint8, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("mg_csr_from_coo", edge_index.data_ptr(), E, N, int(by_target), rowptr.data_ptr(), col.data_ptr(),
+             eid.data_ptr(), work.data_ptr(), status.data_ptr(), _stream())
+    if check and int(status.item()) != 0:
+        raise IndexError(f"edge_index holds node ids outside [0, {N})")
+    return rowptr, col[:E], eid[:E]
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling / un-pooling
+# ---------------------------------------------------------------------------------------------
+def pool_patches(x: torch.Tensor, ph: int, pw: Optional[int] = None, out_dtype: Optional[torch.dtype] = None):
+    """Patch mean pool ``(B,C,Hf,Wf) -> (B, Hp*Wp, C)`` (zero padded right/bottom, divisor ph*pw)."""
+    _need_cuda(x)
+    if x.dim() != 4:
+        raise ValueError("pool_patches expects (B, C, Hf, Wf)")
+    pw = ph if pw is None else pw
+    x = x.contiguous()
+    B, Cc, Hf, Wf = x.shape
+    Hp, Wp = -(-Hf // ph), -(-Wf // pw)
+    out_dtype = x.dtype if out_dtype is None else out_dtype
+    out = torch.empty((B, Hp * Wp, Cc), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        call("mg_pool_patches", x.data_ptr(), _dtype_code(x.dtype), B, Cc, Hf, Wf, ph, pw, out.data_ptr(),
+             _dtype_code(out_dtype), _stream())
+    return out
+
+
+def segment_mean(h: torch.Tensor, labels: torch.Tensor, K: int, with_counts: bool = False):
+    """Region mean pool ``(B,N,D),(B,N) int32 -> (B,K,D)``; empty regions give zeros."""
+    _need_cuda(h, labels)
+    if h.dtype != torch.float32 or labels.dtype != torch.int32:
+        raise RuntimeError("segment_mean expects float32 features and int32 labels")
+    h, labels = h.contiguous(), labels.contiguous()
+    B, N, D = h.shape
+    out = torch.empty((B, K, D), dtype=torch.float32, device=h.device)
+    counts = torch.empty((B, K), dtype=torch.int32, device=h.device) if with_counts else None
+    with torch.cuda.device(h.device):
+        call("mg_segment_mean", h.data_ptr(), labels.data_ptr(), B, N, D, K, out.data_ptr(), _ptr(counts), _stream())
+    return (out, counts) if with_counts else out
+
+
+def unpool_nearest(table: torch.Tensor, labels: Optional[torch.Tensor], Hp: int, Wp: int, H: int, W: int,
+                   out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """``out[b,d,y,x] = table[b, labels[b, iy*Wp+ix], d]`` with torch's nearest index rule.
+    ``out`` may be a channel slice ``buf[:, c0:c0+D]`` of a contiguous ``(B,Ctot,H,W)`` buffer."""
+    _need_cuda(table, labels, out)
+    if table.dtype != torch.float32:
+        raise RuntimeError("unpool_nearest expects a float32 table")
+    table = table.contiguous()
+    B, K, D = table.shape
+    if labels is not None:
+        if labels.dtype != torch.int32:
+            raise RuntimeError("labels must be int32")
+        labels = labels.contiguous()
+    if out is None:
+        out = torch.empty((B, D, H, W), dtype=out_dtype, device=table.device)
+    if tuple(out.shape) != (B, D, H, W) or out.stride()[1:] != (H * W, W, 1):
+        raise ValueError("out must be (B,D,H,W) with contiguous (D,H,W) planes")
+    with torch.cuda.device(table.device):
+        call("mg_unpool_nearest", table.data_ptr(), _ptr(labels), B, K, D, Hp, Wp, H, W, out.data_ptr(),
+             _dtype_code(out.dtype), out.stride(0) if B > 1 else D * H * W, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# graph attention
+# ---------------------------------------------------------------------------------------------
+def gat_forward(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, W: torch.Tensor, a: torch.Tensor,
+                concat: bool = False, slope: float = 0.2, nodes_per_graph: int = 0,
+                out_dtype: Optional[torch.dtype] = None, save: bool = False):
+    """Multi-head GAT layer forward (eval semantics).  ``x (N,in)`` f32|bf16, ``W (H,F,in)``,
+    ``a (H,2F)`` f32, in-CSR ``rowptr/col`` int32.  Returns ``out`` or ``(out, den, z)`` if ``save``."""
+    _need_cuda(x, rowptr, col, W, a)
+    if x.dim() != 2 or W.dim() != 3 or a.dim() != 2:
+        raise ValueError("gat_forward expects x (N,in), W (H,F,in), a (H,2F)")
+    N, in_dim = x.shape
+    heads, F, in_w = W.shape
+    if in_w != in_dim or tuple(a.shape) != (heads, 2 * F):
+        raise ValueError(f"weight shapes {tuple(W.shape)} / {tuple(a.shape)} do not match x {tuple(x.shape)}")
+    E = col.numel()
+    if E == 0:
+        # the reference fails in torch.max(e) on an empty tensor (graph_attention.py:86)
+        raise RuntimeError("gat_forward: edge_index is empty (max() of an empty edge set)")
+    x = x.contiguous()
+    W = W.contiguous().float()
+    a = a.contiguous().float()
+    out_dtype = x.dtype if out_dtype is None else out_dtype
+    out = torch.empty((N, heads * F if concat else F), dtype=out_dtype, device=x.device)
+    G = N // nodes_per_graph if nodes_per_graph > 0 else 1
+    lib = _lib.load()
+    work = torch.empty(max(int(lib.mg_gat_work_bytes(N, in_dim, F, heads, G)), 256), dtype=torch.uint8, device=x.device)
+    den = torch.empty((N, heads), dtype=torch.float32, device=x.device) if save else None
+    z = torch.empty((N, heads, in_dim), dtype=torch.float32, device=x.device) if save else None
+    with torch.cuda.device(x.device):
+        call("mg_gat_forward", x.data_ptr(), _dtype_code(x.dtype), rowptr.data_ptr(), col.data_ptr(), N, E,
+             W.data_ptr(), a.data_ptr(), in_dim, F, heads, int(concat), float(slope), int(nodes_per_graph),
+             out.data_ptr(), _dtype_code(out_dtype), work.data_ptr(), _ptr(den), _ptr(z), _stream())
+    return (out, den, z) if save else out
+
+
+def softmax_argmax(logits: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Row softmax and first-max argmax of ``(N,K)`` float32 logits -> ``S (N,K)``, ``labels (N) int32``."""
+    _need_cuda(logits)
+    if logits.dtype != torch.float32:
+        raise RuntimeError("softmax_argmax expects float32 logits")
+    logits = logits.contiguous()
+    N, K = logits.shape
+    S = torch.empty_like(logits)
+    labels = torch.empty(N, dtype=torch.int32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        call("mg_softmax_argmax", logits.data_ptr(), N, K, S.data_ptr(), labels.data_ptr(), _stream())
+    return S, labels
+
+
+# ---------------------------------------------------------------------------------------------
+# normalized cut
+# ---------------------------------------------------------------------------------------------
+def ncut_edge_weights(h: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """``w_e = exp(-|h[src]-h[tgt]|^2 / 2)`` in COO order (mincut_refinement.py:43-51)."""
+    _need_cuda(h, edge_index)
+    if h.dtype != torch.float32:
+        raise RuntimeError("ncut_edge_weights expects float32 features")
+    h = h.contiguous()
+    edge_index = edge_index.long().contiguous()
+    N, D = h.shape
+    E = edge_index.shape[1]
+    w = torch.empty(E, dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        call("mg_ncut_edge_weights", h.data_ptr(), N, D, edge_index.data_ptr(), E, w.data_ptr(), _stream())
+    return w
+
+
+def ncut_loss(h: torch.Tensor, S: torch.Tensor, rowptr_out: torch.Tensor, col_out: torch.Tensor,
+              nodes_per_graph: int = 0) -> torch.Tensor:
+    """Soft normalized-cut loss per graph -> ``(G,)`` float32 (mincut_refinement.py:55-160)."""
+    _need_cuda(h, S, rowptr_out, col_out)
+    if h.dtype != torch.float32 or S.dtype != torch.float32:
+        raise RuntimeError("ncut_loss expects float32 tensors")
+    h, S = h.contiguous(), S.contiguous()
+    N, D = h.shape
+    K = S.shape[1]
+    G = N // nodes_per_graph if nodes_per_graph > 0 else 1
+    loss = torch.empty(G, dtype=torch.float32, device=h.device)
+    work = torch.empty(int(_lib.load().mg_ncut_work_bytes(N, K, G)), dtype=torch.uint8, device=h.device)
+    with torch.cuda.device(h.device):
+        call("mg_ncut_loss", h.data_ptr(), S.data_ptr(), rowptr_out.data_ptr(), col_out.data_ptr(), N, D, K,
+             int(nodes_per_graph), loss.data_ptr(), work.data_ptr(), _stream())
+    return loss

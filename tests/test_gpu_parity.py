@@ -1,0 +1,401 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against the CPU oracle and the golden
+fixtures generated from the untouched reference.  Tolerances (BASELINE.json north_star):
+``edge_index`` / labels / CSR bit-exact; fp32 outputs max-abs <= 1e-5; bf16 <= 2e-2."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import mingraph_unet_b200 as m
+    return m
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def T(a, dev="cuda"):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def maxabs(a, b):
+    return float((a.detach().float().cpu() - b.detach().float().cpu()).abs().max()) if a.numel() else 0.0
+
+
+def load_heads(net, Ws, As):
+    """Copy oracle head stacks into a GATNetwork / MultiHeadGATLayer through state_dict."""
+    layer = net.gat_layers[0] if hasattr(net, "gat_layers") else net
+    sd = {}
+    for h in range(Ws.shape[0]):
+        sd[f"heads.{h}.W.weight"] = torch.as_tensor(Ws[h]).clone()
+        sd[f"heads.{h}.a.weight"] = torch.as_tensor(As[h]).reshape(1, -1).clone()
+    layer.load_state_dict(sd)
+    return net
+
+
+# ---------------------------------------------------------------------------------------------
+# graph construction: bit-exact
+# ---------------------------------------------------------------------------------------------
+def test_grid_edge_index_bit_exact(mg, golden):
+    g = golden("kat3_edge_index.npz")
+    for key in [k for k in g.files if k.startswith("sha_")]:
+        hp, wp = map(int, key[4:].split("x"))
+        ei = mg.ops.grid_edge_index(hp, wp, "cuda")
+        assert ei.dtype == torch.int64 and tuple(ei.shape) == tuple(g[f"shape_{hp}x{wp}"])
+        assert sha16(ei.cpu().numpy()) == str(g[key])
+        assert np.array_equal(ei.cpu().numpy(), O.grid_edge_index(hp, wp))
+
+
+@pytest.mark.parametrize("hp,wp,B", [(1, 4, 1), (4, 1, 2), (3, 5, 3), (16, 16, 1), (32, 32, 16), (7, 64, 2)])
+def test_grid_csr_matches_stable_sort(mg, hp, wp, B):
+    ei = O.grid_edge_index(hp, wp)
+    N, E = hp * wp, ei.shape[1]
+    rowptr, col, eid_in, eid_out = mg.ops.grid_csr(hp, wp, "cuda", B, with_eid=True)
+    rowptr, col, eid_in, eid_out = (t.cpu().numpy() for t in (rowptr, col, eid_in, eid_out))
+    for view, key, other in ((eid_in, 1, 0), (eid_out, 0, 1)):
+        order = np.argsort(ei[key], kind="stable")
+        cnt = np.bincount(ei[key], minlength=N)
+        rp = np.concatenate([[0], np.cumsum(cnt)])
+        for b in range(B):
+            assert np.array_equal(rowptr[b * N:(b + 1) * N + 1], rp + b * E)
+            assert np.array_equal(view[b * E:(b + 1) * E], order)
+            assert np.array_equal(col[b * E:(b + 1) * E], ei[other][order] + b * N)
+    # batched COO with node offsets
+    eb = mg.ops.grid_edge_index(hp, wp, "cuda", B, offset_nodes=True).cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(eb[:, b * E:(b + 1) * E], ei + b * N)
+
+
+def test_complete_graph(mg):
+    for K in (1, 2, 3, 5, 8):
+        ei = mg.ops.complete_edge_index(K, "cuda").cpu().numpy()
+        assert np.array_equal(ei, O.complete_edge_index(K))
+        if K > 1:
+            rowptr, col = mg.ops.complete_csr(K, "cuda", 2)
+            ref = O.complete_edge_index(K)
+            order = np.argsort(ref[1], kind="stable")
+            assert np.array_equal(col.cpu().numpy()[: K * (K - 1)], ref[0][order])
+            assert np.array_equal(rowptr.cpu().numpy(), np.arange(2 * K + 1) * (K - 1))
+
+
+@pytest.mark.parametrize("N,E,seed", [(53, 311, 0), (1000, 20000, 1), (5000, 5000, 2), (7, 300, 3), (40000, 300000, 4)])
+def test_csr_from_coo_stable(mg, N, E, seed):
+    rng = np.random.default_rng(seed)
+    ei = rng.integers(0, N, size=(2, E)).astype(np.int64)
+    for by_target in (True, False):
+        key, other = (1, 0) if by_target else (0, 1)
+        rowptr, col, eid = mg.ops.csr_from_coo(T(ei), N, by_target=by_target, check=True)
+        order = np.argsort(ei[key], kind="stable")
+        assert np.array_equal(eid.cpu().numpy(), order)
+        assert np.array_equal(col.cpu().numpy(), ei[other][order])
+        assert np.array_equal(rowptr.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(ei[key], minlength=N))]))
+    bad = ei.copy()
+    bad[0, 3] = N
+    with pytest.raises(IndexError):
+        mg.ops.csr_from_coo(T(bad), N, check=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GAT: golden fixtures (reference outputs) and oracle
+# ---------------------------------------------------------------------------------------------
+def test_kat1_analytic_head(mg, golden):
+    g = golden("kat1_head.npz")
+    head = mg.GraphAttentionLayer(2, 2, 0.0, 0.2).cuda().eval()
+    with torch.no_grad():
+        head.W.weight.copy_(torch.eye(2))
+        head.a.weight.copy_(torch.tensor([[1.0, 0, 0, 1.0]]))
+        y = head(T(g["x"]), T(g["ei"]))
+    assert maxabs(y, T(g["y"])) <= FP32_TOL
+
+
+def test_kat2_default_patch_gat(mg, golden):
+    g = golden("kat2_patch_gat.npz")
+    net = load_heads(mg.GATNetwork(20, 128, 64, 4, 1, 0.1, 0.2), g["W"], g["a"]).cuda().eval()
+    x = T(g["x"])
+    feats, ei = mg.PatchGraphConstructor(16).construct_patch_graph(torch.zeros(3, 256, 256), x)
+    assert feats is x and sha16(ei.cpu().numpy()) == "79180fa641eb7814"
+    with torch.no_grad():
+        y = net(x, ei)
+    assert y.shape == (256, 64) and y.dtype == torch.float32
+    assert maxabs(y, T(g["y"])) <= FP32_TOL
+    # caller-supplied copy of the same edge list goes through the COO->CSR sort path
+    with torch.no_grad():
+        y2 = net(x, ei.clone())
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("name,fin,fout,heads,concat", [("avg_17_24_3", 17, 24, 3, False), ("cat_33_32_4", 33, 32, 4, True),
+                                                       ("avg_64_2_2", 64, 2, 2, False), ("avg_130_40_1", 130, 40, 1, False)])
+def test_layers_random_multigraph(mg, golden, name, fin, fout, heads, concat):
+    g = golden("layers_random_graph.npz")
+    layer = load_heads(mg.MultiHeadGATLayer(fin, fout, heads, 0.1, 0.2, concat=concat), g[name + "_W"], g[name + "_a"])
+    layer = layer.cuda().eval()
+    with torch.no_grad():
+        y = layer(T(g[name + "_x"]), T(g["ei"]))
+    ref = T(g[name + "_y"])
+    assert y.shape == ref.shape
+    assert maxabs(y, ref) <= FP32_TOL
+    assert torch.all(y[5] == 0) and torch.all(y[-3:] == 0)           # zero in-degree rows are exactly 0
+
+
+@pytest.mark.parametrize("N,k,fin,fout,heads", [(1000, 8, 64, 64, 4), (4096, 16, 128, 128, 4), (2048, 32, 256, 64, 1),
+                                                (1024, 8, 512, 512, 4), (3000, 5, 20, 64, 4), (777, 3, 48, 10, 8)])
+def test_gat_sweep_shapes_vs_oracle(mg, N, k, fin, fout, heads):
+    gen = torch.Generator().manual_seed(N + k)
+    x = torch.randn(N, fin, generator=gen)
+    tgt = torch.arange(N).repeat_interleave(k)
+    src = torch.randint(0, N, (N * k,), generator=gen)
+    ei = torch.stack([src, tgt])
+    Ws, As = O.init_gat_params(fin, fout, heads, gen)
+    ref = O.gat_layer(x, ei, Ws, As, 0.2, concat=False)
+    layer = load_heads(mg.MultiHeadGATLayer(fin, fout, heads, 0.0, 0.2, concat=False), Ws, As).cuda().eval()
+    with torch.no_grad():
+        y = layer(x.cuda(), ei.cuda())
+    assert maxabs(y, ref) <= FP32_TOL
+    # bf16 storage, fp32 math
+    with torch.no_grad():
+        yb = layer(x.cuda().bfloat16(), ei.cuda())
+    assert yb.dtype == torch.bfloat16
+    assert maxabs(yb, ref) <= BF16_TOL
+
+
+def test_gat_batched_per_graph_max(mg):
+    """Block-diagonal batch: the softmax shift is per image; results equal per-image runs."""
+    gen = torch.Generator().manual_seed(11)
+    B, hp, wp = 5, 6, 7
+    N = hp * wp
+    x = torch.randn(B, N, 20, generator=gen)
+    x[2] *= 8.0                                   # very different logit scale in one image
+    Ws, As = O.init_gat_params(20, 64, 4, gen)
+    ei = torch.from_numpy(O.grid_edge_index(hp, wp))
+    ref = torch.stack([O.gat_network(x[b], ei, Ws, As) for b in range(B)])
+    g = mg.Graph.grid(hp, wp, torch.device("cuda"), B)
+    y = mg.ops.gat_forward(x.view(B * N, 20).cuda(), g.rowptr_in, g.col_in, Ws.cuda(), As.cuda(), concat=False,
+                           nodes_per_graph=N)
+    err = (y.view(B, N, 64).cpu() - ref).abs().amax(dim=(1, 2))
+    assert float(err[[0, 1, 3, 4]].max()) <= FP32_TOL
+    assert float(err[2]) <= 8 * FP32_TOL           # 8x inputs: fp32 re-association noise scales with magnitude
+
+
+def test_gat_errors(mg):
+    layer = mg.MultiHeadGATLayer(8, 4, 2, 0.0, 0.2, concat=False).cuda().eval()
+    x = torch.randn(5, 8, device="cuda")
+    with pytest.raises(RuntimeError):
+        layer(x, torch.zeros((2, 0), dtype=torch.long, device="cuda"))       # empty edge set, graph_attention.py:86
+    with pytest.raises(RuntimeError):
+        layer(torch.randn(5, 7, device="cuda"), torch.tensor([[0, 1], [1, 0]], device="cuda"))
+    with pytest.raises(RuntimeError):
+        layer(x.cpu(), torch.tensor([[0, 1], [1, 0]]))                       # no CPU fallback
+    with pytest.raises(AssertionError):
+        mg.MultiHeadGATLayer(8, 5, 2, 0.0, 0.2, concat=True)                 # graph_attention.py:138
+    net = mg.GATNetwork(8, 16, 4, 2, num_gat_layers=2).cuda().eval()         # reference width bug is inherited
+    with pytest.raises(RuntimeError):
+        net(x, torch.tensor([[0, 1], [1, 0]], device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------
+# N-cut, pooling, un-pool
+# ---------------------------------------------------------------------------------------------
+def test_ncut_golden(mg, golden):
+    g = golden("ncut.npz")
+    hp, wp = (int(v) for v in g["grid"])
+    h = T(g["h"])
+    _, ei = mg.PatchGraphConstructor(16).construct_patch_graph(torch.zeros(1, hp * 16, wp * 16), h)
+    mc = mg.MinCutRefinement().cuda().eval()
+    w = mc.compute_edge_weights_for_ncut(h, ei)
+    assert maxabs(w, T(g["w"])) <= 1e-6
+    pred = load_heads(mg.GATNetwork(64, 32, 3, 2, 1, 0.1, 0.2), g["W"], g["a"]).cuda().eval()
+    with torch.no_grad():
+        loss, S = mc(h, ei, 3, pred)
+    assert maxabs(S, T(g["S"])) <= FP32_TOL
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
+    with torch.no_grad():
+        loss0, _ = mc(T(g["h_big"]), ei, 3, pred)
+    assert float(loss0) == 0.0
+    with pytest.raises(ValueError):
+        mc.normalized_cut_loss(h, ei, S[:, :2], 3)
+    with pytest.raises(ValueError):
+        mc(h, ei, 3, None)
+
+
+def test_ncut_random_graph_vs_oracle(mg):
+    gen = torch.Generator().manual_seed(5)
+    N, E, D, K = 500, 4000, 48, 5
+    h = 0.2 * torch.randn(N, D, generator=gen)
+    ei = torch.randint(0, N, (2, E), generator=gen)
+    S = torch.softmax(torch.randn(N, K, generator=gen), 1)
+    ref = O.ncut_loss(h, ei, S, K)
+    mc = mg.MinCutRefinement()
+    got = mc.normalized_cut_loss(h.cuda(), ei.cuda(), S.cuda(), K)
+    assert float(got) == pytest.approx(float(ref), rel=2e-5)
+    assert maxabs(mc.compute_edge_weights_for_ncut(h.cuda(), ei.cuda()), O.ncut_edge_weights(h, ei)) <= 1e-6
+
+
+def test_patch_pool_golden(mg, golden):
+    g = golden("patch_pool.npz")
+    fm = T(g["fm"])
+    pgc = mg.PatchGraphConstructor(16)
+    pooled = pgc.get_patch_features(fm)
+    assert maxabs(pooled, T(g["pooled"])) <= 1e-6
+    p, grid = pgc.image_to_patches(fm)
+    assert grid == (5, 5) and sha16(p.cpu().numpy()) == str(g["patches_sha"])
+    with pytest.raises(NotImplementedError):
+        pgc.get_patch_features_from_unet_encoder(None, None)
+
+
+@pytest.mark.parametrize("B,C,H,W,p", [(2, 20, 64, 64, 16), (1, 33, 70, 75, 16), (3, 512, 32, 32, 1), (2, 32, 128, 96, 8),
+                                       (1, 5, 37, 53, 7), (2, 20, 512, 512, 16)])
+def test_patch_pool_vs_oracle(mg, B, C, H, W, p):
+    gen = torch.Generator().manual_seed(C)
+    x = torch.randn(B, C, H, W, generator=gen)
+    ref = torch.stack([O.patch_mean_pool(x[b], p) for b in range(B)])
+    got = mg.ops.pool_patches(x.cuda(), p)
+    assert got.shape == ref.shape and maxabs(got, ref) <= 2e-6
+    xb = x.bfloat16()
+    refb = torch.stack([O.patch_mean_pool(xb[b].float(), p) for b in range(B)])
+    gotb = mg.ops.pool_patches(xb.cuda(), p)
+    assert gotb.dtype == torch.bfloat16 and maxabs(gotb, refb) <= 8e-3
+    assert maxabs(mg.ops.pool_patches(xb.cuda(), p, out_dtype=torch.float32), refb) <= 2e-6
+
+
+def test_segment_mean_vs_oracle(mg):
+    gen = torch.Generator().manual_seed(2)
+    B, N, D, K = 3, 200, 64, 4
+    h = torch.randn(B, N, D, generator=gen)
+    labels = torch.randint(0, K - 1, (B, N), generator=gen)         # region K-1 is empty everywhere
+    ref = torch.stack([O.region_mean_pool(h[b], labels[b], K) for b in range(B)])
+    got, cnt = mg.ops.segment_mean(h.cuda(), labels.int().cuda(), K, with_counts=True)
+    assert maxabs(got, ref) <= 2e-6
+    assert torch.all(got[:, K - 1] == 0)
+    assert np.array_equal(cnt.cpu().numpy(), np.stack([np.bincount(labels[b].numpy(), minlength=K) for b in range(B)]))
+
+
+@pytest.mark.parametrize("H,W,p", [(64, 64, 16), (70, 75, 16), (128, 96, 16), (33, 47, 16), (96, 100, 16)])
+def test_unpool_bit_exact_vs_torch_nearest(mg, H, W, p):
+    gen = torch.Generator().manual_seed(H)
+    B, K, D = 2, 3, 8
+    nph, npw = O.grid_dims(H, W, p)
+    table = torch.randn(B, K, D, generator=gen)
+    labels = torch.randint(0, K, (B, nph * npw), generator=gen)
+    ref = torch.stack([O.unpool_nearest(table[b][labels[b]], nph, npw, H, W) for b in range(B)])
+    got = mg.ops.unpool_nearest(table.cuda(), labels.int().cuda(), nph, npw, H, W)
+    assert torch.equal(got.cpu(), ref)                                  # pure gather: bit-exact
+    gotb = mg.ops.unpool_nearest(table.cuda(), labels.int().cuda(), nph, npw, H, W, out_dtype=torch.bfloat16)
+    assert torch.equal(gotb.cpu(), ref.bfloat16())
+    # write into a channel slice of a fusion buffer
+    buf = torch.zeros(B, 5 + D, H, W, device="cuda")
+    mg.ops.unpool_nearest(table.cuda(), labels.int().cuda(), nph, npw, H, W, out=buf[:, 5:])
+    assert torch.equal(buf[:, 5:].cpu(), ref) and torch.all(buf[:, :5] == 0)
+    # labels=None: table is the per-patch matrix
+    per_patch = torch.randn(B, nph * npw, D, generator=gen)
+    ref2 = torch.stack([O.unpool_nearest(per_patch[b], nph, npw, H, W) for b in range(B)])
+    assert torch.equal(mg.ops.unpool_nearest(per_patch.cuda(), None, nph, npw, H, W).cpu(), ref2)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole block
+# ---------------------------------------------------------------------------------------------
+def _block_from_params(mg, params, in_dim, K):
+    blk = mg.GraphBlock(node_feature_dim=in_dim, num_segments=K)
+    load_heads(blk.patch_gat_model, params["patch_W"], params["patch_a"])
+    load_heads(blk.segment_predictor.gnn_predictor, params["pred_W"], params["pred_a"])
+    load_heads(blk.region_gat_model, params["region_W"], params["region_a"])
+    return blk.cuda().eval()
+
+
+def _check_block(out, refs, tol, dense_tol):
+    """refs: list of oracle dicts per image.  Labels must agree wherever the oracle's top-2 soft
+    assignments are separated by more than the tolerance; dense maps are compared on those images
+    whose labels agree everywhere (the usual case)."""
+    B = len(refs)
+    for b, r in enumerate(refs):
+        assert maxabs(out.patch_features[b], r["h"]) <= tol
+        assert maxabs(out.soft_assignments[b], r["S"]) <= tol
+        top2 = torch.topk(r["S"], 2, dim=1).values if r["S"].shape[1] > 1 else None
+        lab = out.hard_labels[b].cpu().long()
+        diff = lab != r["hard"]
+        if diff.any():
+            assert top2 is not None and float((top2[diff, 0] - top2[diff, 1]).abs().max()) <= 4 * tol
+            continue
+        assert float(out.l_partition[b]) == pytest.approx(float(r["loss"]), rel=1e-4, abs=1e-7)
+        assert maxabs(out.region_features[b], r["region_out"]) <= tol
+        if out.f_g is not None and "f_g" in r:
+            assert maxabs(out.f_g[b], r["f_g"]) <= dense_tol
+    return B
+
+
+@pytest.mark.parametrize("tag", ["64x64", "128x96", "70x75", "256x256"])
+def test_block_golden_per_image(mg, golden, tag):
+    g = golden("block_images.npz")
+    H, W, in_dim, K, nph, npw = (int(v) for v in g[f"{tag}_meta"])
+    params = {f"{n}_{p}": torch.from_numpy(g[f"{tag}_{n}_{p}"]) for n in ("patch", "pred", "region") for p in ("W", "a")}
+    blk = _block_from_params(mg, params, in_dim, K)
+    with torch.no_grad():
+        out = blk(node_features=T(g[f"{tag}_x"]).unsqueeze(0), image_size=(H, W), out_dtype=torch.float32)
+    assert out.grid == (nph, npw)
+    assert maxabs(out.patch_features[0], T(g[f"{tag}_h"])) <= FP32_TOL
+    assert maxabs(out.soft_assignments[0], T(g[f"{tag}_S"])) <= FP32_TOL
+    assert np.array_equal(out.hard_labels[0].cpu().numpy(), g[f"{tag}_hard"])
+    assert float(out.l_partition[0]) == pytest.approx(float(g[f"{tag}_loss"]), rel=1e-4, abs=1e-7)
+    assert maxabs(out.region_features[0], T(g[f"{tag}_G"])) <= FP32_TOL
+    assert abs(float(out.f_g.double().sum()) - float(g[f"{tag}_fg_sum"])) <= 1e-5 * out.f_g.numel()
+    if f"{tag}_fg" in g.files:
+        assert maxabs(out.f_g[0], T(g[f"{tag}_fg"])) <= FP32_TOL
+
+
+@pytest.mark.parametrize("B,H,W,K,dtype", [(4, 128, 128, 2, torch.float32), (3, 70, 75, 3, torch.float32),
+                                           (16, 512, 512, 2, torch.bfloat16), (2, 1024, 1024, 2, torch.bfloat16)])
+def test_block_batched_vs_oracle(mg, B, H, W, K, dtype):
+    """BASELINE configs 2 (512^2 x 16, bf16) and 3 (1024^2 shard) plus fp32 / padded-grid cases."""
+    in_dim = 20
+    params = O.init_block_params(in_dim, 64, 4, K, seed=1234)
+    blk = _block_from_params(mg, params, in_dim, K)
+    nph, npw = O.grid_dims(H, W)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(B, nph * npw, in_dim, generator=gen)
+    xin = x.to(dtype)
+    want_dense_ref = H * W <= 512 * 512
+    refs = [O.graph_block_image(xin[b].float(), H, W, params, K=K, want_dense=want_dense_ref and b < 2) for b in range(B)]
+    with torch.no_grad():
+        out = blk(node_features=xin.cuda(), image_size=(H, W))
+    assert out.f_g.dtype == dtype and tuple(out.f_g.shape) == (B, 64, H, W)
+    tol = FP32_TOL
+    _check_block(out, refs, tol, FP32_TOL if dtype == torch.float32 else BF16_TOL)
+    # size-independent property at full size: the dense map is the per-patch map replicated
+    if H % 16 == 0 and W % 16 == 0:
+        fp = torch.gather(out.region_features, 1, out.hard_labels.long().unsqueeze(-1).expand(-1, -1, 64))
+        dense = fp.transpose(1, 2).reshape(B, 64, nph, 1, npw, 1).expand(B, 64, nph, 16, npw, 16).reshape(B, 64, H, W)
+        assert torch.equal(out.f_g, dense.to(dtype))
+
+
+def test_block_feature_map_input(mg):
+    """Per-pixel feature map -> K1 patch-mean pooling -> block == block on oracle-pooled features."""
+    B, C, H, W, K = 2, 20, 96, 64, 2
+    params = O.init_block_params(C, 64, 4, K, seed=7)
+    blk = _block_from_params(mg, params, C, K)
+    fm = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(3))
+    refs = [O.graph_block_image(O.patch_mean_pool(fm[b], 16), H, W, params, K=K) for b in range(B)]
+    with torch.no_grad():
+        out = blk(feature_map=fm.cuda())
+    _check_block(out, refs, FP32_TOL, FP32_TOL)
+
+
+def test_block_errors(mg):
+    blk = mg.GraphBlock().cuda().eval()
+    with pytest.raises(ValueError):
+        blk(node_features=torch.randn(1, 10, 20, device="cuda"), image_size=(64, 64))     # patch count mismatch
+    with pytest.raises(RuntimeError):
+        blk(node_features=torch.randn(1, 1, 20, device="cuda"), image_size=(16, 16))      # 1x1 grid: no edges
+    with pytest.raises(ValueError):
+        blk()

@@ -1,0 +1,182 @@
+"""CPU: the C-ABI library loads and exports every symbol of include/mingraph_b200.h, the host-side
+mirror has the reference's interface (constructor signatures, state_dict keys/shapes, error
+behaviour that does not need a device), and the multi-GPU plumbing works over gloo (world 2)."""
+import ctypes
+import inspect
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import ref_loader
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import mingraph_unet_b200 as m
+    return m
+
+
+def test_library_exports_every_header_symbol(mg):
+    from mingraph_unet_b200 import _lib
+    names = _lib.header_symbols()
+    assert len(names) >= 19 and len(set(names)) == len(names)
+    assert set(names) == set(_lib.PROTOTYPES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert _lib.load().mg_version() == 100
+    assert _lib.load().mg_grid_num_edges(16, 16) == 960 and _lib.load().mg_grid_num_edges(1, 1) == 0
+    assert _lib.load().mg_grid_num_edges(64, 64) == 16128
+
+
+def test_argument_validation_without_device(mg):
+    """Host-side argument checks return MG_ERR_INVALID before any CUDA call."""
+    from mingraph_unet_b200 import _lib
+    with pytest.raises(_lib.MinGraphError) as e:
+        _lib.call("mg_grid_edge_index", 0, 4, 1, 0, None, None)
+    assert e.value.code == _lib.MG_ERR_INVALID and "bad grid" in e.value.text
+    with pytest.raises(_lib.MinGraphError) as e:
+        _lib.call("mg_gat_forward", 1, 0, 1, None, 4, 0, 1, 1, 8, 8, 1, 0, 0.2, 0, 1, 0, 1, None, None, None)
+    assert "empty edge_index" in e.value.text
+
+
+def test_no_cpu_fallback(mg):
+    x = torch.randn(4, 8)
+    ei = torch.tensor([[0, 1], [1, 0]])
+    layer = mg.MultiHeadGATLayer(8, 4, 2, 0.0, 0.2, concat=False).eval()
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        layer(x, ei)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        mg.PatchGraphConstructor(16).construct_patch_graph(torch.zeros(3, 32, 32), torch.zeros(4, 8))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        mg.ops.pool_patches(torch.zeros(1, 2, 32, 32), 16)
+
+
+def test_missing_library_fails_loudly():
+    code = ("import os; os.environ['MINGRAPH_B200_LIB']='/nonexistent/lib.so'\n"
+            "try:\n    import mingraph_unet_b200\nexcept ImportError as e:\n    print('IMPORTERROR', 'no CPU fallback' in str(e).replace('There is no CPU fallback','no CPU fallback'))\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert "IMPORTERROR True" in out.stdout, out.stdout + out.stderr
+
+
+def test_constructor_errors_match_reference(mg):
+    with pytest.raises(AssertionError):
+        mg.MultiHeadGATLayer(8, 5, 2, 0.0, 0.2, concat=True)           # graph_attention.py:138
+    with pytest.raises(ValueError):
+        mg.PatchGraphConstructor(16).construct_patch_graph(torch.zeros(3, 64, 64), torch.zeros(5, 8))
+    with pytest.raises(ValueError):
+        mg.PatchSegmentPredictor(8, 2, use_gnn=True)(torch.zeros(4, 8), None)   # train_end_to_end.py:66-67
+    with pytest.raises(ValueError):
+        mg.MinCutRefinement()(torch.zeros(4, 8), torch.zeros(2, 0, dtype=torch.long), 2, None)
+    with pytest.raises(NotImplementedError):
+        mg.PatchGraphConstructor().get_patch_features_from_unet_encoder(None, None)
+
+
+def test_default_block_parameter_count(mg):
+    blk = mg.GraphBlock()
+    counts = [sum(p.numel() for p in m.parameters()) for m in (blk.patch_gat_model, blk.segment_predictor, blk.region_gat_model)]
+    assert counts == [5632, 264, 16896]
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_interface_matches_live_reference(mg):
+    R = ref_loader.load()
+    pairs = [(R.GraphAttentionLayer, mg.GraphAttentionLayer), (R.MultiHeadGATLayer, mg.MultiHeadGATLayer),
+             (R.GATNetwork, mg.GATNetwork), (R.MinCutRefinement, mg.MinCutRefinement),
+             (R.PatchGraphConstructor, mg.PatchGraphConstructor)]
+    if R.PatchSegmentPredictor is not None:
+        pairs.append((R.PatchSegmentPredictor, mg.PatchSegmentPredictor))
+    for ref_cls, our_cls in pairs:
+        assert str(inspect.signature(ref_cls.__init__)) == str(inspect.signature(our_cls.__init__)), ref_cls.__name__
+        if hasattr(ref_cls, "forward"):
+            assert list(inspect.signature(ref_cls.forward).parameters) == list(inspect.signature(our_cls.forward).parameters)
+    for name in ("image_to_patches", "construct_patch_graph", "get_patch_features_from_unet_encoder"):
+        assert list(inspect.signature(getattr(R.PatchGraphConstructor, name)).parameters) == \
+            list(inspect.signature(getattr(mg.PatchGraphConstructor, name)).parameters)
+    for name in ("compute_edge_weights_for_ncut", "normalized_cut_loss"):
+        assert list(inspect.signature(getattr(R.MinCutRefinement, name)).parameters) == \
+            list(inspect.signature(getattr(mg.MinCutRefinement, name)).parameters)
+    # state_dict: same keys and shapes, loads both ways, same init distribution bounds
+    for args in [(20, 128, 64, 4, 1, 0.1, 0.2), (64, 32, 2, 2, 1), (12, 16, 8, 2, 3)]:
+        torch.manual_seed(0)
+        ref = R.GATNetwork(*args)
+        torch.manual_seed(0)
+        ours = mg.GATNetwork(*args)
+        rs, os_ = ref.state_dict(), ours.state_dict()
+        assert list(rs) == list(os_)
+        for k in rs:
+            assert rs[k].shape == os_[k].shape and torch.equal(rs[k], os_[k])       # same RNG consumption order
+        ours.load_state_dict(rs)
+        ref.load_state_dict(os_)
+    if R.PatchSegmentPredictor is not None:
+        for kw in (dict(use_gnn=True, num_heads=2, hidden_dim=32), dict(use_gnn=False)):
+            a, b = R.PatchSegmentPredictor(64, 2, **kw), mg.PatchSegmentPredictor(64, 2, **kw)
+            assert {k: v.shape for k, v in a.state_dict().items()} == {k: v.shape for k, v in b.state_dict().items()}
+    # image_to_patches is a view-level restatement: identical on CPU
+    img = torch.randn(3, 70, 75)
+    pr, gr = R.PatchGraphConstructor(16).image_to_patches(img)
+    po, go = mg.PatchGraphConstructor(16).image_to_patches(img)
+    assert gr == go and torch.equal(pr, po)
+
+
+def test_shard_range():
+    from mingraph_unet_b200.distributed import shard_range
+    for B, world in [(64, 8), (64, 2), (16, 1), (10, 4), (3, 8), (32, 8)]:
+        spans = [shard_range(B, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 4, 4)
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["MG_ROOT"])
+from mingraph_unet_b200.distributed import shard_range, gather_block_outputs, allreduce_graph_grads
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+Bg, K, D, N = int(os.environ["MG_BG"]), 2, 4, 6
+g = torch.Generator().manual_seed(0)
+loss = torch.rand(Bg, generator=g); reg = torch.randn(Bg, K, D, generator=g)
+lab = torch.randint(0, K, (Bg, N), generator=g).int()
+lo, hi = shard_range(Bg, rank, world)
+out = gather_block_outputs(loss[lo:hi], reg[lo:hi], lab[lo:hi], Bg)
+assert torch.equal(out.l_partition, loss) and torch.equal(out.region_features, reg) and torch.equal(out.hard_labels, lab)
+nf = out.node_features()
+assert nf.shape == (Bg, N, D) and torch.equal(nf[1, 3], reg[1, lab[1, 3].item()])
+m = torch.nn.Linear(3, 2)
+for p in m.parameters():
+    p.grad = torch.full_like(p, float(rank + 1))
+n = allreduce_graph_grads(m)
+assert n == 8 and all(torch.allclose(p.grad, torch.full_like(p, (world + 1) / 2)) for p in m.parameters())
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+@pytest.mark.parametrize("Bg", [8, 5])
+def test_gloo_world2_gather_and_grad_allreduce(tmp_path, Bg):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MG_ROOT=ROOT, MG_BG=str(Bg), MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + Bg), str(script)]
+    out = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.count("OK") == 2, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--workload", "cfg1"], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
