@@ -220,31 +220,25 @@ def run_ours(args):
     fm_dev = fm_host.to(dev)
     fusion = torch.zeros(B, C_UNET + D_OUT, H, W, dtype=dtype, device=dev)     # [0:32] decoder features, [32:96] F_g
     f_g_slice = fusion[:, C_UNET:]
-    small_f = torch.empty(B * (1 + K_SEG * D_OUT), dtype=torch.float32, device=dev)
-    small_i = torch.empty(B * N, dtype=torch.int32, device=dev)
-    gath_f = torch.empty(world * small_f.numel(), dtype=torch.float32, device=dev) if world > 1 else None
-    gath_i = torch.empty(world * small_i.numel(), dtype=torch.int32, device=dev) if world > 1 else None
-    host_f = torch.empty(small_f.numel(), dtype=torch.float32).pin_memory()
-    host_i = torch.empty(small_i.numel(), dtype=torch.int32).pin_memory()
+    n_small = B * (1 + K_SEG * D_OUT + N)                                       # loss | region features | labels
+    gathered = torch.empty(world * n_small, dtype=torch.float32, device=dev) if world > 1 else None
+    host_loss = torch.empty(B, dtype=torch.float32).pin_memory()
+    host_region = torch.empty(B, K_SEG, D_OUT, dtype=torch.float32).pin_memory()
+    host_labels = torch.empty(B, N, dtype=torch.int32).pin_memory()
 
-    unpool_ev = []
+    # public API: the block recorded once into a CUDA graph (pool -> fused block kernel -> un-pool), replayed per step
+    runner = mg.CapturedGraphBlock(blk, fm_dev, image_size=(H, W), out=f_g_slice)
 
-    def step(x_dev, time_unpool=False):
-        with torch.no_grad():
-            out = blk(feature_map=x_dev, image_size=(H, W), want_dense=False)
-            if time_unpool:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            mg.ops.unpool_nearest(out.region_features, out.hard_labels, nph, npw, H, W, out=f_g_slice)
-            if time_unpool:
-                e1.record()
-                unpool_ev.append((e0, e1))
-            small_f[:B].copy_(out.l_partition)
-            small_f[B:].copy_(out.region_features.reshape(-1))
-            small_i.copy_(out.hard_labels.reshape(-1))
-            if world > 1:
-                dist.all_gather_into_tensor(gath_f, small_f)
-                dist.all_gather_into_tensor(gath_i, small_i)
+    def exchange(out):
+        """N>1: one NCCL all-gather of the small per-image outputs (never the dense map)."""
+        if world > 1:
+            packed = torch.cat([out.l_partition, out.region_features.reshape(-1),
+                                out.hard_labels.reshape(-1).view(torch.float32)])
+            dist.all_gather_into_tensor(gathered, packed)
+
+    def step():
+        out = runner()                  # static input already resident in HBM
+        exchange(out)
         return out
 
     def barrier():
@@ -254,7 +248,7 @@ def run_ours(args):
 
     # ---- device-resident timing (value) ------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        step(fm_dev)
+        step()
     sampler = ClockSampler(local)
     barrier()
     launches0 = _lib.launch_count()
@@ -262,11 +256,12 @@ def run_ours(args):
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for _ in range(args.steps):
-        step(fm_dev, time_unpool=True)
+        step()
     t_end.record()
     barrier()
     sampler.stop()
-    launches = _lib.launch_count() - launches0
+    # kernels recorded in the graph launch once per replay: 3 of ours per step (pool, block, un-pool)
+    launches = (_lib.launch_count() - launches0) + 3 * args.steps
     ms_total = t_start.elapsed_time(t_end)
     note = "sampled during the timed region"
     if len(sampler.samples) < 5:        # very short timed region: keep the same load running while sampling
@@ -274,18 +269,46 @@ def run_ours(args):
         t_until = time.time() + 1.0
         while time.time() < t_until:
             for _ in range(20):
-                step(fm_dev)
+                step()
             torch.cuda.synchronize()
         sampler.stop()
         note = "timed region shorter than the NVML sampling period; sampled under the same load right after it"
-    unpool_ms = statistics.mean(a.elapsed_time(b) for a, b in unpool_ev)
+
+    # ---- per-kernel durations: the same K steps launched eagerly with CUDA events around each kernel ----
+    kern_ev = {"pool": [], "block": [], "unpool": []}
+    layers = (blk.patch_gat_model.gat_layers[0], blk.segment_predictor.gnn_predictor.gat_layers[0],
+              blk.region_gat_model.gat_layers[0])
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    with torch.no_grad():
+        prep = blk._prepared()
+        for i in range(args.steps + 3):
+            torch.cuda._sleep(400_000)      # ~0.2 ms spin so the host runs ahead and the three launches queue back to back
+            e0 = ev()
+            x = mg.ops.pool_patches(fm_dev, PATCH, PATCH)
+            e1 = ev()
+            hh, SS, ll, lo, _, GG = mg.ops.block_forward(x, nph, npw, prep, D_OUT, layers[0].num_heads, layers[1].num_heads,
+                                                         layers[2].num_heads, K_SEG)
+            e2 = ev()
+            mg.ops.unpool_nearest(GG, ll, nph, npw, H, W, out=f_g_slice)
+            e3 = ev()
+            if i >= 3:
+                kern_ev["pool"].append((e0, e1)); kern_ev["block"].append((e1, e2)); kern_ev["unpool"].append((e2, e3))
+    torch.cuda.synchronize()
+    kern_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in kern_ev.items()}
+    unpool_ms = kern_ms["unpool"]
 
     # ---- end-to-end through the public API with host buffers (e2e) ---------------------------
     def e2e_step():
-        x = fm_host.to(dev, non_blocking=True)
-        step(x)
-        host_f.copy_(small_f, non_blocking=True)
-        host_i.copy_(small_i, non_blocking=True)
+        out = runner(fm_host)                                   # H2D of this step's input from pinned memory
+        exchange(out)
+        host_loss.copy_(out.l_partition, non_blocking=True)     # D2H of the step's results
+        host_region.copy_(out.region_features, non_blocking=True)
+        host_labels.copy_(out.hard_labels, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
@@ -326,22 +349,33 @@ def run_ours(args):
             "dtype": "f32" if dtype == torch.float32 else "bf16 storage / f32 math", "data": "synthetic", "config": cfg,
             "edges_per_s": B * world * E * args.steps / (ms_total * 1e-3),
             "step_hbm_gbs": (unpool_bytes + pool_bytes) / (ms_step * 1e-3) / 1e9,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "launch_mode": "CUDA graph replay (3 kernels of libmingraph_b200.so per step)",
             "roofline": {"kernel": "unpool_vec_kernel (K7 nearest un-pool)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": unpool_bytes,
-                         "kernel_ms": unpool_ms, "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "kernel_ms": unpool_ms, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "timing": "CUDA events around each eager launch of the same K steps (graph replays cannot "
+                                   "carry timing events)",
+                         "other_kernels": {
+                             "pool_patches_vec_kernel": {"ms": kern_ms["pool"], "algorithmic_bytes": pool_bytes,
+                                                         "achieved_gbs": pool_bytes / (kern_ms["pool"] * 1e-3) / 1e9,
+                                                         "frac": pool_bytes / (kern_ms["pool"] * 1e-3) / 1e9 / peak},
+                             "block_forward_kernel": {"ms": kern_ms["block"], "note": "latency-bound cluster kernel; "
+                                                      "moves ~%.1f MB" % (B * N * (IN_DIM * b + 4 * (D_OUT + 12)) / 1e6)}}},
             "e2e": {"value": B * world * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": fm_host.numel() * fm_host.element_size(),
-                    "d2h_bytes_per_step": host_f.numel() * 4 + host_i.numel() * 4, "steps": e2e_steps,
-                    "api": "GraphBlock.forward(feature_map=pinned host tensor -> device) + D2H of loss/region/labels"},
+                    "d2h_bytes_per_step": 4 * (host_loss.numel() + host_region.numel() + host_labels.numel()),
+                    "steps": e2e_steps,
+                    "api": "CapturedGraphBlock(GraphBlock)(pinned host feature map): H2D + graph replay + D2H of "
+                           "loss / region features / labels"},
             "clocks": sampler.summary(note),
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             cpu_block_images(args.workload, 1)
-            n_img = args.cpu_sample_images or (8 if H >= 512 else 32)
+            probe = cpu_block_images(args.workload, 4) / 4                      # s/image
+            n_img = args.cpu_sample_images or int(min(4000, max(8, 12.0 / probe)))   # ~12 s of CPU work
             secs = cpu_block_images(args.workload, n_img)
             line["cpu_baseline"] = {"value": n_img / secs, "unit": "images/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "sample": f"{n_img} images of the workload, oracle/restate.py fp32, "

@@ -132,6 +132,27 @@ MG_API int mg_ncut_loss(const float* h, const float* S, const int32_t* rowptr_ou
 MG_API int mg_unpool_nearest(const float* table, const int32_t* labels, int B, int K, int D, int Hp, int Wp, int H, int W,
                       void* out, int out_dtype, int64_t out_batch_stride, mg_stream_t stream);
 
+/* ---- fused per-image block (forward) ------------------------------------------------------------
+ * The per-image loop of scripts/train_end_to_end.py:329-389 for a batch of B images in ONE launch:
+ * patch GAT -> predictor GAT -> softmax/argmax -> N-cut loss -> region mean-pool -> region GAT on the
+ * 4-connected Hp x Wp patch grid (one thread-block cluster per image).  Weights are those of the
+ * three 1-layer GATNetworks (heads.{h}.W.weight stacked: W1 (H1,D,in), W2 (H2,K,D), W3 (H3,D,D);
+ * heads.{h}.a.weight stacked: a1 (H1,2D), a2 (H2,2K), a3 (H3,2D)); mg_block_prepare re-arranges them
+ * into `prep` (mg_block_prep_floats() floats, 16-byte aligned) once per weight version.
+ *   x (B,N,in) f32|bf16 -> h (B,N,D), S (B,N,K), labels (B,N) int32, loss (B), region_in (B,K,D, nullable),
+ *   region_out (B,K,D); q_work: B*N*(2*H2 + H2*K) floats of scratch.
+ * mg_block_supported() != 0 tells whether the shape fits the fused kernel (in <= 64, D in {32,64,128},
+ * heads <= 4, K <= 8, shared-memory budget); otherwise compose the stand-alone entry points above. */
+MG_API int64_t mg_block_prep_floats(int in_dim, int D, int H1, int H2, int H3, int K);
+MG_API int mg_block_supported(int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K);
+MG_API int mg_block_prepare(const float* W1, const float* a1, const float* W2, const float* a2, const float* W3,
+                            const float* a3, int in_dim, int D, int H1, int H2, int H3, int K, float* prep,
+                            mg_stream_t stream);
+MG_API int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3,
+                            int K, float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work,
+                            float* S, int32_t* labels, float* loss, float* region_in, float* region_out,
+                            mg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,8 @@ class GraphBlock(nn.Module):
         self.mincut_module = MinCutRefinement()
         self.region_gat_model = GATNetwork(gat_output_dim, gat_hidden_dim, gat_output_dim, num_heads, 1,
                                            dropout_rate, alpha)
+        self.fused = True            # False: compose the stand-alone kernels (same results, more launches)
+        self._prep_cache = None
 
     def forward(self, node_features: Optional[torch.Tensor] = None, image_size: Optional[Tuple[int, int]] = None,
                 feature_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
@@ -89,28 +91,55 @@ class GraphBlock(nn.Module):
                              f"({nph * npw}) for image {H}x{W} and patch size {self.patch_size}.")
         dev = node_features.device
         K, D = self.num_segments, self.gat_output_dim
-        g = Graph.grid(nph, npw, dev, B)
-        if g.E == 0:
+        if nph * npw < 2:
             raise RuntimeError("max(): Expected reduction dim to be specified for input.numel() == 0 "
                                "(a 1x1 patch grid has no edges)")
-        x = node_features.reshape(B * N, -1)
-        patch_layer = self.patch_gat_model.gat_layers[0]
-        h = _batched_layer(patch_layer, x, g, torch.float32)                       # :332
-        pred_layer = self.segment_predictor.gnn_predictor.gat_layers[0]
-        logits = _batched_layer(pred_layer, h, g, torch.float32)                   # mincut_refinement.py:192
-        S, labels = ops.softmax_argmax(logits)                                     # :193, train_end_to_end.py:356
-        loss = ops.ncut_loss(h, S, g.rowptr_out, g.col_out, g.nodes_per_graph if B > 1 else 0)   # :196
-        R = ops.segment_mean(h.view(B, N, D), labels.view(B, N), K)                # :368-373
-        if K > 1:                                                                  # :383-389
-            rg = Graph.complete(K, dev, B)
-            G = _batched_layer(self.region_gat_model.gat_layers[0], R.view(B * K, D), rg, torch.float32).view(B, K, D)
+        dense_dtype = out_dtype if out_dtype is not None else node_features.dtype
+        layers = (self.patch_gat_model.gat_layers[0], self.segment_predictor.gnn_predictor.gat_layers[0],
+                  self.region_gat_model.gat_layers[0])
+        needs_autograd = torch.is_grad_enabled() and (node_features.requires_grad or
+                                                      any(p.requires_grad for p in self.parameters()))
+        use_fused = (self.fused and not needs_autograd and not (self.training and any(l.dropout_rate > 0 for l in layers))
+                     and ops.block_supported(B, nph, npw, node_features.shape[-1], D, layers[0].num_heads,
+                                             layers[1].num_heads, layers[2].num_heads, K))
+        if use_fused:
+            # ONE launch: patch GAT -> predictor GAT -> softmax/argmax -> N-cut -> region pool -> region GAT
+            h, S, labels, loss, _, G = ops.block_forward(
+                node_features, nph, npw, self._prepared(), D, layers[0].num_heads, layers[1].num_heads,
+                layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers))
         else:
-            G = R
+            g = Graph.grid(nph, npw, dev, B)
+            x = node_features.reshape(B * N, -1)
+            h = _batched_layer(layers[0], x, g, torch.float32)                          # :332
+            logits = _batched_layer(layers[1], h, g, torch.float32)                     # mincut_refinement.py:192
+            S, labels = ops.softmax_argmax(logits)                                      # :193, train_end_to_end.py:356
+            loss = ops.ncut_loss(h, S, g.rowptr_out, g.col_out, g.nodes_per_graph)      # :196
+            R = ops.segment_mean(h.view(B, N, D), labels.view(B, N), K)                 # :368-373
+            if K > 1:                                                                   # :383-389
+                rg = Graph.complete(K, dev, B)
+                G = _batched_layer(layers[2], R.view(B * K, D), rg, torch.float32).view(B, K, D)
+            else:
+                G = R
+            h, S, labels = h.view(B, N, D), S.view(B, N, K), labels.view(B, N)
         f_g = None
-        if want_dense:                                                             # :403-421
-            f_g = ops.unpool_nearest(G, labels.view(B, N), nph, npw, H, W, out=out,
-                                     out_dtype=out_dtype if out_dtype is not None else node_features.dtype)
-        return GraphBlockOutput(f_g, loss, S.view(B, N, K), labels.view(B, N), h.view(B, N, D), G, (nph, npw))
+        if want_dense:                                                                  # :403-421
+            f_g = ops.unpool_nearest(G, labels, nph, npw, H, W, out=out, out_dtype=dense_dtype)
+        return GraphBlockOutput(f_g, loss, S, labels, h, G, (nph, npw))
+
+    def _prepared(self) -> torch.Tensor:
+        """Weights re-arranged for the fused kernel, cached per weight version (one tiny launch when
+        any parameter changed, e.g. after an optimizer step or ``load_state_dict``)."""
+        nets = (self.patch_gat_model, self.segment_predictor.gnn_predictor, self.region_gat_model)
+        ps = [p for net in nets for p in net.parameters()]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._prep_cache is None or self._prep_cache[0] != key:
+            stacks = []
+            for net in nets:
+                heads = list(net.gat_layers[0].heads)
+                stacks.append(torch.stack([hd.W.weight.detach() for hd in heads], 0))
+                stacks.append(torch.stack([hd.a.weight.detach().view(-1) for hd in heads], 0))
+            self._prep_cache = (key, ops.block_prepare(*stacks, out=None if self._prep_cache is None else self._prep_cache[1]))
+        return self._prep_cache[1]
 
 
 def _batched_layer(layer, x: torch.Tensor, g: Graph, out_dtype: torch.dtype) -> torch.Tensor:

@@ -1,0 +1,866 @@
+// Fused per-image graph block (forward): ONE launch runs, for every image of the batch,
+//   patch GAT -> predictor GAT -> softmax/argmax -> N-cut loss -> region mean-pool -> region GAT
+// i.e. scripts/train_end_to_end.py:329-389 of the reference (model/gat/graph_attention.py:40-160,
+// model/graph_partition/mincut_refinement.py:43-160,192-193) on the 4-connected patch grid.
+//
+// B200 mapping: each image is owned by one thread-block CLUSTER (<= 8 CTAs, one per SM).  The
+// image's nodes are split row-major over the cluster's CTAs; the stages that need a per-image
+// reduction (the global softmax shift of graph_attention.py:86, the N-cut sums, the region
+// means) exchange a few floats through distributed shared memory and a hardware cluster
+// barrier instead of a kernel boundary.  Neighbours are closed-form (up, left, right, down =
+// ascending COO edge id), so no edge list is read at all.  Node-level intermediates that
+// neighbouring CTAs need (h, predictor scalars, S) go through global memory (L2 resident) and
+// become visible at the cluster barriers (release/acquire at cluster scope).
+//
+// Weights are pre-arranged once per weight version by mg_block_prepare (transposed W, attention
+// vectors u = W^T a) and staged into shared memory with one TMA bulk copy (cp.async.bulk).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mg {
+
+constexpr int kBT = 256;          // threads per CTA
+constexpr int kTileN = 128;       // nodes per aggregation/transform tile
+constexpr int kMaxHeads = 4;
+constexpr int kMaxSeg = 8;        // K
+constexpr int kMaxCluster = 8;
+
+struct BlockShape {
+  int B, Hp, Wp, N;               // images, patch grid, nodes per image
+  int in_dim, in_pad, D;          // node feature width (padded to 4), GAT output width
+  int H1, H2, H3, K;              // heads of patch / predictor / region GAT, segments
+  int cluster, npc;               // CTAs per image, nodes per CTA
+  float slope1, slope2, slope3;   // LeakyReLU slopes
+};
+
+// prepared-weight blob layout (floats).  Part A is staged to shared memory by every CTA.
+struct PrepLayout {
+  int w1t, u1, w2, u2, sizeA;     // A: W1t [H1][in_pad][D] | u1 [2H1][in_pad] | W2 [H2][K][D] | u2 [2H2][D]
+  int w3t, u3, total;             // B: W3t [H3][D][D] (i-major, f fastest) | u3 [2H3][D]
+};
+__host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
+__host__ __device__ inline PrepLayout prep_layout(const BlockShape& s) {
+  PrepLayout p;
+  int o = 0;
+  p.w1t = o; o += s.H1 * s.in_pad * s.D;
+  p.u1 = o;  o += 2 * s.H1 * s.in_pad;
+  p.w2 = o;  o += s.H2 * s.K * s.D;
+  p.u2 = o;  o += 2 * s.H2 * s.D;
+  o = round_up4(o);
+  p.sizeA = o;
+  p.w3t = o; o += s.H3 * s.D * s.D;
+  p.u3 = o;  o += 2 * s.H3 * s.D;
+  p.total = round_up4(o);
+  return p;
+}
+
+// shared-memory layout of the main kernel (float offsets)
+struct SmemLayout {
+  int prep, s1, alpha, zs, wts, deg, S, lab, red, cmax1, cmax2, exp_part, exp_rsum, exp_rcnt, region, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(const BlockShape& s) {
+  const PrepLayout p = prep_layout(s);
+  SmemLayout L;
+  int o = 4;                                    // [0..1] mbarrier (8 bytes), keep 16-byte alignment
+  L.prep = o;     o += p.sizeA;
+  L.s1 = o;       o += round_up4((s.npc + 2 * s.Wp) * 2 * s.H1);
+  L.alpha = o;    o += kTileN * s.H1 * 4;
+  L.zs = o;       o += kTileN * s.H1 * s.in_pad;
+  L.wts = o;      o += s.npc * 4;
+  L.deg = o;      o += round_up4(s.npc);
+  L.S = o;        o += round_up4(s.npc * s.K);
+  L.lab = o;      o += round_up4(s.npc);
+  L.red = o;      o += 8 * 64;                  // block reductions: 8 warps x up to 64 values
+  L.cmax1 = o;    o += 4;
+  L.cmax2 = o;    o += 4;
+  L.exp_part = o; o += round_up4(2 * s.K);
+  L.exp_rsum = o; o += s.K * s.D;
+  L.exp_rcnt = o; o += round_up4(s.K);
+  // rank-0 scratch of the region stage: R [K][D], s3 [K][2H3], a3 [K][H3][K], z3 [K][H3][D], y3 [K][H3][D]
+  L.region = o;   o += s.K * s.D + round_up4(s.K * 2 * s.H3) + round_up4(s.K * s.H3 * s.K) + 2 * s.K * s.H3 * s.D;
+  L.total = o;
+  return L;
+}
+
+struct BlockArgs {
+  BlockShape s;
+  const void* x;            // (B, N, in) f32|bf16
+  const float* prep;        // prepared weights (mg_block_prepare)
+  float* h;                 // (B, N, D)   patch-GAT output
+  float* q;                 // (B, N, NQ)  scratch: predictor scalars (s2_src | s2_tgt | t[h2][c])
+  float* S;                 // (B, N, K)
+  int32_t* labels;          // (B, N)
+  float* loss;              // (B)
+  float* region_in;         // (B, K, D) or null
+  float* region_out;        // (B, K, D)
+};
+
+// ---------------------------------------------------------------------------------------------
+// weight preparation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) block_prepare_kernel(BlockShape s, const float* __restrict__ W1,
+                                                           const float* __restrict__ a1, const float* __restrict__ W2,
+                                                           const float* __restrict__ a2, const float* __restrict__ W3,
+                                                           const float* __restrict__ a3, float* __restrict__ prep) {
+  const PrepLayout p = prep_layout(s);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.total; idx += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (idx < p.u1) {                                  // W1t[h][i][f] = W1[h][f][i], zero padded in i
+      const int r = idx - p.w1t, f = r % s.D, i = (r / s.D) % s.in_pad, h = r / (s.D * s.in_pad);
+      if (i < s.in_dim) v = W1[((size_t)h * s.D + f) * s.in_dim + i];
+    } else if (idx < p.w2) {                           // u1[q][i] = sum_f a1[h][half*D + f] W1[h][f][i]
+      const int r = idx - p.u1, i = r % s.in_pad, qq = r / s.in_pad;
+      const int h = qq % s.H1, half = qq / s.H1;
+      if (i < s.in_dim)
+        for (int f = 0; f < s.D; ++f) v = fmaf(a1[(size_t)h * 2 * s.D + half * s.D + f], W1[((size_t)h * s.D + f) * s.in_dim + i], v);
+    } else if (idx < p.u2) {                           // W2[h][c][d] as given
+      v = W2[idx - p.w2];
+    } else if (idx < p.u2 + 2 * s.H2 * s.D) {          // u2[q][d] = sum_c a2[h][half*K + c] W2[h][c][d]
+      const int r = idx - p.u2, d = r % s.D, qq = r / s.D;
+      const int h = qq % s.H2, half = qq / s.H2;
+      for (int c = 0; c < s.K; ++c) v = fmaf(a2[(size_t)h * 2 * s.K + half * s.K + c], W2[((size_t)h * s.K + c) * s.D + d], v);
+    } else if (idx < p.w3t) {
+      v = 0.f;                                         // alignment padding
+    } else if (idx < p.u3) {                           // W3t[h][i][f] = W3[h][f][i]
+      const int r = idx - p.w3t, f = r % s.D, i = (r / s.D) % s.D, h = r / (s.D * s.D);
+      v = W3[((size_t)h * s.D + f) * s.D + i];
+    } else if (idx < p.u3 + 2 * s.H3 * s.D) {          // u3[q][i]
+      const int r = idx - p.u3, i = r % s.D, qq = r / s.D;
+      const int h = qq % s.H3, half = qq / s.H3;
+      for (int f = 0; f < s.D; ++f) v = fmaf(a3[(size_t)h * 2 * s.D + half * s.D + f], W3[((size_t)h * s.D + f) * s.D + i], v);
+    }
+    prep[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> this CTA's shared memory, completion on an mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename TX>
+__device__ __forceinline__ void load4(const TX* p, float* o);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float* o) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+  o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+
+// in-neighbours of grid node n in ascending COO edge id: up, left, right, down
+__device__ __forceinline__ int grid_nbrs(int n, int Hp, int Wp, int* nb) {
+  const int r = n / Wp, c = n - r * Wp;
+  int k = 0;
+  if (r > 0) nb[k++] = n - Wp;
+  if (c > 0) nb[k++] = n - 1;
+  if (c + 1 < Wp) nb[k++] = n + 1;
+  if (r + 1 < Hp) nb[k++] = n + Wp;
+  return k;
+}
+
+// deterministic block reduction of nv (<= MAXV) per-thread values; result in out[0..nv)
+template <bool IS_MAX, int MAXV>
+__device__ __forceinline__ void block_reduce(const float (&v)[MAXV], int nv, float* red /* [8][64] */, float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      float t = v[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float u = __shfl_xor_sync(kFull, t, o);
+        t = IS_MAX ? fmaxf(t, u) : t + u;
+      }
+      if (lane == 0) red[warp * 64 + i] = t;
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nv) {
+    float t = red[threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < kBT / 32; ++w) t = IS_MAX ? fmaxf(t, red[w * 64 + threadIdx.x]) : t + red[w * 64 + threadIdx.x];
+    out[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float sel4(const float (&a)[kMaxHeads], int h) {
+  float v = a[0];
+#pragma unroll
+  for (int i = 1; i < kMaxHeads; ++i) v = (h == i) ? a[i] : v;
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+template <typename TX>
+__global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const BlockShape& s = A.s;
+  const SmemLayout L = smem_layout(s);
+  const PrepLayout P = prep_layout(s);
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int crank = (int)cluster.block_rank();
+  const int b = blockIdx.x / s.cluster;
+  const int N = s.N, Hp = s.Hp, Wp = s.Wp, D = s.D, H1 = s.H1, H2 = s.H2, K = s.K;
+  const int in_dim = s.in_dim, in_pad = s.in_pad;
+  const int NQ = 2 * H2 + H2 * K;
+  const int n0 = min(N, crank * s.npc), n1 = min(N, n0 + s.npc), cnt = n1 - n0;
+  const int h0 = max(0, n0 - Wp), h1 = min(N, n1 + Wp);
+  const size_t gb = (size_t)b * N;
+
+  float* w1t = sm + L.prep + P.w1t;
+  float* u1 = sm + L.prep + P.u1;
+  float* w2 = sm + L.prep + P.w2;
+  float* u2 = sm + L.prep + P.u2;
+  float* s1 = sm + L.s1;
+  float* alpha = sm + L.alpha;
+  float* zs = sm + L.zs;
+  float* wts = sm + L.wts;
+  float* deg = sm + L.deg;
+  float* Sown = sm + L.S;
+  int* lab = reinterpret_cast<int*>(sm + L.lab);
+  float* red = sm + L.red;
+
+  // ---- P0: stage the prepared weights with one TMA bulk copy -------------------------------
+  if (tid == 0) {
+    mbar_init(sm, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)P.sizeA * 4u;
+    mbar_expect_tx(sm, bytes);
+    tma_bulk_g2s(sm + L.prep, A.prep, bytes, sm);
+  }
+  mbar_wait(sm, 0);
+
+  // ---- P1: attention scalars of the patch GAT for own + halo nodes ---------------------------
+  const TX* xg = reinterpret_cast<const TX*>(A.x) + gb * in_dim;
+  const bool vec_in = (in_dim & 3) == 0;
+  for (int t = tid; t < h1 - h0; t += kBT) {
+    const int n = h0 + t;
+    float acc[2 * kMaxHeads];
+#pragma unroll
+    for (int qq = 0; qq < 2 * kMaxHeads; ++qq) acc[qq] = 0.f;
+    const TX* row = xg + (size_t)n * in_dim;
+    for (int i = 0; i < in_dim; i += 4) {
+      float xv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec_in) {
+        load4<TX>(row + i, xv);
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (i + v < in_dim) xv[v] = to_f32<TX>(row[i + v]);
+      }
+#pragma unroll
+      for (int qq = 0; qq < 2 * kMaxHeads; ++qq) {
+        if (qq < 2 * H1) {
+          const float4 uv = *reinterpret_cast<const float4*>(u1 + qq * in_pad + i);
+          acc[qq] = fmaf(xv[0], uv.x, acc[qq]);
+          acc[qq] = fmaf(xv[1], uv.y, acc[qq]);
+          acc[qq] = fmaf(xv[2], uv.z, acc[qq]);
+          acc[qq] = fmaf(xv[3], uv.w, acc[qq]);
+        }
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < 2 * kMaxHeads; ++qq)
+      if (qq < 2 * H1) s1[t * 2 * H1 + qq] = acc[qq];
+  }
+  __syncthreads();
+
+  // per-image max of s_src[i] + s_tgt[j] over edges (graph_attention.py:86), per head
+  {
+    float m[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) m[h] = -INFINITY;
+    for (int t = tid; t < cnt; t += kBT) {
+      const int n = n0 + t;
+      int nb[4];
+      const int dg = grid_nbrs(n, Hp, Wp, nb);
+      for (int k = 0; k < dg; ++k)
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+          if (h < H1) m[h] = fmaxf(m[h], s1[(nb[k] - h0) * 2 * H1 + h] + s1[(n - h0) * 2 * H1 + H1 + h]);
+    }
+    block_reduce<true, kMaxHeads>(m, H1, red, sm + L.cmax1);
+  }
+  cluster.sync();                                                                   // #1
+  float M1[kMaxHeads];
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    float m = -INFINITY;
+    if (h < H1)
+      for (int r = 0; r < s.cluster; ++r) m = fmaxf(m, cluster.map_shared_rank(sm + L.cmax1, r)[h]);
+    M1[h] = leaky_relu(m, s.slope1);
+  }
+
+  // ---- P2: patch GAT for own nodes, tile by tile ----------------------------------------------
+  const int FG = D >> 2;                          // feature quads per node (power of two <= 32)
+  const int zs_stride = H1 * in_pad;
+  for (int tile = 0; tile < cnt; tile += kTileN) {
+    const int tn = min(kTileN, cnt - tile);
+    // (a) attention coefficients alpha[q][h][k]
+    for (int idx = tid; idx < tn * H1; idx += kBT) {
+      const int qn = idx / H1, h = idx - qn * H1;
+      const int n = n0 + tile + qn;
+      int nb[4];
+      const int dg = grid_nbrs(n, Hp, Wp, nb);
+      const float st = s1[(n - h0) * 2 * H1 + H1 + h];
+      const float mh = sel4(M1, h);
+      float p[4], den = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        p[k] = 0.f;
+        if (k < dg) {
+          p[k] = expf(leaky_relu(s1[(nb[k] - h0) * 2 * H1 + h] + st, s.slope1) - mh);
+          den += p[k];
+        }
+      }
+      const float dn = den + 1e-10f;                                               // graph_attention.py:96
+#pragma unroll
+      for (int k = 0; k < 4; ++k) alpha[(qn * H1 + h) * 4 + k] = p[k] / dn;
+    }
+    __syncthreads();
+    // (b) z[q][h][i] = sum_k alpha_k x[nbr_k][i]   (one gather of x serves every head)
+    const int IQ = in_pad >> 2;
+    for (int idx = tid; idx < tn * IQ; idx += kBT) {
+      const int qn = idx / IQ, i4 = (idx - qn * IQ) * 4;
+      const int n = n0 + tile + qn;
+      int nb[4];
+      const int dg = grid_nbrs(n, Hp, Wp, nb);
+      float xv[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) xv[k][v] = 0.f;
+        if (k < dg) {
+          const TX* row = xg + (size_t)nb[k] * in_dim + i4;
+          if (vec_in) {
+            load4<TX>(row, xv[k]);
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              if (i4 + v < in_dim) xv[k][v] = to_f32<TX>(row[v]);
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < kMaxHeads; ++h) {
+        if (h < H1) {
+          const float4 al = *reinterpret_cast<const float4*>(alpha + (qn * H1 + h) * 4);
+          float4 z;
+          z.x = fmaf(al.w, xv[3][0], fmaf(al.z, xv[2][0], fmaf(al.y, xv[1][0], al.x * xv[0][0])));
+          z.y = fmaf(al.w, xv[3][1], fmaf(al.z, xv[2][1], fmaf(al.y, xv[1][1], al.x * xv[0][1])));
+          z.z = fmaf(al.w, xv[3][2], fmaf(al.z, xv[2][2], fmaf(al.y, xv[1][2], al.x * xv[0][2])));
+          z.w = fmaf(al.w, xv[3][3], fmaf(al.z, xv[2][3], fmaf(al.y, xv[1][3], al.x * xv[0][3])));
+          *reinterpret_cast<float4*>(zs + (size_t)qn * zs_stride + h * in_pad + i4) = z;
+        }
+      }
+    }
+    // rows of the tile beyond tn must not feed garbage into the transform
+    for (int idx = tid + tn * zs_stride; idx < kTileN * zs_stride; idx += kBT) zs[idx] = 0.f;
+    __syncthreads();
+    // (c) h = mean_h ELU(W_h z_h); 4 nodes x 4 features per item; then the predictor scalars
+    //     q[n][v] = h_n . vec_v  (vec = u2 rows, W2 rows) reduced over the FG lanes of a node quad
+    const int items = (kTileN / 4) * FG;
+    const float inv_h = 1.f / (float)H1;
+    for (int it = tid; it < items; it += kBT) {
+      const int ng = it / FG, fg = it - ng * FG;
+      const int q0 = ng * 4, f0 = fg * 4;
+      float o[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[r][c] = 0.f;
+      for (int h = 0; h < H1; ++h) {
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        const float* wh = w1t + (size_t)h * in_pad * D + f0;
+        const float* zh = zs + (size_t)q0 * zs_stride + h * in_pad;
+        for (int i = 0; i < in_pad; i += 4) {
+          float4 zv[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) zv[r] = *reinterpret_cast<const float4*>(zh + (size_t)r * zs_stride + i);
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const float4 wv = *reinterpret_cast<const float4*>(wh + (size_t)(i + ii) * D);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const float zz = ii == 0 ? zv[r].x : (ii == 1 ? zv[r].y : (ii == 2 ? zv[r].z : zv[r].w));
+              acc[r][0] = fmaf(zz, wv.x, acc[r][0]);
+              acc[r][1] = fmaf(zz, wv.y, acc[r][1]);
+              acc[r][2] = fmaf(zz, wv.z, acc[r][2]);
+              acc[r][3] = fmaf(zz, wv.w, acc[r][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) o[r][c] += elu1(acc[r][c]);                  // ELU per head, then mean (:118,:158)
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[r][c] *= inv_h;
+        if (q0 + r < tn)
+          *reinterpret_cast<float4*>(A.h + (gb + n0 + tile + q0 + r) * D + f0) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
+      }
+      // predictor scalars
+      for (int v = 0; v < NQ; ++v) {
+        const float* vec = v < 2 * H2 ? u2 + v * D + f0 : w2 + (v - 2 * H2) * D + f0;
+        const float4 vv = *reinterpret_cast<const float4*>(vec);
+        float pr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) pr[r] = fmaf(o[r][3], vv.w, fmaf(o[r][2], vv.z, fmaf(o[r][1], vv.y, o[r][0] * vv.x)));
+        for (int off = FG >> 1; off > 0; off >>= 1) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) pr[r] += __shfl_xor_sync(kFull, pr[r], off);
+        }
+        if (fg == 0) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (q0 + r < tn) A.q[(gb + n0 + tile + q0 + r) * NQ + v] = pr[r];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cluster.sync();                                                                   // #2: h, q visible
+
+  // ---- P3: predictor max (per image, per head) + N-cut edge weights -----------------------------
+  const float* qg = A.q + gb * NQ;
+  const float* hg = A.h + gb * D;
+  {
+    float m[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) m[h] = -INFINITY;
+    for (int t = tid; t < cnt; t += kBT) {
+      const int n = n0 + t;
+      int nb[4];
+      const int dg = grid_nbrs(n, Hp, Wp, nb);
+      for (int k = 0; k < dg; ++k)
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+          if (h < H2) m[h] = fmaxf(m[h], __ldcg(qg + (size_t)nb[k] * NQ + h) + __ldcg(qg + (size_t)n * NQ + H2 + h));
+    }
+    block_reduce<true, kMaxHeads>(m, H2, red, sm + L.cmax2);
+  }
+  // w[n][k] = exp(-|h_n - h_nbr|^2 / 2) (mincut_refinement.py:43-51), warp per node
+  for (int t = warp; t < cnt; t += kBT / 32) {
+    const int n = n0 + t;
+    int nb[4];
+    const int dg = grid_nbrs(n, Hp, Wp, nb);
+    float d2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = lane * 2; d < D; d += 64) {
+      const float2 a = __ldcg(reinterpret_cast<const float2*>(hg + (size_t)n * D + d));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < dg) {
+          const float2 c = __ldcg(reinterpret_cast<const float2*>(hg + (size_t)nb[k] * D + d));
+          const float e0 = a.x - c.x, e1 = a.y - c.y;
+          d2[k] += e0 * e0 + e1 * e1;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d2[k] = warp_sum(d2[k]);
+    if (lane == 0) {
+      float dsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = k < dg ? expf(-d2[k] / 2.0f) : 0.f;
+        wts[t * 4 + k] = w;
+        dsum += w;
+      }
+      deg[t] = dsum;                                                               // degree by source (:92-96)
+    }
+  }
+  cluster.sync();                                                                   // #3
+  float M2[kMaxHeads];
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    float m = -INFINITY;
+    if (h < H2)
+      for (int r = 0; r < s.cluster; ++r) m = fmaxf(m, cluster.map_shared_rank(sm + L.cmax2, r)[h]);
+    M2[h] = leaky_relu(m, s.slope2);
+  }
+
+  // ---- P4: predictor GAT (transform-first: K scalars per head), softmax, argmax -------------------
+  const float inv_h2 = 1.f / (float)H2;
+  for (int t = tid; t < cnt; t += kBT) {
+    const int n = n0 + t;
+    int nb[4];
+    const int dg = grid_nbrs(n, Hp, Wp, nb);
+    float logit[kMaxSeg];
+#pragma unroll
+    for (int c = 0; c < kMaxSeg; ++c) logit[c] = 0.f;
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+      if (h >= H2) break;
+      const float st = __ldcg(qg + (size_t)n * NQ + H2 + h);
+      float p[4], den = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        p[k] = 0.f;
+        if (k < dg) {
+          p[k] = expf(leaky_relu(__ldcg(qg + (size_t)nb[k] * NQ + h) + st, s.slope2) - M2[h]);
+          den += p[k];
+        }
+      }
+      const float dn = den + 1e-10f;
+#pragma unroll
+      for (int c = 0; c < kMaxSeg; ++c) {
+        if (c < K) {
+          float agg = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < dg) agg = fmaf(p[k] / dn, __ldcg(qg + (size_t)nb[k] * NQ + 2 * H2 + h * K + c), agg);
+          logit[c] += elu1(agg);
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxSeg; ++c)
+      if (c < K) { logit[c] *= inv_h2; mx = fmaxf(mx, logit[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxSeg; ++c)
+      if (c < K) sum += expf(logit[c] - mx);
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxSeg; ++c) {
+      if (c < K) {
+        const float pc = expf(logit[c] - mx) / sum;                                // mincut_refinement.py:193
+        Sown[t * K + c] = pc;
+        A.S[(gb + n) * K + c] = pc;
+        if (pc > best) { best = pc; arg = c; }                                     // train_end_to_end.py:356
+      }
+    }
+    lab[t] = arg;
+    A.labels[gb + n] = arg;
+  }
+  cluster.sync();                                                                   // #4: S visible
+
+  // ---- P5: N-cut partial sums + region partial sums ------------------------------------------------
+  {
+    float va[kMaxSeg], vc[kMaxSeg], vn[kMaxSeg];          // assoc, cut, label counts
+#pragma unroll
+    for (int c = 0; c < kMaxSeg; ++c) va[c] = vc[c] = vn[c] = 0.f;
+    const float* Sg = A.S + gb * K;
+    for (int t = tid; t < cnt; t += kBT) {
+      const int n = n0 + t;
+      int nb[4];
+      const int dg = grid_nbrs(n, Hp, Wp, nb);
+      const float dgw = deg[t];
+      const int l = lab[t];
+#pragma unroll
+      for (int c = 0; c < kMaxSeg; ++c) {
+        if (c < K) {
+          const float sc = Sown[t * K + c];
+          va[c] += sc * dgw;                                                       // assoc (:102)
+          float cut = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < dg) cut += wts[t * 4 + k] * sc * (1.f - __ldcg(Sg + (size_t)nb[k] * K + c));   // (:112-113,149)
+          vc[c] += cut;
+          vn[c] += (l == c) ? 1.f : 0.f;
+        }
+      }
+    }
+    block_reduce<false, kMaxSeg>(va, K, red, sm + L.exp_part);
+    block_reduce<false, kMaxSeg>(vc, K, red, sm + L.exp_part + K);
+    block_reduce<false, kMaxSeg>(vn, K, red, sm + L.exp_rcnt);                     // exact: counts < 2^24
+  }
+  {
+    // region sums: thread (sub, d) walks own nodes sub, sub+NS, ... and adds h[n][d] to its label's slot
+    float* rsum = sm + L.exp_rsum;
+    const int NS = kBT / D > 0 ? kBT / D : 1;            // node subsets (D <= 256)
+    const int d = tid % D, sub = tid / D;
+    float acc[kMaxSeg];
+#pragma unroll
+    for (int c = 0; c < kMaxSeg; ++c) acc[c] = 0.f;
+    if (sub < NS) {
+      for (int t = sub; t < cnt; t += NS) {
+        const float hv = __ldcg(hg + (size_t)(n0 + t) * D + d);
+        const int l = lab[t];
+#pragma unroll
+        for (int c = 0; c < kMaxSeg; ++c) acc[c] += (l == c) ? hv : 0.f;
+      }
+    }
+    // combine the NS subsets in fixed order through the (now free) zs scratch (size checked on host)
+    float* scr = zs;
+    if (sub < NS) {
+#pragma unroll
+      for (int c = 0; c < kMaxSeg; ++c)
+        if (c < K) scr[(sub * K + c) * D + d] = acc[c];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < K * D; idx += kBT) {
+      float t = 0.f;
+      for (int sb = 0; sb < NS; ++sb) t += scr[sb * K * D + idx];
+      rsum[idx] = t;
+    }
+  }
+  cluster.sync();                                                                   // #5: partials exported
+
+  // ---- P6 (rank 0): loss, region means, region GAT on the complete digraph -------------------------
+  if (crank == 0) {
+    const int H3 = s.H3;
+    float* R = sm + L.region;
+    float* s3 = R + K * D;
+    float* a3 = s3 + round_up4(K * 2 * H3);
+    float* z3 = a3 + round_up4(K * H3 * K);
+    float* y3 = z3 + K * H3 * D;
+    const float* w3t = A.prep + P.w3t;
+    const float* u3 = A.prep + P.u3;
+    if (tid == 0) {
+      float l = 0.f;
+      for (int c = 0; c < K; ++c) {
+        float assoc = 0.f, cut = 0.f;
+        for (int r = 0; r < s.cluster; ++r) {
+          const float* part = cluster.map_shared_rank(sm + L.exp_part, r);
+          assoc += part[c];
+          cut += part[K + c];
+        }
+        if (assoc > 1e-8f) l += cut / assoc;                                       // mincut_refinement.py:151-152
+      }
+      A.loss[b] = l;
+    }
+    for (int idx = tid; idx < K * D; idx += kBT) {
+      const int c = idx / D;
+      float t = 0.f, n = 0.f;
+      for (int r = 0; r < s.cluster; ++r) {
+        t += cluster.map_shared_rank(sm + L.exp_rsum, r)[idx];
+        n += cluster.map_shared_rank(sm + L.exp_rcnt, r)[c];
+      }
+      const float m = n > 0.f ? t / n : 0.f;                                  // train_end_to_end.py:368-373
+      R[idx] = m;
+      if (A.region_in) A.region_in[(size_t)b * K * D + idx] = m;
+    }
+    __syncthreads();
+    if (K > 1) {
+      // scores
+      for (int idx = tid; idx < K * 2 * H3; idx += kBT) {
+        const int k = idx / (2 * H3), qq = idx - k * 2 * H3;
+        float acc = 0.f;
+        for (int i = 0; i < D; ++i) acc = fmaf(R[k * D + i], __ldg(u3 + qq * D + i), acc);
+        s3[idx] = acc;
+      }
+      __syncthreads();
+      // attention over in-edges (sources ascending, skipping the node itself)
+      for (int idx = tid; idx < K * H3; idx += kBT) {
+        const int j = idx / H3, h = idx - j * H3;
+        float m = -INFINITY;
+        for (int jj = 0; jj < K; ++jj)
+          for (int i = 0; i < K; ++i)
+            if (i != jj) m = fmaxf(m, s3[i * 2 * H3 + h] + s3[jj * 2 * H3 + H3 + h]);
+        const float M3 = leaky_relu(m, s.slope3);
+        float den = 0.f;
+        for (int i = 0; i < K; ++i) {
+          float p = 0.f;
+          if (i != j) {
+            p = expf(leaky_relu(s3[i * 2 * H3 + h] + s3[j * 2 * H3 + H3 + h], s.slope3) - M3);
+            den += p;
+          }
+          a3[(j * H3 + h) * K + i] = p;
+        }
+        const float dn = den + 1e-10f;
+        for (int i = 0; i < K; ++i) a3[(j * H3 + h) * K + i] /= dn;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < K * H3 * D; idx += kBT) {
+        const int i = idx % D, jh = idx / D, j = jh / H3;
+        float acc = 0.f;
+        for (int src = 0; src < K; ++src)
+          if (src != j) acc = fmaf(a3[jh * K + src], R[src * D + i], acc);
+        z3[idx] = acc;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < K * H3 * D; idx += kBT) {
+        const int f = idx % D, jh = idx / D, h = jh % H3;
+        const float* wcol = w3t + (size_t)h * D * D + f;
+        const float* zr = z3 + (size_t)jh * D;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int i = 0; i < D; i += 4) {
+          acc0 = fmaf(zr[i], __ldg(wcol + (size_t)i * D), acc0);
+          acc1 = fmaf(zr[i + 1], __ldg(wcol + (size_t)(i + 1) * D), acc1);
+          acc2 = fmaf(zr[i + 2], __ldg(wcol + (size_t)(i + 2) * D), acc2);
+          acc3 = fmaf(zr[i + 3], __ldg(wcol + (size_t)(i + 3) * D), acc3);
+        }
+        y3[idx] = elu1((acc0 + acc1) + (acc2 + acc3));
+      }
+      __syncthreads();
+      const float inv_h3 = 1.f / (float)H3;
+      for (int idx = tid; idx < K * D; idx += kBT) {
+        const int j = idx / D, f = idx - j * D;
+        float t = 0.f;
+        for (int h = 0; h < H3; ++h) t += y3[(j * H3 + h) * D + f];
+        A.region_out[(size_t)b * K * D + idx] = t * inv_h3;
+      }
+    } else {
+      for (int idx = tid; idx < K * D; idx += kBT) A.region_out[(size_t)b * K * D + idx] = R[idx];   // :387-389 passthrough
+    }
+  }
+  cluster.sync();                                                                   // #6: keep remote smem alive
+}
+
+static bool shape_supported(const BlockShape& s, const char** why) {
+  *why = nullptr;
+  if (s.in_dim < 1 || s.in_dim > 64) *why = "node feature width must be in [1, 64]";
+  else if (s.D != 32 && s.D != 64 && s.D != 128) *why = "GAT output width must be 32, 64 or 128";
+  else if (s.H1 < 1 || s.H1 > kMaxHeads || s.H2 < 1 || s.H2 > kMaxHeads || s.H3 < 1 || s.H3 > kMaxHeads) *why = "heads must be in [1, 4]";
+  else if (s.K < 1 || s.K > kMaxSeg) *why = "num_segments must be in [1, 8]";
+  else if (s.Hp * s.Wp < 2) *why = "a 1x1 patch grid has no edges";
+  return *why == nullptr;
+}
+
+static int plan_cluster(BlockShape* s) {
+  // smallest cluster (power of two <= 8) with <= 256 nodes per CTA, else 8
+  int c = 1;
+  while (c < kMaxCluster && ceil_div(s->N, c) > 256) c <<= 1;
+  // prefer filling the machine when the batch is small
+  while (c < kMaxCluster && s->B * c * 2 <= num_sms() && ceil_div(s->N, c * 2) >= 64) c <<= 1;
+  s->cluster = c;
+  s->npc = ceil_div(s->N, c);
+  return c;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+static void fill_shape(BlockShape* s, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K, float sl1,
+                       float sl2, float sl3) {
+  s->B = B; s->Hp = Hp; s->Wp = Wp; s->N = Hp * Wp;
+  s->in_dim = in_dim; s->in_pad = round_up4(in_dim); s->D = D;
+  s->H1 = H1; s->H2 = H2; s->H3 = H3; s->K = K;
+  s->slope1 = sl1; s->slope2 = sl2; s->slope3 = sl3;
+  s->cluster = 1; s->npc = s->N;
+}
+
+extern "C" {
+
+int64_t mg_block_prep_floats(int in_dim, int D, int H1, int H2, int H3, int K) {
+  BlockShape s;
+  fill_shape(&s, 1, 2, 2, in_dim, D, H1, H2, H3, K, 0.2f, 0.2f, 0.2f);
+  return prep_layout(s).total;
+}
+
+int mg_block_supported(int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K) {
+  BlockShape s;
+  fill_shape(&s, B, Hp, Wp, in_dim, D, H1, H2, H3, K, 0.2f, 0.2f, 0.2f);
+  const char* why;
+  if (B < 1 || Hp < 1 || Wp < 1 || !shape_supported(s, &why)) return 0;
+  plan_cluster(&s);
+  if ((int64_t)smem_layout(s).total * 4 > 200 * 1024) return 0;
+  if ((kBT / s.D > 0 ? kBT / s.D : 1) * s.K * s.D > kTileN * s.H1 * s.in_pad) return 0;   // region scratch fits in zs
+  return 1;
+}
+
+int mg_block_prepare(const float* W1, const float* a1, const float* W2, const float* a2, const float* W3, const float* a3,
+                     int in_dim, int D, int H1, int H2, int H3, int K, float* prep, mg_stream_t stream) {
+  MG_REQUIRE(W1 && a1 && W2 && a2 && W3 && a3 && prep, MG_ERR_INVALID, "mg_block_prepare: null pointer");
+  BlockShape s;
+  fill_shape(&s, 1, 2, 2, in_dim, D, H1, H2, H3, K, 0.2f, 0.2f, 0.2f);
+  const char* why;
+  MG_REQUIRE(shape_supported(s, &why), MG_ERR_UNSUPPORTED, "mg_block_prepare: %s", why);
+  const int total = prep_layout(s).total;
+  block_prepare_kernel<<<std::min(ceil_div(total, 256), num_sms() * 4), 256, 0, (cudaStream_t)stream>>>(s, W1, a1, W2, a2, W3,
+                                                                                                    a3, prep);
+  return check_launch("block_prepare_kernel");
+}
+
+int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K,
+                     float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work, float* S,
+                     int32_t* labels, float* loss, float* region_in, float* region_out, mg_stream_t stream) {
+  MG_REQUIRE(x && prep && h && q_work && S && labels && loss && region_out, MG_ERR_INVALID, "mg_block_forward: null pointer");
+  MG_REQUIRE(B > 0 && Hp > 0 && Wp > 0, MG_ERR_INVALID, "mg_block_forward: bad sizes");
+  MG_REQUIRE(x_dtype == MG_F32 || x_dtype == MG_BF16, MG_ERR_INVALID, "mg_block_forward: x dtype");
+  MG_REQUIRE(slope1 >= 0.f && slope2 >= 0.f && slope3 >= 0.f, MG_ERR_UNSUPPORTED, "mg_block_forward: negative LeakyReLU slope");
+  BlockShape s;
+  fill_shape(&s, B, Hp, Wp, in_dim, D, H1, H2, H3, K, slope1, slope2, slope3);
+  const char* why;
+  MG_REQUIRE(shape_supported(s, &why), MG_ERR_UNSUPPORTED, "mg_block_forward: %s", why);
+  MG_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)prep % 16 == 0) && ((uintptr_t)h % 16 == 0), MG_ERR_INVALID,
+             "mg_block_forward: x, prep and h must be 16-byte aligned");
+  plan_cluster(&s);
+  const SmemLayout L = smem_layout(s);
+  const size_t smem = (size_t)L.total * 4;
+  MG_REQUIRE(smem <= 200 * 1024, MG_ERR_UNSUPPORTED, "mg_block_forward: image too large for the fused kernel (%zu B smem)", smem);
+  MG_REQUIRE((kBT / s.D > 0 ? kBT / s.D : 1) * s.K * s.D <= kTileN * s.H1 * s.in_pad, MG_ERR_UNSUPPORTED,
+             "mg_block_forward: region scratch does not fit");
+  BlockArgs A;
+  A.s = s; A.x = x; A.prep = prep; A.h = h; A.q = q_work; A.S = S; A.labels = labels; A.loss = loss;
+  A.region_in = region_in; A.region_out = region_out;
+
+  auto kern = x_dtype == MG_F32 ? block_forward_kernel<float> : block_forward_kernel<__nv_bfloat16>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    set_error("mg_block_forward: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+    return MG_ERR_CUDA;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * s.cluster), 1, 1);
+  cfg.blockDim = dim3(kBT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)s.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, A);
+  if (e != cudaSuccess) {
+    set_error("block_forward_kernel: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return MG_ERR_CUDA;
+  }
+  return check_launch("block_forward_kernel");
+}
+
+}  // extern "C"

@@ -260,3 +260,49 @@ def ncut_loss(h: torch.Tensor, S: torch.Tensor, rowptr_out: torch.Tensor, col_ou
         call("mg_ncut_loss", h.data_ptr(), S.data_ptr(), rowptr_out.data_ptr(), col_out.data_ptr(), N, D, K,
              int(nodes_per_graph), loss.data_ptr(), work.data_ptr(), _stream())
     return loss
+
+
+# ---------------------------------------------------------------------------------------------
+# fused per-image block
+# ---------------------------------------------------------------------------------------------
+def block_supported(B: int, Hp: int, Wp: int, in_dim: int, D: int, H1: int, H2: int, H3: int, K: int) -> bool:
+    return bool(_lib.load().mg_block_supported(B, Hp, Wp, in_dim, D, H1, H2, H3, K))
+
+
+def block_prepare(W1, a1, W2, a2, W3, a3, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Re-arrange the three GAT nets' weights for ``block_forward`` (once per weight version).
+    ``out``: refresh an existing blob in place (keeps captured CUDA graphs valid)."""
+    _need_cuda(W1, a1, W2, a2, W3, a3)
+    H1, D, in_dim = W1.shape
+    H2, K, _ = W2.shape
+    H3 = W3.shape[0]
+    ws = [t.detach().contiguous().float() for t in (W1, a1, W2, a2, W3, a3)]
+    n = int(_lib.load().mg_block_prep_floats(in_dim, D, H1, H2, H3, K))
+    prep = out if out is not None and out.numel() == n and out.device == W1.device else \
+        torch.empty(n, dtype=torch.float32, device=W1.device)
+    with torch.cuda.device(W1.device):
+        call("mg_block_prepare", *[w.data_ptr() for w in ws], in_dim, D, H1, H2, H3, K, prep.data_ptr(), _stream())
+    return prep
+
+
+def block_forward(x: torch.Tensor, Hp: int, Wp: int, prep: torch.Tensor, D: int, H1: int, H2: int, H3: int, K: int,
+                  slopes=(0.2, 0.2, 0.2), want_region_in: bool = False):
+    """One launch for the whole per-image pipeline.  ``x (B,N,in)`` f32|bf16.  Returns
+    ``h (B,N,D), S (B,N,K), labels (B,N) int32, loss (B,), region_in|None, region_out (B,K,D)``."""
+    _need_cuda(x, prep)
+    x = x.contiguous()
+    B, N, in_dim = x.shape
+    dev = x.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    h = torch.empty((B, N, D), **f32)
+    q = torch.empty((B, N, 2 * H2 + H2 * K), **f32)
+    S = torch.empty((B, N, K), **f32)
+    labels = torch.empty((B, N), dtype=torch.int32, device=dev)
+    loss = torch.empty(B, **f32)
+    rin = torch.empty((B, K, D), **f32) if want_region_in else None
+    rout = torch.empty((B, K, D), **f32)
+    with torch.cuda.device(dev):
+        call("mg_block_forward", x.data_ptr(), _dtype_code(x.dtype), B, Hp, Wp, in_dim, D, H1, H2, H3, K,
+             float(slopes[0]), float(slopes[1]), float(slopes[2]), prep.data_ptr(), h.data_ptr(), q.data_ptr(),
+             S.data_ptr(), labels.data_ptr(), loss.data_ptr(), _ptr(rin), rout.data_ptr(), _stream())
+    return h, S, labels, loss, rin, rout

@@ -167,7 +167,9 @@ def test_gat_sweep_shapes_vs_oracle(mg, N, k, fin, fout, heads):
     with torch.no_grad():
         yb = layer(x.cuda().bfloat16(), ei.cuda())
     assert yb.dtype == torch.bfloat16
-    assert maxabs(yb, ref) <= BF16_TOL
+    # "identical inputs": the fp32 oracle sees the same bf16-rounded features
+    refb = O.gat_layer(x.bfloat16().float(), ei, Ws, As, 0.2, concat=False)
+    assert maxabs(yb, refb) <= BF16_TOL
 
 
 def test_gat_batched_per_graph_max(mg):
@@ -306,8 +308,9 @@ def test_unpool_bit_exact_vs_torch_nearest(mg, H, W, p):
 # ---------------------------------------------------------------------------------------------
 # whole block
 # ---------------------------------------------------------------------------------------------
-def _block_from_params(mg, params, in_dim, K):
+def _block_from_params(mg, params, in_dim, K, fused=True):
     blk = mg.GraphBlock(node_feature_dim=in_dim, num_segments=K)
+    blk.fused = fused
     load_heads(blk.patch_gat_model, params["patch_W"], params["patch_a"])
     load_heads(blk.segment_predictor.gnn_predictor, params["pred_W"], params["pred_a"])
     load_heads(blk.region_gat_model, params["region_W"], params["region_a"])
@@ -335,12 +338,13 @@ def _check_block(out, refs, tol, dense_tol):
     return B
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("tag", ["64x64", "128x96", "70x75", "256x256"])
-def test_block_golden_per_image(mg, golden, tag):
+def test_block_golden_per_image(mg, golden, tag, fused):
     g = golden("block_images.npz")
     H, W, in_dim, K, nph, npw = (int(v) for v in g[f"{tag}_meta"])
     params = {f"{n}_{p}": torch.from_numpy(g[f"{tag}_{n}_{p}"]) for n in ("patch", "pred", "region") for p in ("W", "a")}
-    blk = _block_from_params(mg, params, in_dim, K)
+    blk = _block_from_params(mg, params, in_dim, K, fused)
     with torch.no_grad():
         out = blk(node_features=T(g[f"{tag}_x"]).unsqueeze(0), image_size=(H, W), out_dtype=torch.float32)
     assert out.grid == (nph, npw)
@@ -354,13 +358,15 @@ def test_block_golden_per_image(mg, golden, tag):
         assert maxabs(out.f_g[0], T(g[f"{tag}_fg"])) <= FP32_TOL
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("B,H,W,K,dtype", [(4, 128, 128, 2, torch.float32), (3, 70, 75, 3, torch.float32),
-                                           (16, 512, 512, 2, torch.bfloat16), (2, 1024, 1024, 2, torch.bfloat16)])
-def test_block_batched_vs_oracle(mg, B, H, W, K, dtype):
+                                           (16, 512, 512, 2, torch.bfloat16), (2, 1024, 1024, 2, torch.bfloat16),
+                                           (5, 48, 16, 1, torch.float32), (2, 200, 40, 8, torch.float32)])
+def test_block_batched_vs_oracle(mg, B, H, W, K, dtype, fused):
     """BASELINE configs 2 (512^2 x 16, bf16) and 3 (1024^2 shard) plus fp32 / padded-grid cases."""
     in_dim = 20
     params = O.init_block_params(in_dim, 64, 4, K, seed=1234)
-    blk = _block_from_params(mg, params, in_dim, K)
+    blk = _block_from_params(mg, params, in_dim, K, fused)
     nph, npw = O.grid_dims(H, W)
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(B, nph * npw, in_dim, generator=gen)
@@ -377,6 +383,49 @@ def test_block_batched_vs_oracle(mg, B, H, W, K, dtype):
         fp = torch.gather(out.region_features, 1, out.hard_labels.long().unsqueeze(-1).expand(-1, -1, 64))
         dense = fp.transpose(1, 2).reshape(B, 64, nph, 1, npw, 1).expand(B, 64, nph, 16, npw, 16).reshape(B, 64, H, W)
         assert torch.equal(out.f_g, dense.to(dtype))
+
+
+def test_block_fused_is_one_launch(mg):
+    """The fused path really is taken: block = 1 launch (+1 un-pool), weights prepared once."""
+    from mingraph_unet_b200 import _lib
+    params = O.init_block_params(20, 64, 4, 2, seed=1)
+    blk = _block_from_params(mg, params, 20, 2)
+    x = torch.randn(4, 64, 20, device="cuda")
+    with torch.no_grad():
+        blk(node_features=x, image_size=(128, 128))            # first call prepares the weights
+        n0 = _lib.launch_count()
+        out = blk(node_features=x, image_size=(128, 128))
+        assert _lib.launch_count() - n0 == 2
+        blk.fused = False
+        n0 = _lib.launch_count()
+        out2 = blk(node_features=x, image_size=(128, 128))
+        assert _lib.launch_count() - n0 > 10
+        # a weight update invalidates the prepared blob
+        blk.fused = True
+        blk.patch_gat_model.gat_layers[0].heads[0].W.weight.mul_(1.5)
+        out3 = blk(node_features=x, image_size=(128, 128))
+    assert maxabs(out.patch_features, out2.patch_features) <= FP32_TOL
+    assert maxabs(out.region_features, out2.region_features) <= FP32_TOL
+    assert maxabs(out3.patch_features, out.patch_features) > 1e-3
+
+
+@pytest.mark.parametrize("in_dim,D,heads,K", [(12, 32, 2, 3), (64, 128, 4, 2), (7, 64, 1, 4), (32, 64, 3, 2)])
+def test_block_fused_other_widths(mg, in_dim, D, heads, K):
+    B, H, W = 3, 80, 112
+    nph, npw = O.grid_dims(H, W)
+    params = O.init_block_params(in_dim, D, heads, K, seed=in_dim)
+    blk = mg.GraphBlock(node_feature_dim=in_dim, gat_output_dim=D, num_heads=heads, num_segments=K)
+    load_heads(blk.patch_gat_model, params["patch_W"], params["patch_a"])
+    load_heads(blk.segment_predictor.gnn_predictor, params["pred_W"], params["pred_a"])
+    load_heads(blk.region_gat_model, params["region_W"], params["region_a"])
+    blk = blk.cuda().eval()
+    # (64,128,4,2) needs 128 KB of weights + 128 KB of tile: beyond the fused kernel's budget -> composed path
+    assert mg.ops.block_supported(B, nph, npw, in_dim, D, heads, max(1, heads // 2), heads, K) == (D < 128)
+    x = torch.randn(B, nph * npw, in_dim, generator=torch.Generator().manual_seed(1))
+    refs = [O.graph_block_image(x[b], H, W, params, K=K) for b in range(B)]
+    with torch.no_grad():
+        out = blk(node_features=x.cuda(), image_size=(H, W))
+    _check_block(out, refs, FP32_TOL, FP32_TOL)
 
 
 def test_block_feature_map_input(mg):
