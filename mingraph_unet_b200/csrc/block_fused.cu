@@ -22,11 +22,12 @@ namespace cg = cooperative_groups;
 
 namespace mg {
 
-constexpr int kBT = 256;          // threads per CTA
+constexpr int kBT = 512;          // threads per CTA
 constexpr int kTileN = 128;       // nodes per aggregation/transform tile
 constexpr int kMaxHeads = 4;
 constexpr int kMaxSeg = 8;        // K
 constexpr int kMaxCluster = 8;
+constexpr int kSmemMax = 220 * 1024;  // dynamic shared memory budget per CTA (227 KB max on sm_100a)
 
 struct BlockShape {
   int B, Hp, Wp, N;               // images, patch grid, nodes per image
@@ -59,21 +60,24 @@ __host__ __device__ inline PrepLayout prep_layout(const BlockShape& s) {
 
 // shared-memory layout of the main kernel (float offsets)
 struct SmemLayout {
-  int prep, s1, alpha, zs, wts, deg, S, lab, red, cmax1, cmax2, exp_part, exp_rsum, exp_rcnt, region, total;
+  int prepA, prepB, s1, alpha, zs, tmp, wts, deg, S, lab, red, cmax1, cmax2, exp_part, exp_rsum, exp_rcnt, region, total;
 };
+__host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ inline SmemLayout smem_layout(const BlockShape& s) {
   const PrepLayout p = prep_layout(s);
   SmemLayout L;
-  int o = 4;                                    // [0..1] mbarrier (8 bytes), keep 16-byte alignment
-  L.prep = o;     o += p.sizeA;
+  int o = 4;                                    // [0..3]: two mbarriers (8 bytes each)
+  L.prepA = o;    o += p.sizeA;
+  L.prepB = o;    o += p.total - p.sizeA;       // W3t | u3 (used by the cluster's rank-0 CTA)
   L.s1 = o;       o += round_up4((s.npc + 2 * s.Wp) * 2 * s.H1);
   L.alpha = o;    o += kTileN * s.H1 * 4;
   L.zs = o;       o += kTileN * s.H1 * s.in_pad;
+  L.tmp = o;      o += round_up4(imax(imax(s.npc * s.H2 * s.K, 3 * s.npc * s.K), (kBT / s.D) * s.K * s.D));
   L.wts = o;      o += s.npc * 4;
   L.deg = o;      o += round_up4(s.npc);
   L.S = o;        o += round_up4(s.npc * s.K);
   L.lab = o;      o += round_up4(s.npc);
-  L.red = o;      o += 8 * 64;                  // block reductions: 8 warps x up to 64 values
+  L.red = o;      o += (kBT / 32) * 8;          // block reductions: per-warp partials of up to 8 values
   L.cmax1 = o;    o += 4;
   L.cmax2 = o;    o += 4;
   L.exp_part = o; o += round_up4(2 * s.K);
@@ -181,20 +185,25 @@ __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, flo
   o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
 }
 
-// in-neighbours of grid node n in ascending COO edge id: up, left, right, down
-__device__ __forceinline__ int grid_nbrs(int n, int Hp, int Wp, int* nb) {
+// In-neighbours of grid node n in ascending COO edge id: slot 0 up, 1 left, 2 right, 3 down.
+// Fixed slots with a validity flag keep every index static (no local-memory arrays).
+struct Nbr {
+  int id[4];
+  bool ok[4];
+};
+__device__ __forceinline__ Nbr grid_nbrs(int n, int Hp, int Wp) {
   const int r = n / Wp, c = n - r * Wp;
-  int k = 0;
-  if (r > 0) nb[k++] = n - Wp;
-  if (c > 0) nb[k++] = n - 1;
-  if (c + 1 < Wp) nb[k++] = n + 1;
-  if (r + 1 < Hp) nb[k++] = n + Wp;
-  return k;
+  Nbr b;
+  b.ok[0] = r > 0;        b.id[0] = b.ok[0] ? n - Wp : n;
+  b.ok[1] = c > 0;        b.id[1] = b.ok[1] ? n - 1 : n;
+  b.ok[2] = c + 1 < Wp;   b.id[2] = b.ok[2] ? n + 1 : n;
+  b.ok[3] = r + 1 < Hp;   b.id[3] = b.ok[3] ? n + Wp : n;
+  return b;
 }
 
-// deterministic block reduction of nv (<= MAXV) per-thread values; result in out[0..nv)
+// deterministic block reduction of nv (<= MAXV <= 8) per-thread values; result in out[0..nv)
 template <bool IS_MAX, int MAXV>
-__device__ __forceinline__ void block_reduce(const float (&v)[MAXV], int nv, float* red /* [8][64] */, float* out) {
+__device__ __forceinline__ void block_reduce(const float (&v)[MAXV], int nv, float* red /* [warps][8] */, float* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -205,14 +214,13 @@ __device__ __forceinline__ void block_reduce(const float (&v)[MAXV], int nv, flo
         const float u = __shfl_xor_sync(kFull, t, o);
         t = IS_MAX ? fmaxf(t, u) : t + u;
       }
-      if (lane == 0) red[warp * 64 + i] = t;
+      if (lane == 0) red[warp * 8 + i] = t;
     }
   }
   __syncthreads();
   if ((int)threadIdx.x < nv) {
     float t = red[threadIdx.x];
-#pragma unroll
-    for (int w = 1; w < kBT / 32; ++w) t = IS_MAX ? fmaxf(t, red[w * 64 + threadIdx.x]) : t + red[w * 64 + threadIdx.x];
+    for (int w = 1; w < kBT / 32; ++w) t = IS_MAX ? fmaxf(t, red[w * 8 + threadIdx.x]) : t + red[w * 8 + threadIdx.x];
     out[threadIdx.x] = t;
   }
   __syncthreads();
@@ -225,6 +233,10 @@ __device__ __forceinline__ float sel4(const float (&a)[kMaxHeads], int h) {
   return v;
 }
 
+// ELU(alpha=1).  exp(v)-1 instead of expm1: the absolute error (<= 1 ulp of 1 = 6e-8) is what the
+// 1e-5 parity budget is about, and it is a third of the instructions.
+__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : expf(v) - 1.f; }
+
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
   const SmemLayout L = smem_layout(s);
   const PrepLayout P = prep_layout(s);
   extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int crank = (int)cluster.block_rank();
   const int b = blockIdx.x / s.cluster;
   const int N = s.N, Hp = s.Hp, Wp = s.Wp, D = s.D, H1 = s.H1, H2 = s.H2, K = s.K;
@@ -245,31 +257,40 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
   const int h0 = max(0, n0 - Wp), h1 = min(N, n1 + Wp);
   const size_t gb = (size_t)b * N;
 
-  float* w1t = sm + L.prep + P.w1t;
-  float* u1 = sm + L.prep + P.u1;
-  float* w2 = sm + L.prep + P.w2;
-  float* u2 = sm + L.prep + P.u2;
+  float* w1t = sm + L.prepA + P.w1t;
+  float* u1 = sm + L.prepA + P.u1;
+  float* w2 = sm + L.prepA + P.w2;
+  float* u2 = sm + L.prepA + P.u2;
   float* s1 = sm + L.s1;
   float* alpha = sm + L.alpha;
   float* zs = sm + L.zs;
+  float* tmp = sm + L.tmp;
   float* wts = sm + L.wts;
   float* deg = sm + L.deg;
   float* Sown = sm + L.S;
   int* lab = reinterpret_cast<int*>(sm + L.lab);
   float* red = sm + L.red;
+  void* barA = sm;
+  void* barB = sm + 2;
 
-  // ---- P0: stage the prepared weights with one TMA bulk copy -------------------------------
+  // ---- P0: stage the prepared weights with TMA bulk copies (region weights only on rank 0) ------
   if (tid == 0) {
-    mbar_init(sm, 1);
+    mbar_init(barA, 1);
+    mbar_init(barB, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (tid == 0) {
-    const uint32_t bytes = (uint32_t)P.sizeA * 4u;
-    mbar_expect_tx(sm, bytes);
-    tma_bulk_g2s(sm + L.prep, A.prep, bytes, sm);
+    const uint32_t bytesA = (uint32_t)P.sizeA * 4u;
+    mbar_expect_tx(barA, bytesA);
+    tma_bulk_g2s(sm + L.prepA, A.prep, bytesA, barA);
+    if (crank == 0) {
+      const uint32_t bytesB = (uint32_t)(P.total - P.sizeA) * 4u;
+      mbar_expect_tx(barB, bytesB);
+      tma_bulk_g2s(sm + L.prepB, A.prep + P.sizeA, bytesB, barB);
+    }
   }
-  mbar_wait(sm, 0);
+  mbar_wait(barA, 0);
 
   // ---- P1: attention scalars of the patch GAT for own + halo nodes ---------------------------
   const TX* xg = reinterpret_cast<const TX*>(A.x) + gb * in_dim;
@@ -293,10 +314,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
       for (int qq = 0; qq < 2 * kMaxHeads; ++qq) {
         if (qq < 2 * H1) {
           const float4 uv = *reinterpret_cast<const float4*>(u1 + qq * in_pad + i);
-          acc[qq] = fmaf(xv[0], uv.x, acc[qq]);
-          acc[qq] = fmaf(xv[1], uv.y, acc[qq]);
-          acc[qq] = fmaf(xv[2], uv.z, acc[qq]);
-          acc[qq] = fmaf(xv[3], uv.w, acc[qq]);
+          acc[qq] = fmaf(xv[3], uv.w, fmaf(xv[2], uv.z, fmaf(xv[1], uv.y, fmaf(xv[0], uv.x, acc[qq]))));
         }
       }
     }
@@ -313,12 +331,12 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
     for (int h = 0; h < kMaxHeads; ++h) m[h] = -INFINITY;
     for (int t = tid; t < cnt; t += kBT) {
       const int n = n0 + t;
-      int nb[4];
-      const int dg = grid_nbrs(n, Hp, Wp, nb);
-      for (int k = 0; k < dg; ++k)
+      const Nbr nb = grid_nbrs(n, Hp, Wp);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int h = 0; h < kMaxHeads; ++h)
-          if (h < H1) m[h] = fmaxf(m[h], s1[(nb[k] - h0) * 2 * H1 + h] + s1[(n - h0) * 2 * H1 + H1 + h]);
+          if (h < H1 && nb.ok[k]) m[h] = fmaxf(m[h], s1[(nb.id[k] - h0) * 2 * H1 + h] + s1[(n - h0) * 2 * H1 + H1 + h]);
     }
     block_reduce<true, kMaxHeads>(m, H1, red, sm + L.cmax1);
   }
@@ -337,26 +355,21 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
   const int zs_stride = H1 * in_pad;
   for (int tile = 0; tile < cnt; tile += kTileN) {
     const int tn = min(kTileN, cnt - tile);
-    // (a) attention coefficients alpha[q][h][k]
+    // (a) attention coefficients alpha[q][h][slot]
     for (int idx = tid; idx < tn * H1; idx += kBT) {
       const int qn = idx / H1, h = idx - qn * H1;
       const int n = n0 + tile + qn;
-      int nb[4];
-      const int dg = grid_nbrs(n, Hp, Wp, nb);
+      const Nbr nb = grid_nbrs(n, Hp, Wp);
       const float st = s1[(n - h0) * 2 * H1 + H1 + h];
       const float mh = sel4(M1, h);
       float p[4], den = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        p[k] = 0.f;
-        if (k < dg) {
-          p[k] = expf(leaky_relu(s1[(nb[k] - h0) * 2 * H1 + h] + st, s.slope1) - mh);
-          den += p[k];
-        }
+        p[k] = nb.ok[k] ? expf(leaky_relu(s1[(nb.id[k] - h0) * 2 * H1 + h] + st, s.slope1) - mh) : 0.f;
+        den += p[k];
       }
       const float dn = den + 1e-10f;                                               // graph_attention.py:96
-#pragma unroll
-      for (int k = 0; k < 4; ++k) alpha[(qn * H1 + h) * 4 + k] = p[k] / dn;
+      *reinterpret_cast<float4*>(alpha + (qn * H1 + h) * 4) = make_float4(p[0] / dn, p[1] / dn, p[2] / dn, p[3] / dn);
     }
     __syncthreads();
     // (b) z[q][h][i] = sum_k alpha_k x[nbr_k][i]   (one gather of x serves every head)
@@ -364,15 +377,14 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
     for (int idx = tid; idx < tn * IQ; idx += kBT) {
       const int qn = idx / IQ, i4 = (idx - qn * IQ) * 4;
       const int n = n0 + tile + qn;
-      int nb[4];
-      const int dg = grid_nbrs(n, Hp, Wp, nb);
+      const Nbr nb = grid_nbrs(n, Hp, Wp);
       float xv[4][4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) xv[k][v] = 0.f;
-        if (k < dg) {
-          const TX* row = xg + (size_t)nb[k] * in_dim + i4;
+        if (nb.ok[k]) {
+          const TX* row = xg + (size_t)nb.id[k] * in_dim + i4;
           if (vec_in) {
             load4<TX>(row, xv[k]);
           } else {
@@ -418,6 +430,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
           for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
         const float* wh = w1t + (size_t)h * in_pad * D + f0;
         const float* zh = zs + (size_t)q0 * zs_stride + h * in_pad;
+#pragma unroll 1
         for (int i = 0; i < in_pad; i += 4) {
           float4 zv[4];
 #pragma unroll
@@ -438,7 +451,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) o[r][c] += elu1(acc[r][c]);                  // ELU per head, then mean (:118,:158)
+          for (int c = 0; c < 4; ++c) o[r][c] += elu_fast(acc[r][c]);              // ELU per head, then mean (:118,:158)
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -448,6 +461,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
           *reinterpret_cast<float4*>(A.h + (gb + n0 + tile + q0 + r) * D + f0) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
       }
       // predictor scalars
+#pragma unroll 1
       for (int v = 0; v < NQ; ++v) {
         const float* vec = v < 2 * H2 ? u2 + v * D + f0 : w2 + (v - 2 * H2) * D + f0;
         const float4 vv = *reinterpret_cast<const float4*>(vec);
@@ -473,48 +487,62 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
   const float* qg = A.q + gb * NQ;
   const float* hg = A.h + gb * D;
   {
-    float m[kMaxHeads];
+    float mh[kMaxHeads];
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) m[h] = -INFINITY;
+    for (int h = 0; h < kMaxHeads; ++h) mh[h] = -INFINITY;
     for (int t = tid; t < cnt; t += kBT) {
       const int n = n0 + t;
-      int nb[4];
-      const int dg = grid_nbrs(n, Hp, Wp, nb);
-      for (int k = 0; k < dg; ++k)
+      const Nbr nb = grid_nbrs(n, Hp, Wp);
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h)
-          if (h < H2) m[h] = fmaxf(m[h], __ldcg(qg + (size_t)nb[k] * NQ + h) + __ldcg(qg + (size_t)n * NQ + H2 + h));
-    }
-    block_reduce<true, kMaxHeads>(m, H2, red, sm + L.cmax2);
-  }
-  // w[n][k] = exp(-|h_n - h_nbr|^2 / 2) (mincut_refinement.py:43-51), warp per node
-  for (int t = warp; t < cnt; t += kBT / 32) {
-    const int n = n0 + t;
-    int nb[4];
-    const int dg = grid_nbrs(n, Hp, Wp, nb);
-    float d2[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int d = lane * 2; d < D; d += 64) {
-      const float2 a = __ldcg(reinterpret_cast<const float2*>(hg + (size_t)n * D + d));
+      for (int h = 0; h < kMaxHeads; ++h) {
+        if (h < H2) {
+          const float st = __ldcg(qg + (size_t)n * NQ + H2 + h);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < dg) {
-          const float2 c = __ldcg(reinterpret_cast<const float2*>(hg + (size_t)nb[k] * D + d));
-          const float e0 = a.x - c.x, e1 = a.y - c.y;
-          d2[k] += e0 * e0 + e1 * e1;
+          for (int k = 0; k < 4; ++k)
+            if (nb.ok[k]) mh[h] = fmaxf(mh[h], __ldcg(qg + (size_t)nb.id[k] * NQ + h) + st);
         }
       }
     }
+    block_reduce<true, kMaxHeads>(mh, H2, red, sm + L.cmax2);
+  }
+  // w[n][slot] = exp(-|h_n - h_nbr|^2 / 2) (mincut_refinement.py:43-51): 8 lanes per node, all rows in flight
+  {
+    const int gl = tid & 7;
+    const int groups = kBT / 8;
+    const int rounds = ceil_div(cnt, groups);
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int t = rd * groups + (tid >> 3);
+      const bool live = t < cnt;
+      const int n = n0 + (live ? t : 0);
+      const Nbr nb = grid_nbrs(n, Hp, Wp);
+      float d2[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int d = gl * 4; d < D; d += 32) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(hg + (size_t)n * D + d));
+        float4 c[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) d2[k] = warp_sum(d2[k]);
-    if (lane == 0) {
-      float dsum = 0.f;
+        for (int k = 0; k < 4; ++k) c[k] = __ldcg(reinterpret_cast<const float4*>(hg + (size_t)nb.id[k] * D + d));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float e0 = a.x - c[k].x, e1 = a.y - c[k].y, e2 = a.z - c[k].z, e3 = a.w - c[k].w;
+          d2[k] += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float w = k < dg ? expf(-d2[k] / 2.0f) : 0.f;
-        wts[t * 4 + k] = w;
-        dsum += w;
+        d2[k] += __shfl_xor_sync(kFull, d2[k], 4);
+        d2[k] += __shfl_xor_sync(kFull, d2[k], 2);
+        d2[k] += __shfl_xor_sync(kFull, d2[k], 1);
       }
-      deg[t] = dsum;                                                               // degree by source (:92-96)
+      if (live && gl == 0) {
+        float w[4], dsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w[k] = nb.ok[k] ? expf(-d2[k] / 2.0f) : 0.f;
+          dsum += w[k];
+        }
+        *reinterpret_cast<float4*>(wts + t * 4) = make_float4(w[0], w[1], w[2], w[3]);
+        deg[t] = dsum;                                                             // degree by source (:92-96)
+      }
     }
   }
   cluster.sync();                                                                   // #3
@@ -528,135 +556,129 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
   }
 
   // ---- P4: predictor GAT (transform-first: K scalars per head), softmax, argmax -------------------
-  const float inv_h2 = 1.f / (float)H2;
-  for (int t = tid; t < cnt; t += kBT) {
+  // step 1: thread per (node, head): ELU(sum_k alpha_k t[nbr_k][h][c]) -> tmp[node][h][c]
+  for (int idx = tid; idx < cnt * H2; idx += kBT) {
+    const int t = idx / H2, h = idx - t * H2;
     const int n = n0 + t;
-    int nb[4];
-    const int dg = grid_nbrs(n, Hp, Wp, nb);
-    float logit[kMaxSeg];
+    const Nbr nb = grid_nbrs(n, Hp, Wp);
+    const float st = __ldcg(qg + (size_t)n * NQ + H2 + h);
+    const float mh = sel4(M2, h);
+    float p[4], den = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxSeg; ++c) logit[c] = 0.f;
-#pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) {
-      if (h >= H2) break;
-      const float st = __ldcg(qg + (size_t)n * NQ + H2 + h);
-      float p[4], den = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        p[k] = 0.f;
-        if (k < dg) {
-          p[k] = expf(leaky_relu(__ldcg(qg + (size_t)nb[k] * NQ + h) + st, s.slope2) - M2[h]);
-          den += p[k];
-        }
-      }
-      const float dn = den + 1e-10f;
-#pragma unroll
-      for (int c = 0; c < kMaxSeg; ++c) {
-        if (c < K) {
-          float agg = 0.f;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < dg) agg = fmaf(p[k] / dn, __ldcg(qg + (size_t)nb[k] * NQ + 2 * H2 + h * K + c), agg);
-          logit[c] += elu1(agg);
-        }
-      }
+    for (int k = 0; k < 4; ++k) {
+      p[k] = nb.ok[k] ? expf(leaky_relu(__ldcg(qg + (size_t)nb.id[k] * NQ + h) + st, s.slope2) - mh) : 0.f;
+      den += p[k];
     }
-    float mx = -INFINITY;
+    const float dn = den + 1e-10f;
 #pragma unroll
-    for (int c = 0; c < kMaxSeg; ++c)
-      if (c < K) { logit[c] *= inv_h2; mx = fmaxf(mx, logit[c]); }
-    float sum = 0.f;
+    for (int k = 0; k < 4; ++k) p[k] /= dn;
+#pragma unroll 1
+    for (int c = 0; c < K; ++c) {
+      float agg = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxSeg; ++c)
-      if (c < K) sum += expf(logit[c] - mx);
-    float best = -INFINITY;
-    int arg = 0;
-#pragma unroll
-    for (int c = 0; c < kMaxSeg; ++c) {
-      if (c < K) {
-        const float pc = expf(logit[c] - mx) / sum;                                // mincut_refinement.py:193
+      for (int k = 0; k < 4; ++k) agg = fmaf(p[k], __ldcg(qg + (size_t)nb.id[k] * NQ + 2 * H2 + h * K + c), agg);
+      tmp[(t * H2 + h) * K + c] = elu_fast(agg);
+    }
+  }
+  __syncthreads();
+  // step 2: thread per node: head mean, softmax (mincut_refinement.py:193), first-max argmax (train_end_to_end.py:356)
+  {
+    const float inv_h2 = 1.f / (float)H2;
+    for (int t = tid; t < cnt; t += kBT) {
+      const int n = n0 + t;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < K; ++c) {
+        float l = 0.f;
+        for (int h = 0; h < H2; ++h) l += tmp[(t * H2 + h) * K + c];
+        l *= inv_h2;
+        Sown[t * K + c] = l;
+        mx = fmaxf(mx, l);
+      }
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < K; ++c) sum += expf(Sown[t * K + c] - mx);
+      float best = -INFINITY;
+      int arg = 0;
+#pragma unroll 1
+      for (int c = 0; c < K; ++c) {
+        const float pc = expf(Sown[t * K + c] - mx) / sum;
         Sown[t * K + c] = pc;
         A.S[(gb + n) * K + c] = pc;
-        if (pc > best) { best = pc; arg = c; }                                     // train_end_to_end.py:356
+        if (pc > best) { best = pc; arg = c; }
       }
+      lab[t] = arg;
+      A.labels[gb + n] = arg;
     }
-    lab[t] = arg;
-    A.labels[gb + n] = arg;
   }
   cluster.sync();                                                                   // #4: S visible
 
   // ---- P5: N-cut partial sums + region partial sums ------------------------------------------------
   {
-    float va[kMaxSeg], vc[kMaxSeg], vn[kMaxSeg];          // assoc, cut, label counts
-#pragma unroll
-    for (int c = 0; c < kMaxSeg; ++c) va[c] = vc[c] = vn[c] = 0.f;
+    // thread per (node, segment): assoc, cut, label-count terms -> tmp[3][cnt*K]
     const float* Sg = A.S + gb * K;
-    for (int t = tid; t < cnt; t += kBT) {
+    const int nk = cnt * K;
+    for (int idx = tid; idx < nk; idx += kBT) {
+      const int t = idx / K, c = idx - t * K;
       const int n = n0 + t;
-      int nb[4];
-      const int dg = grid_nbrs(n, Hp, Wp, nb);
-      const float dgw = deg[t];
-      const int l = lab[t];
-#pragma unroll
-      for (int c = 0; c < kMaxSeg; ++c) {
-        if (c < K) {
-          const float sc = Sown[t * K + c];
-          va[c] += sc * dgw;                                                       // assoc (:102)
-          float cut = 0.f;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < dg) cut += wts[t * 4 + k] * sc * (1.f - __ldcg(Sg + (size_t)nb[k] * K + c));   // (:112-113,149)
-          vc[c] += cut;
-          vn[c] += (l == c) ? 1.f : 0.f;
-        }
+      const Nbr nb = grid_nbrs(n, Hp, Wp);
+      const float sc = Sown[idx];
+      const float4 w = *reinterpret_cast<const float4*>(wts + t * 4);
+      float cut = 0.f;
+      if (nb.ok[0]) cut += w.x * sc * (1.f - __ldcg(Sg + (size_t)nb.id[0] * K + c));   // (:112-113,149)
+      if (nb.ok[1]) cut += w.y * sc * (1.f - __ldcg(Sg + (size_t)nb.id[1] * K + c));
+      if (nb.ok[2]) cut += w.z * sc * (1.f - __ldcg(Sg + (size_t)nb.id[2] * K + c));
+      if (nb.ok[3]) cut += w.w * sc * (1.f - __ldcg(Sg + (size_t)nb.id[3] * K + c));
+      tmp[idx] = sc * deg[t];                                                      // assoc (:102)
+      tmp[nk + idx] = cut;
+      tmp[2 * nk + idx] = (lab[t] == c) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    // one warp per (quantity, segment): fixed-order strided sum + shuffle tree -> exported partials
+    const int warp = tid >> 5;
+    for (int r = warp; r < 3 * K; r += kBT / 32) {
+      const int which = r / K, c = r - which * K;
+      float acc = 0.f;
+      for (int t = lane; t < cnt; t += 32) acc += tmp[which * nk + t * K + c];
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (which < 2) (sm + L.exp_part)[which * K + c] = acc;
+        else (sm + L.exp_rcnt)[c] = acc;                                           // exact: counts < 2^24
       }
     }
-    block_reduce<false, kMaxSeg>(va, K, red, sm + L.exp_part);
-    block_reduce<false, kMaxSeg>(vc, K, red, sm + L.exp_part + K);
-    block_reduce<false, kMaxSeg>(vn, K, red, sm + L.exp_rcnt);                     // exact: counts < 2^24
+    __syncthreads();
   }
   {
     // region sums: thread (sub, d) walks own nodes sub, sub+NS, ... and adds h[n][d] to its label's slot
     float* rsum = sm + L.exp_rsum;
-    const int NS = kBT / D > 0 ? kBT / D : 1;            // node subsets (D <= 256)
+    const int NS = kBT / D;                               // node subsets (D <= 128)
     const int d = tid % D, sub = tid / D;
     float acc[kMaxSeg];
 #pragma unroll
     for (int c = 0; c < kMaxSeg; ++c) acc[c] = 0.f;
-    if (sub < NS) {
-      for (int t = sub; t < cnt; t += NS) {
-        const float hv = __ldcg(hg + (size_t)(n0 + t) * D + d);
-        const int l = lab[t];
+    for (int t = sub; t < cnt; t += NS) {
+      const float hv = __ldcg(hg + (size_t)(n0 + t) * D + d);
+      const int l = lab[t];
 #pragma unroll
-        for (int c = 0; c < kMaxSeg; ++c) acc[c] += (l == c) ? hv : 0.f;
-      }
+      for (int c = 0; c < kMaxSeg; ++c) acc[c] += (l == c) ? hv : 0.f;
     }
-    // combine the NS subsets in fixed order through the (now free) zs scratch (size checked on host)
-    float* scr = zs;
-    if (sub < NS) {
+    // combine the NS subsets in fixed order through tmp
 #pragma unroll
-      for (int c = 0; c < kMaxSeg; ++c)
-        if (c < K) scr[(sub * K + c) * D + d] = acc[c];
-    }
+    for (int c = 0; c < kMaxSeg; ++c)
+      if (c < K) tmp[(sub * K + c) * D + d] = acc[c];
     __syncthreads();
     for (int idx = tid; idx < K * D; idx += kBT) {
       float t = 0.f;
-      for (int sb = 0; sb < NS; ++sb) t += scr[sb * K * D + idx];
+      for (int sb = 0; sb < NS; ++sb) t += tmp[sb * K * D + idx];
       rsum[idx] = t;
     }
   }
   cluster.sync();                                                                   // #5: partials exported
 
   // ---- P6 (rank 0): loss, region means, region GAT on the complete digraph -------------------------
+  const int H3 = s.H3;
+  float* R = sm + L.region;
   if (crank == 0) {
-    const int H3 = s.H3;
-    float* R = sm + L.region;
-    float* s3 = R + K * D;
-    float* a3 = s3 + round_up4(K * 2 * H3);
-    float* z3 = a3 + round_up4(K * H3 * K);
-    float* y3 = z3 + K * H3 * D;
-    const float* w3t = A.prep + P.w3t;
-    const float* u3 = A.prep + P.u3;
     if (tid == 0) {
       float l = 0.f;
       for (int c = 0; c < K; ++c) {
@@ -677,75 +699,86 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
         t += cluster.map_shared_rank(sm + L.exp_rsum, r)[idx];
         n += cluster.map_shared_rank(sm + L.exp_rcnt, r)[c];
       }
-      const float m = n > 0.f ? t / n : 0.f;                                  // train_end_to_end.py:368-373
+      const float m = n > 0.f ? t / n : 0.f;                                       // train_end_to_end.py:368-373
       R[idx] = m;
       if (A.region_in) A.region_in[(size_t)b * K * D + idx] = m;
     }
-    __syncthreads();
-    if (K > 1) {
-      // scores
-      for (int idx = tid; idx < K * 2 * H3; idx += kBT) {
-        const int k = idx / (2 * H3), qq = idx - k * 2 * H3;
-        float acc = 0.f;
-        for (int i = 0; i < D; ++i) acc = fmaf(R[k * D + i], __ldg(u3 + qq * D + i), acc);
-        s3[idx] = acc;
-      }
-      __syncthreads();
-      // attention over in-edges (sources ascending, skipping the node itself)
-      for (int idx = tid; idx < K * H3; idx += kBT) {
-        const int j = idx / H3, h = idx - j * H3;
-        float m = -INFINITY;
-        for (int jj = 0; jj < K; ++jj)
-          for (int i = 0; i < K; ++i)
-            if (i != jj) m = fmaxf(m, s3[i * 2 * H3 + h] + s3[jj * 2 * H3 + H3 + h]);
-        const float M3 = leaky_relu(m, s.slope3);
-        float den = 0.f;
-        for (int i = 0; i < K; ++i) {
-          float p = 0.f;
-          if (i != j) {
-            p = expf(leaky_relu(s3[i * 2 * H3 + h] + s3[j * 2 * H3 + H3 + h], s.slope3) - M3);
-            den += p;
-          }
-          a3[(j * H3 + h) * K + i] = p;
-        }
-        const float dn = den + 1e-10f;
-        for (int i = 0; i < K; ++i) a3[(j * H3 + h) * K + i] /= dn;
-      }
-      __syncthreads();
-      for (int idx = tid; idx < K * H3 * D; idx += kBT) {
-        const int i = idx % D, jh = idx / D, j = jh / H3;
-        float acc = 0.f;
-        for (int src = 0; src < K; ++src)
-          if (src != j) acc = fmaf(a3[jh * K + src], R[src * D + i], acc);
-        z3[idx] = acc;
-      }
-      __syncthreads();
-      for (int idx = tid; idx < K * H3 * D; idx += kBT) {
-        const int f = idx % D, jh = idx / D, h = jh % H3;
-        const float* wcol = w3t + (size_t)h * D * D + f;
-        const float* zr = z3 + (size_t)jh * D;
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-        for (int i = 0; i < D; i += 4) {
-          acc0 = fmaf(zr[i], __ldg(wcol + (size_t)i * D), acc0);
-          acc1 = fmaf(zr[i + 1], __ldg(wcol + (size_t)(i + 1) * D), acc1);
-          acc2 = fmaf(zr[i + 2], __ldg(wcol + (size_t)(i + 2) * D), acc2);
-          acc3 = fmaf(zr[i + 3], __ldg(wcol + (size_t)(i + 3) * D), acc3);
-        }
-        y3[idx] = elu1((acc0 + acc1) + (acc2 + acc3));
-      }
-      __syncthreads();
-      const float inv_h3 = 1.f / (float)H3;
-      for (int idx = tid; idx < K * D; idx += kBT) {
-        const int j = idx / D, f = idx - j * D;
-        float t = 0.f;
-        for (int h = 0; h < H3; ++h) t += y3[(j * H3 + h) * D + f];
-        A.region_out[(size_t)b * K * D + idx] = t * inv_h3;
-      }
-    } else {
-      for (int idx = tid; idx < K * D; idx += kBT) A.region_out[(size_t)b * K * D + idx] = R[idx];   // :387-389 passthrough
-    }
   }
-  cluster.sync();                                                                   // #6: keep remote smem alive
+  cluster.sync();                                                                   // #6: remote smem no longer needed
+  if (crank != 0) return;
+
+  float* s3 = R + K * D;
+  float* a3 = s3 + round_up4(K * 2 * H3);
+  float* z3 = a3 + round_up4(K * H3 * K);
+  float* y3 = z3 + K * H3 * D;
+  if (K > 1) {
+    mbar_wait(barB, 0);                                  // W3t | u3 landed long ago
+    const float* w3t = sm + L.prepB;
+    const float* u3 = w3t + (P.u3 - P.w3t);
+    // scores: warp per (node, q), lanes over the feature dimension
+    const int warp = tid >> 5;
+    for (int idx = warp; idx < K * 2 * H3; idx += kBT / 32) {
+      const int k = idx / (2 * H3), qq = idx - k * 2 * H3;
+      float acc = 0.f;
+      for (int i = lane; i < D; i += 32) acc = fmaf(R[k * D + i], u3[qq * D + i], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s3[idx] = acc;
+    }
+    __syncthreads();
+    // attention over in-edges (sources ascending, skipping the node itself)
+    for (int idx = tid; idx < K * H3; idx += kBT) {
+      const int j = idx / H3, h = idx - j * H3;
+      float m = -INFINITY;
+      for (int jj = 0; jj < K; ++jj)
+        for (int i = 0; i < K; ++i)
+          if (i != jj) m = fmaxf(m, s3[i * 2 * H3 + h] + s3[jj * 2 * H3 + H3 + h]);
+      const float M3 = leaky_relu(m, s.slope3);
+      float den = 0.f;
+      for (int i = 0; i < K; ++i) {
+        float p = 0.f;
+        if (i != j) {
+          p = expf(leaky_relu(s3[i * 2 * H3 + h] + s3[j * 2 * H3 + H3 + h], s.slope3) - M3);
+          den += p;
+        }
+        a3[(j * H3 + h) * K + i] = p;
+      }
+      const float dn = den + 1e-10f;
+      for (int i = 0; i < K; ++i) a3[(j * H3 + h) * K + i] /= dn;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < K * H3 * D; idx += kBT) {
+      const int i = idx % D, jh = idx / D, j = jh / H3;
+      float acc = 0.f;
+      for (int src = 0; src < K; ++src)
+        if (src != j) acc = fmaf(a3[jh * K + src], R[src * D + i], acc);
+      z3[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < K * H3 * D; idx += kBT) {
+      const int f = idx % D, jh = idx / D, h = jh % H3;
+      const float* wcol = w3t + (size_t)h * D * D + f;
+      const float* zr = z3 + (size_t)jh * D;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < D; i += 4) {
+        acc0 = fmaf(zr[i], wcol[(size_t)i * D], acc0);
+        acc1 = fmaf(zr[i + 1], wcol[(size_t)(i + 1) * D], acc1);
+        acc2 = fmaf(zr[i + 2], wcol[(size_t)(i + 2) * D], acc2);
+        acc3 = fmaf(zr[i + 3], wcol[(size_t)(i + 3) * D], acc3);
+      }
+      y3[idx] = elu_fast((acc0 + acc1) + (acc2 + acc3));
+    }
+    __syncthreads();
+    const float inv_h3 = 1.f / (float)H3;
+    for (int idx = tid; idx < K * D; idx += kBT) {
+      const int j = idx / D, f = idx - j * D;
+      float t = 0.f;
+      for (int h = 0; h < H3; ++h) t += y3[(j * H3 + h) * D + f];
+      A.region_out[(size_t)b * K * D + idx] = t * inv_h3;
+    }
+  } else {
+    for (int idx = tid; idx < K * D; idx += kBT) A.region_out[(size_t)b * K * D + idx] = R[idx];   // :387-389 passthrough
+  }
 }
 
 static bool shape_supported(const BlockShape& s, const char** why) {
@@ -796,8 +829,7 @@ int mg_block_supported(int B, int Hp, int Wp, int in_dim, int D, int H1, int H2,
   const char* why;
   if (B < 1 || Hp < 1 || Wp < 1 || !shape_supported(s, &why)) return 0;
   plan_cluster(&s);
-  if ((int64_t)smem_layout(s).total * 4 > 200 * 1024) return 0;
-  if ((kBT / s.D > 0 ? kBT / s.D : 1) * s.K * s.D > kTileN * s.H1 * s.in_pad) return 0;   // region scratch fits in zs
+  if ((int64_t)smem_layout(s).total * 4 > kSmemMax) return 0;
   return 1;
 }
 
@@ -830,15 +862,13 @@ int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, int in_d
   plan_cluster(&s);
   const SmemLayout L = smem_layout(s);
   const size_t smem = (size_t)L.total * 4;
-  MG_REQUIRE(smem <= 200 * 1024, MG_ERR_UNSUPPORTED, "mg_block_forward: image too large for the fused kernel (%zu B smem)", smem);
-  MG_REQUIRE((kBT / s.D > 0 ? kBT / s.D : 1) * s.K * s.D <= kTileN * s.H1 * s.in_pad, MG_ERR_UNSUPPORTED,
-             "mg_block_forward: region scratch does not fit");
+  MG_REQUIRE(smem <= (size_t)kSmemMax, MG_ERR_UNSUPPORTED, "mg_block_forward: shape too large for the fused kernel (%zu B smem)", smem);
   BlockArgs A;
   A.s = s; A.x = x; A.prep = prep; A.h = h; A.q = q_work; A.S = S; A.labels = labels; A.loss = loss;
   A.region_in = region_in; A.region_out = region_out;
 
   auto kern = x_dtype == MG_F32 ? block_forward_kernel<float> : block_forward_kernel<__nv_bfloat16>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess) {
     set_error("mg_block_forward: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
     return MG_ERR_CUDA;
   }
