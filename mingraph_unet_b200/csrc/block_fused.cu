@@ -235,7 +235,31 @@ __device__ __forceinline__ float sel4(const float (&a)[kMaxHeads], int h) {
 
 // ELU(alpha=1).  exp(v)-1 instead of expm1: the absolute error (<= 1 ulp of 1 = 6e-8) is what the
 // 1e-5 parity budget is about, and it is a third of the instructions.
-__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : expf(v) - 1.f; }
+// Branch-free, with the hardware ex2 (relative error ~2^-21 on (0,1], i.e. ~1e-7 absolute).
+__device__ __forceinline__ float elu_fast(float v) {
+  const float e = __expf(fminf(v, 0.f)) - 1.f;
+  return v > 0.f ? v : e;
+}
+
+// Sum over the FGT lanes of a group of 32 per-lane values with a shuffle reduce-scatter: after the
+// log2(FGT) stages lane gl holds the 32/FGT finished sums j = gl*(32/FGT) ... in v[0 .. 32/FGT).
+template <int N, int OFF>
+struct ReduceScatter {
+  static __device__ __forceinline__ void run(float (&v)[32], int gl) {
+    const bool up = (gl & OFF) != 0;
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      const float send = up ? v[j] : v[j + N / 2];
+      const float keep = up ? v[j + N / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(kFull, send, OFF);
+    }
+    ReduceScatter<N / 2, OFF / 2>::run(v, gl);
+  }
+};
+template <int N>
+struct ReduceScatter<N, 0> {
+  static __device__ __forceinline__ void run(float (&)[32], int) {}
+};
 
 // ---------------------------------------------------------------------------------------------
 // main kernel
@@ -341,14 +365,16 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
     block_reduce<true, kMaxHeads>(m, H1, red, sm + L.cmax1);
   }
   cluster.sync();                                                                   // #1
+  // a few threads fetch the other CTAs' maxima through DSMEM and broadcast them in local shared memory
+  if (tid < H1) {
+    float m = -INFINITY;
+    for (int r = 0; r < s.cluster; ++r) m = fmaxf(m, cluster.map_shared_rank(sm + L.cmax1, r)[tid]);
+    red[tid] = leaky_relu(m, s.slope1);
+  }
+  __syncthreads();
   float M1[kMaxHeads];
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) {
-    float m = -INFINITY;
-    if (h < H1)
-      for (int r = 0; r < s.cluster; ++r) m = fmaxf(m, cluster.map_shared_rank(sm + L.cmax1, r)[h]);
-    M1[h] = leaky_relu(m, s.slope1);
-  }
+  for (int h = 0; h < kMaxHeads; ++h) M1[h] = h < H1 ? red[h] : 0.f;
 
   // ---- P2: patch GAT for own nodes, tile by tile ----------------------------------------------
   const int FG = D >> 2;                          // feature quads per node (power of two <= 32)
@@ -365,7 +391,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
       float p[4], den = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        p[k] = nb.ok[k] ? expf(leaky_relu(s1[(nb.id[k] - h0) * 2 * H1 + h] + st, s.slope1) - mh) : 0.f;
+        p[k] = nb.ok[k] ? __expf(leaky_relu(s1[(nb.id[k] - h0) * 2 * H1 + h] + st, s.slope1) - mh) : 0.f;
         den += p[k];
       }
       const float dn = den + 1e-10f;                                               // graph_attention.py:96
@@ -460,22 +486,55 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
         if (q0 + r < tn)
           *reinterpret_cast<float4*>(A.h + (gb + n0 + tile + q0 + r) * D + f0) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
       }
-      // predictor scalars
+      // predictor scalars: 8 vectors x 4 nodes = 32 partial dot products per lane, summed over the node quad's
+      // FG lanes with a reduce-scatter (30 shuffles instead of 128)
+      if (FG == 16 || FG == 8) {
 #pragma unroll 1
-      for (int v = 0; v < NQ; ++v) {
-        const float* vec = v < 2 * H2 ? u2 + v * D + f0 : w2 + (v - 2 * H2) * D + f0;
-        const float4 vv = *reinterpret_cast<const float4*>(vec);
-        float pr[4];
+        for (int v0 = 0; v0 < NQ; v0 += 8) {
+          float pr[32];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) pr[r] = fmaf(o[r][3], vv.w, fmaf(o[r][2], vv.z, fmaf(o[r][1], vv.y, o[r][0] * vv.x)));
-        for (int off = FG >> 1; off > 0; off >>= 1) {
+          for (int vv = 0; vv < 8; ++vv) {
+            const int v = min(v0 + vv, NQ - 1);
+            const float* vec = v < 2 * H2 ? u2 + v * D + f0 : w2 + (v - 2 * H2) * D + f0;
+            const float4 w4 = *reinterpret_cast<const float4*>(vec);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) pr[r] += __shfl_xor_sync(kFull, pr[r], off);
+            for (int r = 0; r < 4; ++r)
+              pr[vv * 4 + r] = fmaf(o[r][3], w4.w, fmaf(o[r][2], w4.z, fmaf(o[r][1], w4.y, o[r][0] * w4.x)));
+          }
+          if (FG == 16) {
+            ReduceScatter<32, 8>::run(pr, fg);
+            const int v = v0 + (fg >> 1), r = (fg & 1) * 2;
+            if (v < NQ) {
+              if (q0 + r < tn) A.q[(gb + n0 + tile + q0 + r) * NQ + v] = pr[0];
+              if (q0 + r + 1 < tn) A.q[(gb + n0 + tile + q0 + r + 1) * NQ + v] = pr[1];
+            }
+          } else {
+            ReduceScatter<32, 4>::run(pr, fg);
+            const int v = v0 + fg;
+            if (v < NQ) {
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+                if (q0 + r < tn) A.q[(gb + n0 + tile + q0 + r) * NQ + v] = pr[r];
+            }
+          }
         }
-        if (fg == 0) {
+      } else {
+#pragma unroll 1
+        for (int v = 0; v < NQ; ++v) {
+          const float* vec = v < 2 * H2 ? u2 + v * D + f0 : w2 + (v - 2 * H2) * D + f0;
+          const float4 vv = *reinterpret_cast<const float4*>(vec);
+          float pr[4];
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-            if (q0 + r < tn) A.q[(gb + n0 + tile + q0 + r) * NQ + v] = pr[r];
+          for (int r = 0; r < 4; ++r) pr[r] = fmaf(o[r][3], vv.w, fmaf(o[r][2], vv.z, fmaf(o[r][1], vv.y, o[r][0] * vv.x)));
+          for (int off = FG >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) pr[r] += __shfl_xor_sync(kFull, pr[r], off);
+          }
+          if (fg == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (q0 + r < tn) A.q[(gb + n0 + tile + q0 + r) * NQ + v] = pr[r];
+          }
         }
       }
     }
@@ -537,7 +596,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
         float w[4], dsum = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          w[k] = nb.ok[k] ? expf(-d2[k] / 2.0f) : 0.f;
+          w[k] = nb.ok[k] ? __expf(-d2[k] / 2.0f) : 0.f;
           dsum += w[k];
         }
         *reinterpret_cast<float4*>(wts + t * 4) = make_float4(w[0], w[1], w[2], w[3]);
@@ -546,14 +605,15 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
     }
   }
   cluster.sync();                                                                   // #3
+  if (tid < H2) {
+    float m = -INFINITY;
+    for (int r = 0; r < s.cluster; ++r) m = fmaxf(m, cluster.map_shared_rank(sm + L.cmax2, r)[tid]);
+    red[tid] = leaky_relu(m, s.slope2);
+  }
+  __syncthreads();
   float M2[kMaxHeads];
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) {
-    float m = -INFINITY;
-    if (h < H2)
-      for (int r = 0; r < s.cluster; ++r) m = fmaxf(m, cluster.map_shared_rank(sm + L.cmax2, r)[h]);
-    M2[h] = leaky_relu(m, s.slope2);
-  }
+  for (int h = 0; h < kMaxHeads; ++h) M2[h] = h < H2 ? red[h] : 0.f;
 
   // ---- P4: predictor GAT (transform-first: K scalars per head), softmax, argmax -------------------
   // step 1: thread per (node, head): ELU(sum_k alpha_k t[nbr_k][h][c]) -> tmp[node][h][c]
@@ -566,7 +626,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
     float p[4], den = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      p[k] = nb.ok[k] ? expf(leaky_relu(__ldcg(qg + (size_t)nb.id[k] * NQ + h) + st, s.slope2) - mh) : 0.f;
+      p[k] = nb.ok[k] ? __expf(leaky_relu(__ldcg(qg + (size_t)nb.id[k] * NQ + h) + st, s.slope2) - mh) : 0.f;
       den += p[k];
     }
     const float dn = den + 1e-10f;

@@ -1,6 +1,8 @@
 // K1 patch mean pooling, region mean pooling (a11) and K7 nearest un-pool (a13).
 // All three are HBM-streaming kernels: K1 reads the feature map once with 16-byte loads,
 // K7 writes the dense (B,D,H,W) map once with 16-byte streaming stores.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mg {
@@ -32,47 +34,110 @@ struct Vec16<__nv_bfloat16> {
   }
 };
 
-constexpr int kPoolCC = 32;   // channels per block
+constexpr int kPoolCC = 32;   // max channels per block
+constexpr int kPoolRows = 16; // rows whose 16-byte loads are issued together
 
-// fast path: pw % VEC == 0, Wf % VEC == 0, (pw/VEC) power of two <= 32
+// fast path: pw % VEC == 0, Wf % VEC == 0, lpp = pw/VEC a power of two <= 32.
+// Block = (x chunk of 32 vectors, channel group) x patch row x image; warp w takes channels w, w+NW, ...
+// of the group and, per channel, issues all ph row loads of its 512-byte strip before summing them.
 template <typename TX, typename TO>
 __global__ void __launch_bounds__(256) pool_patches_vec_kernel(const TX* __restrict__ x, int C, int Hf, int Wf, int ph,
-                                                               int pw, int Hp, int Wp, TO* __restrict__ out) {
+                                                               int pw, int Hp, int Wp, int cg, int xchunks,
+                                                               TO* __restrict__ out) {
   constexpr int VEC = Vec16<TX>::N;
-  extern __shared__ float tile[];   // [Wp][kPoolCC+1]
-  const int b = blockIdx.z, py = blockIdx.y, c0 = blockIdx.x * kPoolCC;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  extern __shared__ float tile[];   // [32 / lpp][cg + 1]
+  const int b = blockIdx.z, py = blockIdx.y;
+  const int xc = blockIdx.x % xchunks, c0 = (blockIdx.x / xchunks) * cg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int lpp = pw / VEC;                               // lanes per patch
-  const int y0 = py * ph, y1 = min(Hf, y0 + ph);
+  const int pp = 32 / lpp;                                // patches per chunk
+  const int y0 = py * ph, rows = min(Hf, y0 + ph) - y0;
   const float inv = 1.f / (float)(ph * pw);
   const int nvec = Wf / VEC;
-  for (int cc = warp; cc < kPoolCC; cc += 8) {
-    const int c = c0 + cc;
-    if (c >= C) break;
-    const TX* plane = x + ((size_t)b * C + c) * Hf * Wf;
-    for (int xv0 = 0; xv0 < nvec; xv0 += 32) {
-      const int xv = xv0 + lane;
-      float acc = 0.f;
-      if (xv < nvec) {
-        const TX* p = plane + (size_t)y0 * Wf + (size_t)xv * VEC;
-        int y = y0;
-        for (; y + 3 < y1; y += 4) {                      // 4 independent 16-byte loads in flight
-          const float s0 = Vec16<TX>::sum(p), s1 = Vec16<TX>::sum(p + Wf), s2 = Vec16<TX>::sum(p + 2 * (size_t)Wf),
-                      s3 = Vec16<TX>::sum(p + 3 * (size_t)Wf);
-          acc += (s0 + s1) + (s2 + s3);
-          p += 4 * (size_t)Wf;
+  const int xv = xc * 32 + lane;
+  const bool in_x = xv < nvec;
+  const int ncc = min(cg, C - c0);
+  for (int cc = warp; cc < ncc; cc += nw) {
+    const TX* p = x + (((size_t)b * C + c0 + cc) * Hf + y0) * Wf + (size_t)xv * VEC;
+    float acc = 0.f;
+    for (int r0 = 0; r0 < rows; r0 += kPoolRows) {
+      float part[kPoolRows];
+#pragma unroll
+      for (int r = 0; r < kPoolRows; ++r)
+        part[r] = (in_x && r0 + r < rows) ? Vec16<TX>::sum(p + (size_t)(r0 + r) * Wf) : 0.f;
+#pragma unroll
+      for (int st = kPoolRows / 2; st > 0; st >>= 1)
+#pragma unroll
+        for (int r = 0; r < st; ++r) part[r] += part[r + st];
+      acc += part[0];
+    }
+    for (int o = 1; o < lpp; o <<= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    if ((lane & (lpp - 1)) == 0) tile[(lane / lpp) * (cg + 1) + cc] = acc * inv;
+  }
+  __syncthreads();
+  const int px0 = xc * pp;
+  for (int idx = threadIdx.x; idx < pp * ncc; idx += blockDim.x) {
+    const int pl = idx / ncc, cc = idx - pl * ncc;
+    if (px0 + pl < Wp)
+      out[((size_t)b * Hp * Wp + (size_t)py * Wp + px0 + pl) * C + c0 + cc] = from_f32<TO>(tile[pl * (cg + 1) + cc]);
+  }
+}
+
+// strip path: warp task = one (image, channel, patch-row) strip = ph full rows, contiguous in memory
+// (ph * Wf elements).  The warp streams the strip with 16-byte loads, 2*kStripRows loads in flight per
+// lane, and folds each vector into its patch column; conditions as for the fast path plus Wf <= 64*VEC*?:
+// handled generally by looping over 32-vector chunks.  Block = NW warps = NW channels of one (b, py).
+constexpr int kStripRows = 8;
+template <typename TX, typename TO>
+__global__ void __launch_bounds__(256) pool_patches_strip_kernel(const TX* __restrict__ x, int C, int Hf, int Wf, int ph,
+                                                                 int pw, int Hp, int Wp, TO* __restrict__ out) {
+  constexpr int VEC = Vec16<TX>::N;
+  extern __shared__ float tile[];   // [Wp][nw + 1]
+  const int b = blockIdx.z, py = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int c = blockIdx.x * nw + warp;
+  const int lpp = pw / VEC, pp = 32 / lpp;
+  const int y0 = py * ph, rows = min(Hf, y0 + ph) - y0;
+  const float inv = 1.f / (float)(ph * pw);
+  const int nvec = Wf / VEC;
+  if (c < C) {
+    const TX* base = x + (((size_t)b * C + c) * Hf + y0) * Wf;
+    for (int xc0 = 0; xc0 < nvec; xc0 += 64) {               // two 32-vector chunks per pass
+      const int xa = xc0 + lane, xb = xc0 + 32 + lane;
+      const bool ina = xa < nvec, inb = xb < nvec;
+      float acca = 0.f, accb = 0.f;
+      for (int r0 = 0; r0 < rows; r0 += kStripRows) {
+        float pa[kStripRows], pb[kStripRows];
+#pragma unroll
+        for (int r = 0; r < kStripRows; ++r) {
+          const bool rk = r0 + r < rows;
+          const TX* rowp = base + (size_t)(r0 + r) * Wf;
+          pa[r] = (ina && rk) ? Vec16<TX>::sum(rowp + (size_t)xa * VEC) : 0.f;
+          pb[r] = (inb && rk) ? Vec16<TX>::sum(rowp + (size_t)xb * VEC) : 0.f;
         }
-        for (; y < y1; ++y) { acc += Vec16<TX>::sum(p); p += Wf; }
+#pragma unroll
+        for (int st = kStripRows / 2; st > 0; st >>= 1)
+#pragma unroll
+          for (int r = 0; r < st; ++r) { pa[r] += pa[r + st]; pb[r] += pb[r + st]; }
+        acca += pa[0];
+        accb += pb[0];
       }
-      for (int o = 1; o < lpp; o <<= 1) acc += __shfl_xor_sync(kFull, acc, o);
-      if (xv < nvec && (lane & (lpp - 1)) == 0) tile[(xv / lpp) * (kPoolCC + 1) + cc] = acc * inv;
+      for (int o = 1; o < lpp; o <<= 1) {
+        acca += __shfl_xor_sync(kFull, acca, o);
+        accb += __shfl_xor_sync(kFull, accb, o);
+      }
+      if ((lane & (lpp - 1)) == 0) {
+        const int pa_ = (xc0 / 32) * pp + lane / lpp, pb_ = pa_ + pp;
+        if (pa_ < Wp) tile[pa_ * (nw + 1) + warp] = acca * inv;
+        if (pb_ < Wp) tile[pb_ * (nw + 1) + warp] = accb * inv;
+      }
     }
   }
   __syncthreads();
-  const int ncc = min(kPoolCC, C - c0);
-  for (int idx = threadIdx.x; idx < Wp * kPoolCC; idx += blockDim.x) {
-    const int px = idx / kPoolCC, cc = idx - px * kPoolCC;
-    if (cc < ncc) out[((size_t)b * Hp * Wp + (size_t)py * Wp + px) * C + c0 + cc] = from_f32<TO>(tile[px * (kPoolCC + 1) + cc]);
+  const int c0 = blockIdx.x * nw, ncc = min(nw, C - c0);
+  for (int idx = threadIdx.x; idx < Wp * ncc; idx += blockDim.x) {
+    const int px = idx / ncc, cc = idx - px * ncc;
+    out[((size_t)b * Hp * Wp + (size_t)py * Wp + px) * C + c0 + cc] = from_f32<TO>(tile[px * (nw + 1) + cc]);
   }
 }
 
@@ -257,13 +322,28 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
   const int Hp = ceil_div(Hf, ph), Wp = ceil_div(Wf, pw);
   const int lpp = pw / VEC;
   const bool fast = (pw % VEC == 0) && (Wf % VEC == 0) && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 &&
-                    ((uintptr_t)x % 16 == 0) && (size_t)Wp * (kPoolCC + 1) * 4 <= 160 * 1024;
+                    ((uintptr_t)x % 16 == 0);
+  static const int variant = getenv("MG_POOL_VARIANT") ? atoi(getenv("MG_POOL_VARIANT")) : 0;
+  if (fast && variant >= 1 && (size_t)Wp * 9 * 4 <= 48 * 1024) {
+    const int nw = variant >= 2 ? variant : 4;             // warps (= channels) per block
+    dim3 grid(ceil_div(C, nw), Hp, B);
+    pool_patches_strip_kernel<TX, TO><<<grid, nw * 32, (size_t)Wp * (nw + 1) * 4, st>>>(
+        reinterpret_cast<const TX*>(x), C, Hf, Wf, ph, pw, Hp, Wp, reinterpret_cast<TO*>(out));
+    return check_launch("pool_patches_strip_kernel");
+  }
   if (fast) {
-    const size_t smem = (size_t)Wp * (kPoolCC + 1) * 4;
-    auto k = pool_patches_vec_kernel<TX, TO>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    dim3 grid(ceil_div(C, kPoolCC), Hp, B);
-    k<<<grid, 256, smem, st>>>(reinterpret_cast<const TX*>(x), C, Hf, Wf, ph, pw, Hp, Wp, reinterpret_cast<TO*>(out));
+    const int cg = std::min(C, kPoolCC);
+    // warps per block: the count in 4..8 that wastes the fewest channel slots (ties -> more warps)
+    int nw = std::min(cg, 8), best_waste = 1 << 30;
+    for (int w = std::min(cg, 8); w >= std::min(cg, 4); --w) {
+      const int waste = ceil_div(cg, w) * w - cg;
+      if (waste < best_waste) { best_waste = waste; nw = w; }
+    }
+    const int xchunks = ceil_div(Wf / VEC, 32);
+    const size_t smem = (size_t)(32 / lpp) * (cg + 1) * 4;
+    dim3 grid(xchunks * ceil_div(C, cg), Hp, B);
+    pool_patches_vec_kernel<TX, TO><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const TX*>(x), C, Hf, Wf, ph, pw, Hp, Wp,
+                                                               cg, xchunks, reinterpret_cast<TO*>(out));
     return check_launch("pool_patches_vec_kernel");
   }
   const int64_t total = (int64_t)B * C * Hp * Wp;
