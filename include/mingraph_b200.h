@@ -101,12 +101,29 @@ MG_API int mg_segment_mean(const float* h, const int32_t* labels, int B, int N, 
  *   aggregated features when the weights do not fit in shared memory).
  *   save_den (N,heads) f32 and save_z (N,heads,in) f32 are optional (nullable) outputs kept
  *   for mg_gat_backward.
+ *   dropout_p > 0 (training): attention dropout (:97) with a counter-based mask keyed on (seed, in-CSR slot,
+ *   head); statistically equivalent to torch's, not the same stream.
  * Empty graphs (E == 0) are rejected with MG_ERR_INVALID like the reference's RuntimeError. */
 MG_API int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int num_graphs);
 MG_API int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, int64_t E,
                    const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
-                   int nodes_per_graph, void* out, int out_dtype, void* work, float* save_den, float* save_z,
-                   mg_stream_t stream);
+                   int nodes_per_graph, float dropout_p, uint64_t seed, void* out, int out_dtype, void* work,
+                   float* save_den, float* save_z, mg_stream_t stream);
+
+/* MultiHeadGATLayer backward (the reference relies on autograd: IndexBackward / ScatterAddBackward / MmBackward
+ * over graph_attention.py:53-118).  Needs both CSR views and, per out-CSR slot, the in-CSR slot of the same edge
+ * (mg_edge_slot_map from the eid arrays of mg_grid_csr / mg_csr_from_coo; work = E int32).
+ *   den (N,heads), z (N,heads,in): saved by mg_gat_forward;  grad_out (N, out_w) f32
+ *   -> grad_x (N,in) f32, grad_W (heads,F,in), grad_a (heads,2F).  dropout_p/seed must equal the forward's.
+ * Deterministic (owner-computes passes by target and by source, fixed-order split reductions). */
+MG_API int mg_edge_slot_map(const int32_t* eid_in, const int32_t* eid_out, int64_t E, int32_t* work, int32_t* slot_out2in,
+                     mg_stream_t stream);
+MG_API int64_t mg_gat_backward_work_bytes(int N, int64_t E, int in_dim, int out_dim, int heads, int num_graphs);
+MG_API int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in, const int32_t* col_in,
+                    const int32_t* rowptr_out, const int32_t* col_out, const int32_t* slot_out2in, int N, int64_t E,
+                    const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
+                    int nodes_per_graph, float dropout_p, uint64_t seed, const float* den, const float* z,
+                    const float* grad_out, float* grad_x, float* grad_W, float* grad_a, void* work, mg_stream_t stream);
 
 /* Row softmax + argmax of the predictor logits — mincut_refinement.py:193 and
  * train_end_to_end.py:356.  logits (N,K) f32 -> S (N,K) f32, labels (N) int32 (first max). */
@@ -118,10 +135,16 @@ MG_API int mg_softmax_argmax(const float* logits, int N, int K, float* S, int32_
 MG_API int mg_ncut_edge_weights(const float* h, int N, int D, const int64_t* edge_index, int64_t E, float* w,
                          mg_stream_t stream);
 /* MinCutRefinement.normalized_cut_loss — :55-160, per graph.  Uses the OUT CSR (degree is
- * summed by source, :96).  loss (G) f32; work: mg_ncut_work_bytes(). */
+ * summed by source, :96).  loss (G) f32; stats (G,2K) nullable: per-graph [assoc | cut] kept for the backward;
+ * work: mg_ncut_work_bytes(). */
 MG_API int64_t mg_ncut_work_bytes(int N, int K, int num_graphs);
 MG_API int mg_ncut_loss(const float* h, const float* S, const int32_t* rowptr_out, const int32_t* col_out, int N, int D,
-                 int K, int nodes_per_graph, float* loss, void* work, mg_stream_t stream);
+                 int K, int nodes_per_graph, float* loss, float* stats, void* work, mg_stream_t stream);
+/* Backward of mg_ncut_loss w.r.t. h and S.  stats (G,2K) = [assoc | cut] as written by mg_ncut_loss (nullable
+ * there); grad_loss (G); -> grad_h (N,D), grad_S (N,K).  Owner-computes over both CSR views, no atomics. */
+MG_API int mg_ncut_backward(const float* h, const float* S, const int32_t* rowptr_out, const int32_t* col_out,
+                     const int32_t* rowptr_in, const int32_t* col_in, int N, int D, int K, int nodes_per_graph,
+                     const float* stats, const float* grad_loss, float* grad_h, float* grad_S, mg_stream_t stream);
 
 /* ---- un-pool ---------------------------------------------------------------------------------
  * train_end_to_end.py:403-421: f_patch = table[labels]; (N,D)->(D,Hp,Wp); nearest up-sampling to

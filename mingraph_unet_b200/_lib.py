@@ -44,11 +44,16 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_pool_patches": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "mg_segment_mean": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "mg_gat_work_bytes": (_i64, [_i, _i, _i, _i, _i]),
-    "mg_gat_forward": (_i, [_p, _i, _p, _p, _i, _i64, _p, _p, _i, _i, _i, _i, _f, _i, _p, _i, _p, _p, _p, _p]),
+    "mg_gat_forward": (_i, [_p, _i, _p, _p, _i, _i64, _p, _p, _i, _i, _i, _i, _f, _i, _f, C.c_uint64, _p, _i, _p, _p, _p, _p]),
+    "mg_edge_slot_map": (_i, [_p, _p, _i64, _p, _p, _p]),
+    "mg_gat_backward_work_bytes": (_i64, [_i, _i64, _i, _i, _i, _i]),
+    "mg_gat_backward": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i64, _p, _p, _i, _i, _i, _i, _f, _i, _f, C.c_uint64,
+                             _p, _p, _p, _p, _p, _p, _p, _p]),
     "mg_softmax_argmax": (_i, [_p, _i, _i, _p, _p, _p]),
     "mg_ncut_edge_weights": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
     "mg_ncut_work_bytes": (_i64, [_i, _i, _i]),
-    "mg_ncut_loss": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "mg_ncut_loss": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "mg_ncut_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "mg_unpool_nearest": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i64, _p]),
     "mg_block_prep_floats": (_i64, [_i] * 6),
     "mg_block_supported": (_i, [_i] * 9),

@@ -28,7 +28,20 @@ struct GatAggArgs {
   int N, in_dim, heads;
   int nodes_per_graph;
   float slope;
+  float dropout_p;        // attention dropout (graph_attention.py:97); 0 in eval mode
+  unsigned long long seed;
 };
+
+// Counter-based Bernoulli mask for attention dropout: a pure function of (seed, in-CSR slot, head), so the
+// backward pass regenerates the forward's mask without storing it.  Returns 0 or 1/(1-p).
+__device__ __forceinline__ float dropout_keep_scale(unsigned long long seed, unsigned slot, unsigned head, float p) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)slot * 8ull + head + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+  return u >= p ? 1.f / (1.f - p) : 0.f;
+}
 
 // Per-warp scratch in shared memory: attention numerators of one edge chunk and its sources.
 struct WarpScratch {
@@ -78,7 +91,8 @@ __device__ __forceinline__ void gat_aggregate_node(const GatAggArgs& a, int j, i
         pv = expf(e - M);
       }
     }
-    den_lane += pv;
+    den_lane += pv;                                  // the softmax denominator is taken before dropout (:94-97)
+    if (a.dropout_p > 0.f && valid && head_ok) pv *= dropout_keep_scale(a.seed, (unsigned)k, (unsigned)hl, a.dropout_p);
     __syncwarp();
     sc->p[lane] = pv;
     if (hl == 0) sc->src[el] = srcn;

@@ -243,6 +243,34 @@ static int launch_scores(const void* x, int N, int in_dim, const float* W, const
   return MG_ERR_UNSUPPORTED;
 }
 
+
+// scores s (N, 2*heads) = [s_src | s_tgt] and the per-graph raw edge maxima gmax (G, heads); shared with backward
+int gat_scores_and_max(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, const float* W,
+                       const float* a, int in_dim, int out_dim, int heads, int nodes_per_graph, float* s, float* gmax,
+                       float* u, cudaStream_t st) {
+  DimCfg d;
+  if (!pick_dims(in_dim, &d)) {
+    set_error("gat: in_dim=%d unsupported", in_dim);
+    return MG_ERR_UNSUPPORTED;
+  }
+  const int G = nodes_per_graph > 0 ? N / nodes_per_graph : 1;
+  int rc;
+  // attention vectors: recomputed per block when cheap, otherwise one small kernel
+  const float* u_global = nullptr;
+  if ((int64_t)in_dim * out_dim * heads > 32768 || u != nullptr) {
+    gat_u_kernel<<<ceil_div(2 * heads * in_dim, 128), 128, 0, st>>>(W, a, in_dim, out_dim, heads, u);
+    if ((rc = check_launch("gat_u_kernel"))) return rc;
+    u_global = u;
+  }
+  if (x_dtype == MG_F32)
+    rc = launch_scores<float>(x, N, in_dim, W, a, u_global, out_dim, heads, G, s, gmax, d, st);
+  else
+    rc = launch_scores<__nv_bfloat16>(x, N, in_dim, W, a, u_global, out_dim, heads, G, s, gmax, d, st);
+  if (rc) return rc;
+  gat_edge_max_kernel<<<ceil_div(N, 256), 256, 0, st>>>(rowptr, col, s, N, heads, nodes_per_graph, gmax);
+  return check_launch("gat_edge_max_kernel");
+}
+
 struct WorkLayout { size_t s_off, gmax_off, u_off, z_off, total; };
 static WorkLayout work_layout(int N, int in_dim, int out_dim, int heads, int G, bool need_z) {
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -273,8 +301,8 @@ int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int num_gra
 
 int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, int64_t E,
                    const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
-                   int nodes_per_graph, void* out, int out_dtype, void* work, float* save_den, float* save_z,
-                   mg_stream_t stream) {
+                   int nodes_per_graph, float dropout_p, uint64_t seed, void* out, int out_dtype, void* work,
+                   float* save_den, float* save_z, mg_stream_t stream) {
   MG_REQUIRE(x && rowptr && W && a && out && work, MG_ERR_INVALID, "mg_gat_forward: null pointer");
   MG_REQUIRE(N > 0 && in_dim > 0 && out_dim > 0, MG_ERR_INVALID, "mg_gat_forward: bad sizes N=%d in=%d out=%d", N, in_dim,
              out_dim);
@@ -282,6 +310,7 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   MG_REQUIRE(E > 0 && col, MG_ERR_INVALID,
              "mg_gat_forward: empty edge_index (the reference raises in torch.max, graph_attention.py:86)");
   MG_REQUIRE(slope >= 0.f, MG_ERR_UNSUPPORTED, "mg_gat_forward: negative LeakyReLU slope is not monotone");
+  MG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, MG_ERR_INVALID, "mg_gat_forward: dropout_p must be in [0, 1)");
   MG_REQUIRE(x_dtype == MG_F32 || x_dtype == MG_BF16, MG_ERR_INVALID, "mg_gat_forward: x dtype");
   MG_REQUIRE(out_dtype == MG_F32 || out_dtype == MG_BF16, MG_ERR_INVALID, "mg_gat_forward: out dtype");
   MG_REQUIRE(nodes_per_graph >= 0 && (nodes_per_graph == 0 || N % nodes_per_graph == 0), MG_ERR_INVALID,
@@ -300,24 +329,13 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
 
-  // attention vectors: recomputed per block when cheap, otherwise one small kernel
-  const float* u_global = nullptr;
-  if ((int64_t)in_dim * out_dim * heads > 32768) {
-    gat_u_kernel<<<ceil_div(2 * heads * in_dim, 128), 128, 0, st>>>(W, a, in_dim, out_dim, heads, u);
-    if ((rc = check_launch("gat_u_kernel"))) return rc;
-    u_global = u;
-  }
-  if (x_dtype == MG_F32)
-    rc = launch_scores<float>(x, N, in_dim, W, a, u_global, out_dim, heads, G, s, gmax, d, st);
-  else
-    rc = launch_scores<__nv_bfloat16>(x, N, in_dim, W, a, u_global, out_dim, heads, G, s, gmax, d, st);
-  if (rc) return rc;
-  gat_edge_max_kernel<<<ceil_div(N, 256), 256, 0, st>>>(rowptr, col, s, N, heads, nodes_per_graph, gmax);
-  if ((rc = check_launch("gat_edge_max_kernel"))) return rc;
+  if ((rc = gat_scores_and_max(x, x_dtype, rowptr, col, N, W, a, in_dim, out_dim, heads, nodes_per_graph, s, gmax, u, st)))
+    return rc;
 
   GatAggArgs ag;
   ag.x = x; ag.rowptr = rowptr; ag.col = col; ag.s = s; ag.gmax = gmax;
   ag.N = N; ag.in_dim = in_dim; ag.heads = heads; ag.nodes_per_graph = nodes_per_graph; ag.slope = slope;
+  ag.dropout_p = dropout_p; ag.seed = seed;
 
   if (plan.ok) {
     GatFusedArgs A;

@@ -6,6 +6,10 @@
 namespace mg {
 
 struct DimCfg { int V, T; };
+
+int gat_scores_and_max(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, const float* W,
+                       const float* a, int in_dim, int out_dim, int heads, int nodes_per_graph, float* s, float* gmax,
+                       float* u, cudaStream_t st);
 static constexpr int64_t kSmemBudget = 200 * 1024;
 
 // ------------------------------------------------------------------------------------------

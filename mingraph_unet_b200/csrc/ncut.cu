@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) ncut_node_terms_kernel(const float* __res
 
 // one block per graph: fixed-order tree reduction of the 2K columns over the graph's nodes
 __global__ void __launch_bounds__(256) ncut_reduce_kernel(const float* __restrict__ node_terms, int nodes_per_graph,
-                                                         int K, float* __restrict__ loss) {
+                                                         int K, float* __restrict__ loss, float* __restrict__ stats) {
   __shared__ float red[8][2 * kMaxK];
   __shared__ float tot[2 * kMaxK];
   const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -155,6 +155,116 @@ __global__ void __launch_bounds__(256) ncut_reduce_kernel(const float* __restric
     for (int c = 0; c < K; ++c)
       if (tot[c] > 1e-8f) l += tot[K + c] / tot[c];          // mincut_refinement.py:151-152
     loss[g] = l;
+  }
+  if (stats && threadIdx.x < twoK) stats[(size_t)g * twoK + threadIdx.x] = tot[threadIdx.x];   // [assoc | cut]
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the loss w.r.t. the node features h and the soft assignments S (autograd dual of
+// mincut_refinement.py:43-51,92-113,149-152).  With A_c = assoc_c, C_c = cut_c (saved), active c: A_c > 1e-8,
+//   dL/dC_c = 1/A_c, dL/dA_c = -C_c/A_c^2,
+//   dL/dw_e = sum_c S[s,c] ((1 - S[t,c])/A_c - C_c/A_c^2)                  (deg_s contains w_e)
+//   dL/dS[i,c] = sum_{e: src=i} w_e ((1 - S[t,c])/A_c - C_c/A_c^2)  -  sum_{e: tgt=i} w_e S[s,c]/A_c
+//   dL/dh_s -= dL/dw_e w_e (h_s - h_t),   dL/dh_t += dL/dw_e w_e (h_s - h_t)
+// Owner-computes: a group of 8 lanes per node walks its out-edges (source terms) and its in-edges (target
+// terms); no atomics.  D % 4 == 0, D <= 128.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ncut_backward_kernel(const float* __restrict__ h, const float* __restrict__ S,
+                                                           const int32_t* __restrict__ rp_out, const int32_t* __restrict__ col_out,
+                                                           const int32_t* __restrict__ rp_in, const int32_t* __restrict__ col_in,
+                                                           int N, int D, int K, int nodes_per_graph,
+                                                           const float* __restrict__ stats, const float* __restrict__ gloss,
+                                                           float* __restrict__ gh, float* __restrict__ gS) {
+  const int gl = threadIdx.x & (kEG - 1);
+  const int groups = (gridDim.x * blockDim.x) / kEG;
+  const int iters = ceil_div(N, groups);
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) / kEG;
+  for (int it = 0; it < iters; ++it, i += groups) {
+    const bool ok = i < N;
+    const int ic = ok ? i : 0;
+    const int g = nodes_per_graph > 0 ? ic / nodes_per_graph : 0;
+    const float gL = __ldg(gloss + g);
+    // per-lane segment coefficients: lane owns c = gl + q*kEG
+    float invA[kMaxK / kEG], cA[kMaxK / kEG], Si[kMaxK / kEG], gSi[kMaxK / kEG];
+#pragma unroll
+    for (int q = 0; q < kMaxK / kEG; ++q) {
+      const int c = gl + q * kEG;
+      invA[q] = cA[q] = Si[q] = gSi[q] = 0.f;
+      if (c < K) {
+        const float A = __ldg(stats + (size_t)g * 2 * K + c), C = __ldg(stats + (size_t)g * 2 * K + K + c);
+        if (A > 1e-8f) { invA[q] = gL / A; cA[q] = -gL * C / (A * A); }
+        Si[q] = __ldg(S + (size_t)ic * K + c);
+      }
+    }
+    float acc[4][4];                                  // g_h_i for dims d = (gl + 8t)*4 .. +3, t < 4  (D <= 128)
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[t][v] = 0.f;
+    const float* hi = h + (size_t)ic * D;
+    for (int pass = 0; pass < 2; ++pass) {            // 0: out-edges (i is the source), 1: in-edges (i is the target)
+      const int32_t* rp = pass == 0 ? rp_out : rp_in;
+      const int32_t* cl = pass == 0 ? col_out : col_in;
+      const int beg = ok ? __ldg(rp + ic) : 0, end = ok ? __ldg(rp + ic + 1) : 0;
+      int deg_n = end - beg, maxdeg = deg_n;
+#pragma unroll
+      for (int o = 16; o >= kEG; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(kFull, maxdeg, o));
+      for (int k = 0; k < maxdeg; ++k) {
+        const bool live = k < deg_n;
+        const int j = live ? __ldg(cl + beg + k) : ic;
+        const float* hj = h + (size_t)j * D;
+        const float d2 = group_sqdist<kEG>(hi, hj, D, gl, true);
+        const float w = expf(-d2 / 2.0f);
+        // gw = dL/dw_e (summed over segments), and this node's dL/dS contributions
+        float gw = 0.f;
+#pragma unroll
+        for (int q = 0; q < kMaxK / kEG; ++q) {
+          const int c = gl + q * kEG;
+          if (c < K && live) {
+            const float Sj = __ldg(S + (size_t)j * K + c);
+            if (pass == 0) {
+              const float coef = (1.f - Sj) * invA[q] + cA[q];
+              gw += Si[q] * coef;
+              gSi[q] += w * coef;
+            } else {
+              gw += Sj * ((1.f - Si[q]) * invA[q] + cA[q]);
+              gSi[q] -= w * Sj * invA[q];
+            }
+          }
+        }
+        gw += __shfl_xor_sync(kFull, gw, 4);
+        gw += __shfl_xor_sync(kFull, gw, 2);
+        gw += __shfl_xor_sync(kFull, gw, 1);
+        if (live) {
+          // out-edge: dL/dh_i -= gw w (h_i - h_j); in-edge (j -> i): dL/dh_i += gw w (h_j - h_i): same expression
+          const float sc = -gw * w;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int d = (gl + kEG * t) * 4;
+            if (d < D) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(hi + d));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(hj + d));
+              acc[t][0] = fmaf(sc, a.x - b.x, acc[t][0]);
+              acc[t][1] = fmaf(sc, a.y - b.y, acc[t][1]);
+              acc[t][2] = fmaf(sc, a.z - b.z, acc[t][2]);
+              acc[t][3] = fmaf(sc, a.w - b.w, acc[t][3]);
+            }
+          }
+        }
+      }
+    }
+    if (ok) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int d = (gl + kEG * t) * 4;
+        if (d < D) *reinterpret_cast<float4*>(gh + (size_t)i * D + d) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+      }
+#pragma unroll
+      for (int q = 0; q < kMaxK / kEG; ++q) {
+        const int c = gl + q * kEG;
+        if (c < K) gS[(size_t)i * K + c] = gSi[q];
+      }
+    }
   }
 }
 
@@ -188,7 +298,7 @@ int64_t mg_ncut_work_bytes(int N, int K, int num_graphs) {
 }
 
 int mg_ncut_loss(const float* h, const float* S, const int32_t* rowptr_out, const int32_t* col_out, int N, int D, int K,
-                 int nodes_per_graph, float* loss, void* work, mg_stream_t stream) {
+                 int nodes_per_graph, float* loss, float* stats, void* work, mg_stream_t stream) {
   MG_REQUIRE(h && S && rowptr_out && loss && work && N > 0 && D > 0, MG_ERR_INVALID, "mg_ncut_loss: bad arguments");
   MG_REQUIRE(K >= 1 && K <= kMaxK, MG_ERR_UNSUPPORTED, "mg_ncut_loss: K=%d (supported 1..%d)", K, kMaxK);
   MG_REQUIRE(nodes_per_graph >= 0 && (nodes_per_graph == 0 || N % nodes_per_graph == 0), MG_ERR_INVALID,
@@ -202,8 +312,24 @@ int mg_ncut_loss(const float* h, const float* S, const int32_t* rowptr_out, cons
   ncut_node_terms_kernel<<<grid, 256, 0, st>>>(h, S, rowptr_out, col_out, N, D, K, terms);
   int rc;
   if ((rc = check_launch("ncut_node_terms_kernel"))) return rc;
-  ncut_reduce_kernel<<<G, 256, 0, st>>>(terms, npg, K, loss);
+  ncut_reduce_kernel<<<G, 256, 0, st>>>(terms, npg, K, loss, stats);
   return check_launch("ncut_reduce_kernel");
+}
+
+int mg_ncut_backward(const float* h, const float* S, const int32_t* rowptr_out, const int32_t* col_out,
+                     const int32_t* rowptr_in, const int32_t* col_in, int N, int D, int K, int nodes_per_graph,
+                     const float* stats, const float* grad_loss, float* grad_h, float* grad_S, mg_stream_t stream) {
+  MG_REQUIRE(h && S && rowptr_out && rowptr_in && stats && grad_loss && grad_h && grad_S && N > 0, MG_ERR_INVALID,
+             "mg_ncut_backward: bad arguments");
+  MG_REQUIRE(K >= 1 && K <= kMaxK, MG_ERR_UNSUPPORTED, "mg_ncut_backward: K=%d (supported 1..%d)", K, kMaxK);
+  MG_REQUIRE((D & 3) == 0 && D <= 128 && ((uintptr_t)h % 16 == 0) && ((uintptr_t)grad_h % 16 == 0), MG_ERR_UNSUPPORTED,
+             "mg_ncut_backward: D=%d must be a multiple of 4, <= 128, with 16-byte aligned rows", D);
+  MG_REQUIRE(nodes_per_graph >= 0 && (nodes_per_graph == 0 || N % nodes_per_graph == 0), MG_ERR_INVALID,
+             "mg_ncut_backward: N=%d is not a multiple of nodes_per_graph=%d", N, nodes_per_graph);
+  const int grid = (int)std::min<int64_t>(ceil_div64((int64_t)N * kEG, 256), (int64_t)num_sms() * 8);
+  ncut_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, S, rowptr_out, col_out, rowptr_in, col_in, N, D, K,
+                                                              nodes_per_graph, stats, grad_loss, grad_h, grad_S);
+  return check_launch("ncut_backward_kernel");
 }
 
 }  // extern "C"

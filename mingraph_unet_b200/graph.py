@@ -31,6 +31,7 @@ class Graph:
         self.rowptr_in = self.col_in = self.eid_in = None
         self.rowptr_out = self.col_out = self.eid_out = None
         self.symmetric_csr = False
+        self.slot_out2in = None
 
     # -- constructors ---------------------------------------------------------------------------
     @classmethod
@@ -41,6 +42,9 @@ class Graph:
             N, E = Hp * Wp, ops.grid_num_edges(Hp, Wp)
             g = cls(B * N, B * E, device, nodes_per_graph=N if B > 1 else 0)
             g.rowptr_in, g.col_in, g.eid_in, g.eid_out = ops.grid_csr(Hp, Wp, device, B, with_eid=True)
+            if B > 1:      # eids are per-image COO ids: offset them so they index the batched edge list
+                off = (torch.arange(B, device=device, dtype=torch.int32) * E).repeat_interleave(E)
+                g.eid_in, g.eid_out = g.eid_in + off, g.eid_out + off
             g.rowptr_out, g.col_out = g.rowptr_in, g.col_in       # the grid is symmetric
             g.symmetric_csr = True
             g.per_graph_edges = E
@@ -55,6 +59,7 @@ class Graph:
         g = _STATIC.get(key)
         if g is None:
             g = cls(B * K, B * K * (K - 1), device, nodes_per_graph=K if B > 1 else 0)
+            g.edge_index = ops.complete_edge_index(K, device, B, offset_nodes=True)
             g.rowptr_in, g.col_in = ops.complete_csr(K, device, B)
             g.rowptr_out, g.col_out = g.rowptr_in, g.col_in
             g.symmetric_csr = True
@@ -83,6 +88,17 @@ class Graph:
     def need_out_csr(self) -> None:
         if self.rowptr_out is None:
             self.rowptr_out, self.col_out, self.eid_out = ops.csr_from_coo(self.edge_index, self.N, by_target=False)
+
+    def need_backward_maps(self) -> None:
+        """Both CSR views plus, per out-CSR slot, the in-CSR slot of the same edge (GAT backward)."""
+        if self.slot_out2in is not None:
+            return
+        if self.eid_in is None or self.eid_out is None:
+            if self.edge_index is None:
+                raise RuntimeError("graph has no edge_index to derive the backward maps from")
+            self.rowptr_in, self.col_in, self.eid_in = ops.csr_from_coo(self.edge_index, self.N, by_target=True)
+            self.rowptr_out, self.col_out, self.eid_out = ops.csr_from_coo(self.edge_index, self.N, by_target=False)
+        self.slot_out2in = ops.edge_slot_map(self.eid_in, self.eid_out)
 
 
 _STATIC: Dict[tuple, Graph] = {}

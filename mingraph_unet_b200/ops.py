@@ -181,7 +181,7 @@ def unpool_nearest(table: torch.Tensor, labels: Optional[torch.Tensor], Hp: int,
 # ---------------------------------------------------------------------------------------------
 def gat_forward(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, W: torch.Tensor, a: torch.Tensor,
                 concat: bool = False, slope: float = 0.2, nodes_per_graph: int = 0,
-                out_dtype: Optional[torch.dtype] = None, save: bool = False):
+                out_dtype: Optional[torch.dtype] = None, save: bool = False, dropout_p: float = 0.0, seed: int = 0):
     """Multi-head GAT layer forward (eval semantics).  ``x (N,in)`` f32|bf16, ``W (H,F,in)``,
     ``a (H,2F)`` f32, in-CSR ``rowptr/col`` int32.  Returns ``out`` or ``(out, den, z)`` if ``save``."""
     _need_cuda(x, rowptr, col, W, a)
@@ -208,8 +208,46 @@ def gat_forward(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, W: tor
     with torch.cuda.device(x.device):
         call("mg_gat_forward", x.data_ptr(), _dtype_code(x.dtype), rowptr.data_ptr(), col.data_ptr(), N, E,
              W.data_ptr(), a.data_ptr(), in_dim, F, heads, int(concat), float(slope), int(nodes_per_graph),
-             out.data_ptr(), _dtype_code(out_dtype), work.data_ptr(), _ptr(den), _ptr(z), _stream())
+             float(dropout_p), int(seed), out.data_ptr(), _dtype_code(out_dtype), work.data_ptr(), _ptr(den), _ptr(z),
+             _stream())
     return (out, den, z) if save else out
+
+
+def edge_slot_map(eid_in: torch.Tensor, eid_out: torch.Tensor) -> torch.Tensor:
+    """For every out-CSR slot, the in-CSR slot holding the same edge (needed by ``gat_backward``)."""
+    _need_cuda(eid_in, eid_out)
+    E = eid_in.numel()
+    out = torch.empty(max(E, 1), dtype=torch.int32, device=eid_in.device)
+    work = torch.empty(max(E, 1), dtype=torch.int32, device=eid_in.device)
+    with torch.cuda.device(eid_in.device):
+        call("mg_edge_slot_map", eid_in.data_ptr(), eid_out.data_ptr(), E, work.data_ptr(), out.data_ptr(), _stream())
+    return out[:E]
+
+
+def gat_backward(x, rowptr_in, col_in, rowptr_out, col_out, slot_out2in, W, a, den, z, grad_out, concat: bool = False,
+                 slope: float = 0.2, nodes_per_graph: int = 0, dropout_p: float = 0.0, seed: int = 0):
+    """Backward of ``gat_forward``: returns ``grad_x (N,in) f32, grad_W (H,F,in), grad_a (H,2F)``."""
+    _need_cuda(x, W, a, den, z, grad_out)
+    N, in_dim = x.shape
+    heads, F, _ = W.shape
+    E = col_in.numel()
+    x = x.contiguous()
+    W = W.contiguous().float()
+    a = a.contiguous().float()
+    grad_out = grad_out.contiguous().float()
+    dev = x.device
+    gx = torch.empty((N, in_dim), dtype=torch.float32, device=dev)
+    gW = torch.empty((heads, F, in_dim), dtype=torch.float32, device=dev)
+    ga = torch.empty((heads, 2 * F), dtype=torch.float32, device=dev)
+    G = N // nodes_per_graph if nodes_per_graph > 0 else 1
+    work = torch.empty(max(int(_lib.load().mg_gat_backward_work_bytes(N, E, in_dim, F, heads, G)), 256), dtype=torch.uint8,
+                       device=dev)
+    with torch.cuda.device(dev):
+        call("mg_gat_backward", x.data_ptr(), _dtype_code(x.dtype), rowptr_in.data_ptr(), col_in.data_ptr(),
+             rowptr_out.data_ptr(), col_out.data_ptr(), slot_out2in.data_ptr(), N, E, W.data_ptr(), a.data_ptr(), in_dim, F,
+             heads, int(concat), float(slope), int(nodes_per_graph), float(dropout_p), int(seed), den.data_ptr(),
+             z.data_ptr(), grad_out.data_ptr(), gx.data_ptr(), gW.data_ptr(), ga.data_ptr(), work.data_ptr(), _stream())
+    return gx, gW, ga
 
 
 def softmax_argmax(logits: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -245,8 +283,9 @@ def ncut_edge_weights(h: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor
 
 
 def ncut_loss(h: torch.Tensor, S: torch.Tensor, rowptr_out: torch.Tensor, col_out: torch.Tensor,
-              nodes_per_graph: int = 0) -> torch.Tensor:
-    """Soft normalized-cut loss per graph -> ``(G,)`` float32 (mincut_refinement.py:55-160)."""
+              nodes_per_graph: int = 0, with_stats: bool = False):
+    """Soft normalized-cut loss per graph -> ``(G,)`` float32 (mincut_refinement.py:55-160).
+    ``with_stats``: also return ``(G, 2K)`` = per-graph ``[assoc | cut]`` for :func:`ncut_backward`."""
     _need_cuda(h, S, rowptr_out, col_out)
     if h.dtype != torch.float32 or S.dtype != torch.float32:
         raise RuntimeError("ncut_loss expects float32 tensors")
@@ -255,11 +294,28 @@ def ncut_loss(h: torch.Tensor, S: torch.Tensor, rowptr_out: torch.Tensor, col_ou
     K = S.shape[1]
     G = N // nodes_per_graph if nodes_per_graph > 0 else 1
     loss = torch.empty(G, dtype=torch.float32, device=h.device)
+    stats = torch.empty((G, 2 * K), dtype=torch.float32, device=h.device) if with_stats else None
     work = torch.empty(int(_lib.load().mg_ncut_work_bytes(N, K, G)), dtype=torch.uint8, device=h.device)
     with torch.cuda.device(h.device):
         call("mg_ncut_loss", h.data_ptr(), S.data_ptr(), rowptr_out.data_ptr(), col_out.data_ptr(), N, D, K,
-             int(nodes_per_graph), loss.data_ptr(), work.data_ptr(), _stream())
-    return loss
+             int(nodes_per_graph), loss.data_ptr(), _ptr(stats), work.data_ptr(), _stream())
+    return (loss, stats) if with_stats else loss
+
+
+def ncut_backward(h, S, rowptr_out, col_out, rowptr_in, col_in, stats, grad_loss, nodes_per_graph: int = 0):
+    """Gradients of the per-graph N-cut loss w.r.t. ``h (N,D)`` and ``S (N,K)``."""
+    _need_cuda(h, S, stats, grad_loss)
+    h, S = h.contiguous(), S.contiguous()
+    N, D = h.shape
+    K = S.shape[1]
+    gh = torch.empty_like(h)
+    gS = torch.empty_like(S)
+    grad_loss = grad_loss.contiguous().float()
+    with torch.cuda.device(h.device):
+        call("mg_ncut_backward", h.data_ptr(), S.data_ptr(), rowptr_out.data_ptr(), col_out.data_ptr(), rowptr_in.data_ptr(),
+             col_in.data_ptr(), N, D, K, int(nodes_per_graph), stats.data_ptr(), grad_loss.data_ptr(), gh.data_ptr(),
+             gS.data_ptr(), _stream())
+    return gh, gS
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,209 @@
+"""GPU: backward kernels (GAT layer, N-cut loss) against torch autograd through the CPU oracle
+restatement (which is written in differentiable torch ops, like the reference)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import mingraph_unet_b200 as m
+    return m
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _load(layer, Ws, As):
+    sd = {}
+    for h in range(Ws.shape[0]):
+        sd[f"heads.{h}.W.weight"] = Ws[h].clone()
+        sd[f"heads.{h}.a.weight"] = As[h].reshape(1, -1).clone()
+    layer.load_state_dict(sd)
+    return layer
+
+
+def _oracle_grads(x, ei, Ws, As, gout, concat):
+    x = x.clone().requires_grad_(True)
+    Ws = Ws.clone().requires_grad_(True)
+    As = As.clone().requires_grad_(True)
+    y = O.gat_layer(x, ei, Ws, As, 0.2, concat=concat)
+    (y * gout).sum().backward()
+    return y.detach(), x.grad, Ws.grad, As.grad
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("case", ["grid_20_64_4", "grid_64_2_2", "rand_33_32_4_cat", "rand_64_64_4", "rand_12_8_1", "complete_64_64_4"])
+def test_gat_backward_vs_autograd(mg, case, seed):
+    gen = torch.Generator().manual_seed(sum(map(ord, case)) + seed)
+    concat = case.endswith("cat")
+    if case.startswith("grid"):
+        _, fin, fout, heads = case.split("_")
+        fin, fout, heads = int(fin), int(fout), int(heads)
+        hp, wp = 9, 7
+        N = hp * wp
+        ei = torch.from_numpy(O.grid_edge_index(hp, wp))
+    elif case.startswith("complete"):
+        fin, fout, heads = 64, 64, 4
+        N = 5
+        ei = torch.from_numpy(O.complete_edge_index(N))
+    else:
+        parts = case.split("_")
+        fin, fout, heads = int(parts[1]), int(parts[2]), int(parts[3])
+        N = 97
+        ei = torch.randint(0, N - 2, (2, 700), generator=gen)      # multigraph; last nodes isolated
+        ei[1, ei[1] == 5] = 6
+    x = torch.randn(N, fin, generator=gen)
+    head_out = fout // heads if concat else fout
+    Ws, As = O.init_gat_params(fin, head_out, heads, gen)
+    gout = torch.randn(N, fout, generator=gen)
+    y_ref, gx_ref, gW_ref, ga_ref = _oracle_grads(x, ei, Ws, As, gout, concat)
+
+    layer = _load(mg.MultiHeadGATLayer(fin, fout, heads, 0.0, 0.2, concat=concat), Ws, As).cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    if case.startswith("grid"):
+        _, eig = mg.PatchGraphConstructor(16).construct_patch_graph(torch.zeros(1, hp * 16, wp * 16), xg)
+    else:
+        eig = ei.cuda()
+    y = layer(xg, eig)
+    assert float((y.detach().cpu() - y_ref).abs().max()) <= 1e-5
+    (y * gout.cuda()).sum().backward()
+    gW = torch.stack([h.W.weight.grad for h in layer.heads]).cpu()
+    ga = torch.stack([h.a.weight.grad.view(-1) for h in layer.heads]).cpu()
+    assert rel_err(xg.grad, gx_ref) <= 2e-5
+    assert rel_err(gW, gW_ref) <= 2e-5
+    assert rel_err(ga, ga_ref) <= 5e-5
+    # a second backward through a fresh forward gives bitwise identical gradients (no atomics)
+    xg2 = x.cuda().requires_grad_(True)
+    for p in layer.parameters():
+        p.grad = None
+    (layer(xg2, eig) * gout.cuda()).sum().backward()
+    assert torch.equal(xg2.grad, xg.grad)
+    assert torch.equal(torch.stack([h.W.weight.grad for h in layer.heads]).cpu(), gW)
+
+
+def test_gat_backward_batched_grid(mg):
+    """Block-diagonal batch (per-image softmax shift) == per-image autograd."""
+    gen = torch.Generator().manual_seed(3)
+    B, hp, wp, fin, fout, heads = 3, 5, 6, 20, 64, 4
+    N = hp * wp
+    x = torch.randn(B, N, fin, generator=gen)
+    Ws, As = O.init_gat_params(fin, fout, heads, gen)
+    gout = torch.randn(B, N, fout, generator=gen)
+    ei = torch.from_numpy(O.grid_edge_index(hp, wp))
+    gx_ref, gW_ref, ga_ref = torch.zeros_like(x), torch.zeros_like(Ws), torch.zeros_like(As)
+    for b in range(B):
+        _, gx, gW, ga = _oracle_grads(x[b], ei, Ws, As, gout[b], False)
+        gx_ref[b] = gx
+        gW_ref += gW
+        ga_ref += ga
+    from mingraph_unet_b200.autograd import gat_layer_apply
+    g = mg.Graph.grid(hp, wp, torch.device("cuda"), B)
+    xg = x.view(B * N, fin).cuda().requires_grad_(True)
+    Wg, Ag = Ws.cuda().requires_grad_(True), As.cuda().requires_grad_(True)
+    y = gat_layer_apply(xg, g, Wg, Ag, False, 0.2)
+    (y * gout.view(B * N, fout).cuda()).sum().backward()
+    assert rel_err(xg.grad.view(B, N, fin), gx_ref) <= 2e-5
+    assert rel_err(Wg.grad, gW_ref) <= 2e-5 and rel_err(Ag.grad, ga_ref) <= 5e-5
+
+
+def test_gat_attention_dropout_statistics_and_replay(mg):
+    """Train-mode attention dropout: keep rate ~ 1-p, expectation preserved, backward replays the mask."""
+    from mingraph_unet_b200.autograd import gat_layer_apply
+    gen = torch.Generator().manual_seed(0)
+    hp, wp, fin, fout, heads, p = 24, 24, 16, 8, 4, 0.3
+    N = hp * wp
+    g = mg.Graph.grid(hp, wp, torch.device("cuda"), 1)
+    x = torch.randn(N, fin, generator=gen).cuda()
+    Ws, As = O.init_gat_params(fin, fout, heads, gen)
+    Wg, Ag = Ws.cuda(), As.cuda()
+    y0 = gat_layer_apply(x, g, Wg, Ag, False, 0.2, 0.0)
+    torch.manual_seed(5)
+    ys = torch.stack([gat_layer_apply(x, g, Wg, Ag, False, 0.2, p) for _ in range(64)])
+    assert float((ys[0] - ys[1]).abs().max()) > 1e-3                       # different masks per call
+    # E[dropout(alpha)] = alpha, but ELU is nonlinear: compare loosely on the mean
+    assert float((ys.mean(0) - y0).abs().mean()) < 0.12
+    assert float((ys[0] - y0).abs().mean()) > float((ys.mean(0) - y0).abs().mean()) * 2     # averaging shrinks the noise
+    # mask replay: the same CPU-generator state reproduces the mask, and the backward pass (which regenerates
+    # the mask from the saved seed) matches a central finite difference taken under that fixed mask
+    xg = x.clone().requires_grad_(True)
+    torch.manual_seed(9)
+    y = gat_layer_apply(xg, g, Wg.clone().requires_grad_(True), Ag.clone().requires_grad_(True), False, 0.2, p)
+    w = torch.randn(y.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    (y * w).sum().backward()
+    d = torch.randn(x.shape, generator=torch.Generator().manual_seed(2)).cuda()
+    eps = 1e-3
+    torch.manual_seed(9)
+    y2 = gat_layer_apply(x, g, Wg, Ag, False, 0.2, p)
+    assert torch.equal(y.detach(), y2)
+    torch.manual_seed(9)
+    yp = gat_layer_apply(x + eps * d, g, Wg, Ag, False, 0.2, p)
+    torch.manual_seed(9)
+    ym = gat_layer_apply(x - eps * d, g, Wg, Ag, False, 0.2, p)
+    fd = float(((yp.double() - ym.double()) * w.double()).sum() / (2 * eps))
+    an = float((xg.grad.double() * d.double()).sum())
+    assert abs(fd - an) <= 0.03 * abs(an) + 0.3
+
+
+@pytest.mark.parametrize("kind", ["grid", "random"])
+def test_ncut_backward_vs_autograd(mg, kind):
+    gen = torch.Generator().manual_seed(11)
+    D, K = 64, 3
+    if kind == "grid":
+        hp, wp = 7, 6
+        N = hp * wp
+        ei = torch.from_numpy(O.grid_edge_index(hp, wp))
+    else:
+        N = 80
+        ei = torch.randint(0, N, (2, 500), generator=gen)
+    h = (0.2 * torch.randn(N, D, generator=gen)).requires_grad_(True)
+    logits = torch.randn(N, K, generator=gen).requires_grad_(True)
+    S = torch.softmax(logits, 1)
+    O.ncut_loss(h, ei, S, K).backward()
+    hg = h.detach().cuda().requires_grad_(True)
+    lg = logits.detach().cuda().requires_grad_(True)
+    mc = mg.MinCutRefinement()
+    loss = mc.normalized_cut_loss(hg, ei.cuda(), torch.softmax(lg, 1), K)
+    loss.backward()
+    assert rel_err(hg.grad, h.grad) <= 5e-5
+    assert rel_err(lg.grad, logits.grad) <= 5e-5
+
+
+def test_mincut_module_end_to_end_grads(mg):
+    """patch GAT -> predictor GAT -> softmax -> N-cut, gradients to every parameter, vs oracle autograd."""
+    gen = torch.Generator().manual_seed(21)
+    hp, wp, fin, D, K = 6, 8, 20, 64, 2
+    N = hp * wp
+    ei = torch.from_numpy(O.grid_edge_index(hp, wp))
+    x = 0.3 * torch.randn(N, fin, generator=gen)
+    P = O.init_block_params(fin, D, 4, K, seed=3)
+    P = {k: (0.5 * v) for k, v in P.items()}                                  # keep edge weights away from underflow
+    ps = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    hh = O.gat_network(x, ei, ps["patch_W"], ps["patch_a"])
+    loss, S = O.mincut_forward(hh, ei, K, lambda f, e: O.gat_network(f, e, ps["pred_W"], ps["pred_a"]))
+    loss.backward()
+
+    patch = _load(mg.GATNetwork(fin, 128, D, 4, 1, 0.0, 0.2).gat_layers[0], P["patch_W"], P["patch_a"]).cuda()
+    pred_net = mg.GATNetwork(D, 32, K, 2, 1, 0.0, 0.2)
+    _load(pred_net.gat_layers[0], P["pred_W"], P["pred_a"])
+    for m in pred_net.modules():
+        if hasattr(m, "dropout_rate"):
+            m.dropout_rate = 0.0
+    pred_net = pred_net.cuda().eval()            # eval: no dropout; gradients still flow
+    patch.train()
+    xg = x.cuda()
+    _, eig = mg.PatchGraphConstructor(16).construct_patch_graph(torch.zeros(1, hp * 16, wp * 16), xg)
+    hg = patch(xg, eig)
+    lg, Sg = mg.MinCutRefinement()(hg, eig, K, pred_net)
+    assert float(lg.detach()) == pytest.approx(float(loss), rel=1e-4)
+    lg.backward()
+    gW = torch.stack([hd.W.weight.grad for hd in patch.heads]).cpu()
+    assert rel_err(gW, ps["patch_W"].grad) <= 1e-4
+    gWp = torch.stack([hd.W.weight.grad for hd in pred_net.gat_layers[0].heads]).cpu()
+    assert rel_err(gWp, ps["pred_W"].grad) <= 1e-4
