@@ -155,6 +155,23 @@ MG_API int mg_ncut_backward(const float* h, const float* S, const int32_t* rowpt
 MG_API int mg_unpool_nearest(const float* table, const int32_t* labels, int B, int K, int D, int Hp, int Wp, int H, int W,
                       void* out, int out_dtype, int64_t out_batch_stride, mg_stream_t stream);
 
+/* ---- backward of the glue stages (training) -------------------------------------------------------
+ * The reference gets these from autograd (UpsampleNearest2DBackward + IndexBackward for
+ * train_end_to_end.py:403-421, IndexBackward/MeanBackward for :368-373, SoftmaxBackward for
+ * mincut_refinement.py:193).  All deterministic, no atomics.
+ * mg_unpool_nearest_backward: grad_out (B,D,H,W) planes f32|bf16 (image b at grad_out + b*grad_batch_stride
+ * elements) -> grad_table (B,K,D) f32 = sum of the gradient over the pixels whose patch carries label k
+ * (labels NULL: K == Hp*Wp, per-patch sums).  work: mg_unpool_backward_work_bytes() bytes. */
+MG_API int64_t mg_unpool_backward_work_bytes(int B, int D, int Hp, int Wp);
+MG_API int mg_unpool_nearest_backward(const void* grad_out, int grad_dtype, int64_t grad_batch_stride, const int32_t* labels,
+                               int B, int K, int D, int Hp, int Wp, int H, int W, void* work, float* grad_table,
+                               mg_stream_t stream);
+/* grad_h (B,N,D) (+)= grad_out[b, labels[b,n], :] / counts[b, labels[b,n]]  (counts from mg_segment_mean). */
+MG_API int mg_segment_mean_backward(const float* grad_out, const int32_t* labels, const int32_t* counts, int B, int N, int D,
+                             int K, int accumulate, float* grad_h, mg_stream_t stream);
+/* grad_logits = S * (grad_S - rowsum(grad_S * S)). */
+MG_API int mg_softmax_backward(const float* S, const float* grad_S, int N, int K, float* grad_logits, mg_stream_t stream);
+
 /* ---- fused per-image block (forward) ------------------------------------------------------------
  * The per-image loop of scripts/train_end_to_end.py:329-389 for a batch of B images in ONE launch:
  * patch GAT -> predictor GAT -> softmax/argmax -> N-cut loss -> region mean-pool -> region GAT on the

@@ -55,6 +55,10 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_ncut_loss": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "mg_ncut_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "mg_unpool_nearest": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i64, _p]),
+    "mg_unpool_backward_work_bytes": (_i64, [_i, _i, _i, _i]),
+    "mg_unpool_nearest_backward": (_i, [_p, _i, _i64, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "mg_segment_mean_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "mg_softmax_backward": (_i, [_p, _p, _i, _i, _p, _p]),
     "mg_block_prep_floats": (_i64, [_i] * 6),
     "mg_block_supported": (_i, [_i] * 9),
     "mg_block_prepare": (_i, [_p] * 6 + [_i] * 6 + [_p, _p]),

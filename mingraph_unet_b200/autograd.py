@@ -14,10 +14,11 @@ def _wants_grad(*ts) -> bool:
 
 class _GATLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, a, g: Graph, concat: bool, slope: float, att_dropout: float):
+    def forward(ctx, x, W, a, g: Graph, concat: bool, slope: float, att_dropout: float, out_dtype=None):
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if att_dropout > 0.0 else 0     # CPU generator: no device sync
         out, den, z = ops.gat_forward(x, g.rowptr_in, g.col_in, W, a, concat=concat, slope=slope,
-                                      nodes_per_graph=g.nodes_per_graph, save=True, dropout_p=att_dropout, seed=seed)
+                                      nodes_per_graph=g.nodes_per_graph, save=True, dropout_p=att_dropout, seed=seed,
+                                      out_dtype=out_dtype)
         ctx.save_for_backward(x, W, a, den, z)
         ctx.g, ctx.concat, ctx.slope, ctx.p, ctx.seed = g, concat, slope, att_dropout, seed
         return out
@@ -30,25 +31,99 @@ class _GATLayerFn(torch.autograd.Function):
         gx, gW, ga = ops.gat_backward(x, g.rowptr_in, g.col_in, g.rowptr_out, g.col_out, g.slot_out2in, W, a, den, z,
                                       grad_out, concat=ctx.concat, slope=ctx.slope, nodes_per_graph=g.nodes_per_graph,
                                       dropout_p=ctx.p, seed=ctx.seed)
-        return gx.to(x.dtype), gW.to(W.dtype), ga.to(a.dtype), None, None, None, None
+        return gx.to(x.dtype), gW.to(W.dtype), ga.to(a.dtype), None, None, None, None, None
 
 
 def gat_layer_apply(x: torch.Tensor, g: Graph, W: torch.Tensor, a: torch.Tensor, concat: bool, slope: float,
-                    att_dropout: float = 0.0) -> torch.Tensor:
+                    att_dropout: float = 0.0, out_dtype=None) -> torch.Tensor:
     """Multi-head GAT layer on graph ``g``; differentiable w.r.t. ``x``, ``W``, ``a``."""
     if _wants_grad(x, W, a):
-        return _GATLayerFn.apply(x, W, a, g, concat, slope, att_dropout)
+        return _GATLayerFn.apply(x, W, a, g, concat, slope, att_dropout, out_dtype)
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if att_dropout > 0.0 else 0
     return ops.gat_forward(x, g.rowptr_in, g.col_in, W.detach(), a.detach(), concat=concat, slope=slope,
-                           nodes_per_graph=g.nodes_per_graph, dropout_p=att_dropout, seed=seed)
+                           nodes_per_graph=g.nodes_per_graph, dropout_p=att_dropout, seed=seed, out_dtype=out_dtype)
+
+
+class _SoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits):
+        S, labels = ops.softmax_argmax(logits)
+        ctx.save_for_backward(S)
+        ctx.mark_non_differentiable(labels)
+        return S, labels
+
+    @staticmethod
+    def backward(ctx, grad_S, _grad_labels):
+        (S,) = ctx.saved_tensors
+        return ops.softmax_backward(S, grad_S)
+
+
+def softmax_rows_with_labels(logits: torch.Tensor):
+    """``(softmax(logits, 1), argmax)`` in one kernel; differentiable in the first output."""
+    if _wants_grad(logits):
+        return _SoftmaxFn.apply(logits.contiguous())
+    return ops.softmax_argmax(logits)
 
 
 def softmax_rows(logits: torch.Tensor) -> torch.Tensor:
     """``softmax(logits, dim=1)`` (mincut_refinement.py:193)."""
     if _wants_grad(logits):
-        return torch.softmax(logits, dim=1)           # stock autograd op until the fused backward lands
+        return _SoftmaxFn.apply(logits.contiguous())[0]
     S, _ = ops.softmax_argmax(logits)
     return S
+
+
+class _SegmentMeanFn(torch.autograd.Function):
+    """Region mean pool (train_end_to_end.py:368-373); labels are data (argmax), not differentiated."""
+
+    @staticmethod
+    def forward(ctx, h, labels, K: int):
+        out, counts = ops.segment_mean(h, labels, K, with_counts=True)
+        ctx.save_for_backward(labels, counts)
+        ctx.N = h.shape[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        labels, counts = ctx.saved_tensors
+        return ops.segment_mean_backward(grad_out, labels, counts, ctx.N), None, None
+
+
+def segment_mean_apply(h: torch.Tensor, labels: torch.Tensor, K: int) -> torch.Tensor:
+    if _wants_grad(h):
+        return _SegmentMeanFn.apply(h.contiguous(), labels, K)
+    return ops.segment_mean(h, labels, K)
+
+
+class _UnpoolFn(torch.autograd.Function):
+    """Gather by label + nearest up-sampling (train_end_to_end.py:403-421); the backward is the segmented
+    reduction of the dense gradient back onto the K region rows."""
+
+    @staticmethod
+    def forward(ctx, table, labels, Hp, Wp, H, W, out, out_dtype):
+        res = ops.unpool_nearest(table, labels, Hp, Wp, H, W, out=out, out_dtype=out_dtype)
+        ctx.save_for_backward(labels)
+        ctx.dims = (table.shape[1], Hp, Wp)
+        if out is not None:
+            ctx.mark_dirty(out)
+        return res
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (labels,) = ctx.saved_tensors
+        K, Hp, Wp = ctx.dims
+        return ops.unpool_nearest_backward(grad_out, labels, K, Hp, Wp), None, None, None, None, None, None, None
+
+
+def unpool_apply(table, labels, Hp, Wp, H, W, out=None, out_dtype=torch.float32):
+    if _wants_grad(table):
+        if out is not None:
+            # writing into a caller-owned slice under autograd: produce a fresh tensor, then copy (keeps the graph simple)
+            res = _UnpoolFn.apply(table.contiguous(), labels, Hp, Wp, H, W, None, out.dtype)
+            out.copy_(res.detach())
+            return res
+        return _UnpoolFn.apply(table.contiguous(), labels, Hp, Wp, H, W, None, out_dtype)
+    return ops.unpool_nearest(table, labels, Hp, Wp, H, W, out=out, out_dtype=out_dtype)
 
 
 class _NcutFn(torch.autograd.Function):

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .autograd import gat_layer_apply
+from .autograd import ncut_loss_apply, segment_mean_apply, softmax_rows_with_labels, unpool_apply
 from .graph import Graph
 from .modules import GATNetwork, MinCutRefinement, PatchGraphConstructor, PatchSegmentPredictor, _layer_forward
 
@@ -107,6 +107,22 @@ class GraphBlock(nn.Module):
             h, S, labels, loss, _, G = ops.block_forward(
                 node_features, nph, npw, self._prepared(), D, layers[0].num_heads, layers[1].num_heads,
                 layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers))
+        elif needs_autograd or (self.training and any(l.dropout_rate > 0 for l in layers)):
+            # training: the same stages as differentiable ops (csrc/gat_backward.cu, ncut.cu, block_backward.cu)
+            g = Graph.grid(nph, npw, dev, B)
+            x = node_features.reshape(B * N, -1)
+            h = _train_layer(layers[0], x, g)                                           # :332
+            logits = _train_layer(layers[1], h, g)                                      # mincut_refinement.py:192
+            S, labels = softmax_rows_with_labels(logits)                                # :193, train_end_to_end.py:356
+            loss = ncut_loss_apply(h, S, g)                                             # :196
+            R = segment_mean_apply(h.view(B, N, D), labels.view(B, N), K)               # :368-373
+            if K > 1:                                                                   # :383-389
+                G = _train_layer(layers[2], R.reshape(B * K, D), Graph.complete(K, dev, B)).view(B, K, D)
+            else:
+                G = R
+            h, S, labels = h.view(B, N, D), S.view(B, N, K), labels.view(B, N)
+            f_g = unpool_apply(G, labels, nph, npw, H, W, out=out, out_dtype=dense_dtype) if want_dense else None
+            return GraphBlockOutput(f_g, loss, S, labels, h, G, (nph, npw))
         else:
             g = Graph.grid(nph, npw, dev, B)
             x = node_features.reshape(B * N, -1)
@@ -140,6 +156,14 @@ class GraphBlock(nn.Module):
                 stacks.append(torch.stack([hd.a.weight.detach().view(-1) for hd in heads], 0))
             self._prep_cache = (key, ops.block_prepare(*stacks, out=None if self._prep_cache is None else self._prep_cache[1]))
         return self._prep_cache[1]
+
+
+def _train_layer(layer, x: torch.Tensor, g: Graph) -> torch.Tensor:
+    """Differentiable multi-head layer on a block-diagonal batch: attention dropout inside the kernel, output
+    dropout (graph_attention.py:160) by ``nn.Dropout``; fp32 between stages like the inference path."""
+    out = _layer_forward(list(layer.heads), x, g, layer.concat, layer.alpha,
+                         att_dropout=layer.dropout_rate if layer.training else 0.0, out_dtype=torch.float32)
+    return layer.dropout(out)
 
 
 def _batched_layer(layer, x: torch.Tensor, g: Graph, out_dtype: torch.dtype) -> torch.Tensor:

@@ -84,3 +84,61 @@ def allreduce_graph_grads(module: torch.nn.Module, group: Optional[dist.ProcessG
         p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
     return off
+
+
+class OverlappedGather:
+    """Per-step all-gather of the small per-image outputs, issued on a side stream so that it overlaps
+    the next step's kernels instead of extending the step by the collective's launch latency.
+
+    ``push(out)`` packs ``(l_partition | region_features | hard_labels)`` of the local shard into one of
+    two rotating buffers on the current stream and enqueues ONE ``all_gather_into_tensor`` on the side
+    stream; ``latest()`` makes the current stream wait for the most recent gather and returns
+    :class:`GatheredOutputs` views of its result.  With two buffers a step never waits for its own
+    gather, only (at most) for the one issued two steps earlier.  Equal shard sizes are required
+    (``global_batch % world == 0``); use :func:`gather_block_outputs` otherwise."""
+
+    def __init__(self, B: int, N: int, K: int, D: int, device, group: Optional[dist.ProcessGroup] = None):
+        self.B, self.N, self.K, self.D, self.group = B, N, K, D, group
+        self.world = dist.get_world_size(group)
+        self.n_small = B * (1 + K * D + N)
+        self.packed = [torch.empty(self.n_small, dtype=torch.float32, device=device) for _ in range(2)]
+        self.gathered = [torch.empty(self.world * self.n_small, dtype=torch.float32, device=device) for _ in range(2)]
+        self.done = [None, None]
+        self.side = torch.cuda.Stream(device=device)
+        self.turn = 0
+
+    def push(self, l_partition: torch.Tensor, region_features: torch.Tensor, hard_labels: torch.Tensor) -> None:
+        i = self.turn
+        cur = torch.cuda.current_stream()
+        if self.done[i] is not None:
+            cur.wait_event(self.done[i])              # the gather that last read this buffer (two steps ago)
+        B, K, D, N = self.B, self.K, self.D, self.N
+        buf = self.packed[i]
+        torch.cat([l_partition.reshape(-1), region_features.reshape(-1), hard_labels.reshape(-1).view(torch.float32)],
+                  out=buf)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            dist.all_gather_into_tensor(self.gathered[i], buf, group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[i] = ev
+        self.turn = 1 - i
+
+    def latest(self) -> GatheredOutputs:
+        i = 1 - self.turn
+        if self.done[i] is None:
+            raise RuntimeError("OverlappedGather.latest() before any push()")
+        torch.cuda.current_stream().wait_event(self.done[i])
+        B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
+        g = self.gathered[i].view(W, self.n_small)
+        loss = g[:, :B].reshape(W * B)
+        reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
+        lab = g[:, B + B * K * D:].reshape(W * B, N).view(torch.int32)
+        return GatheredOutputs(loss, reg, lab)
+
+    def drain(self) -> None:
+        for ev in self.done:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)

@@ -66,7 +66,7 @@ class GraphAttentionLayer(nn.Module):
 
 
 def _layer_forward(heads: List[GraphAttentionLayer], x: torch.Tensor, edge_index, concat: bool, alpha: float,
-                   att_dropout: float) -> torch.Tensor:
+                   att_dropout: float, out_dtype=None) -> torch.Tensor:
     if isinstance(edge_index, Graph):
         g = edge_index
     else:
@@ -85,7 +85,7 @@ def _layer_forward(heads: List[GraphAttentionLayer], x: torch.Tensor, edge_index
         W = torch.stack([h.W.weight for h in heads], 0)
         a = torch.stack([h.a.weight.view(-1) for h in heads], 0)
     xp, Wp = _pad_in_dim(x, W)
-    return gat_layer_apply(xp, g, Wp, a, concat, alpha, att_dropout)
+    return gat_layer_apply(xp, g, Wp, a, concat, alpha, att_dropout, out_dtype)
 
 
 class MultiHeadGATLayer(nn.Module):

@@ -319,6 +319,51 @@ def ncut_backward(h, S, rowptr_out, col_out, rowptr_in, col_in, stats, grad_loss
 
 
 # ---------------------------------------------------------------------------------------------
+# backward of the glue stages (training)
+# ---------------------------------------------------------------------------------------------
+def unpool_nearest_backward(grad_out: torch.Tensor, labels: Optional[torch.Tensor], K: int, Hp: int, Wp: int) -> torch.Tensor:
+    """``grad_table (B,K,D)`` = sum of ``grad_out (B,D,H,W)`` over the pixels whose patch carries label k
+    (dual of :func:`unpool_nearest`)."""
+    _need_cuda(grad_out, labels)
+    if grad_out.dim() != 4:
+        raise ValueError("grad_out must be (B, D, H, W)")
+    if grad_out.stride()[1:] != (grad_out.shape[2] * grad_out.shape[3], grad_out.shape[3], 1):
+        grad_out = grad_out.contiguous()
+    B, D, H, W = grad_out.shape
+    if labels is not None:
+        labels = labels.contiguous()
+    work = torch.empty(int(_lib.load().mg_unpool_backward_work_bytes(B, D, Hp, Wp)), dtype=torch.uint8, device=grad_out.device)
+    gt = torch.empty((B, K, D), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        call("mg_unpool_nearest_backward", grad_out.data_ptr(), _dtype_code(grad_out.dtype),
+             grad_out.stride(0) if B > 1 else D * H * W, _ptr(labels), B, K, D, Hp, Wp, H, W, work.data_ptr(), gt.data_ptr(),
+             _stream())
+    return gt
+
+
+def segment_mean_backward(grad_out: torch.Tensor, labels: torch.Tensor, counts: torch.Tensor, N: int) -> torch.Tensor:
+    """``grad_h (B,N,D) = grad_out[b, labels[b,n], :] / counts[b, labels[b,n]]`` (dual of :func:`segment_mean`)."""
+    _need_cuda(grad_out, labels, counts)
+    grad_out = grad_out.contiguous().float()
+    B, K, D = grad_out.shape
+    gh = torch.empty((B, N, D), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        call("mg_segment_mean_backward", grad_out.data_ptr(), labels.contiguous().data_ptr(), counts.contiguous().data_ptr(),
+             B, N, D, K, 0, gh.data_ptr(), _stream())
+    return gh
+
+
+def softmax_backward(S: torch.Tensor, grad_S: torch.Tensor) -> torch.Tensor:
+    _need_cuda(S, grad_S)
+    S, grad_S = S.contiguous(), grad_S.contiguous().float()
+    N, K = S.shape
+    gl = torch.empty_like(S)
+    with torch.cuda.device(S.device):
+        call("mg_softmax_backward", S.data_ptr(), grad_S.data_ptr(), N, K, gl.data_ptr(), _stream())
+    return gl
+
+
+# ---------------------------------------------------------------------------------------------
 # fused per-image block
 # ---------------------------------------------------------------------------------------------
 def block_supported(B: int, Hp: int, Wp: int, in_dim: int, D: int, H1: int, H2: int, H3: int, K: int) -> bool:

@@ -207,3 +207,101 @@ def test_mincut_module_end_to_end_grads(mg):
     assert rel_err(gW, ps["patch_W"].grad) <= 1e-4
     gWp = torch.stack([hd.W.weight.grad for hd in pred_net.gat_layers[0].heads]).cpu()
     assert rel_err(gWp, ps["pred_W"].grad) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# glue-stage backward (un-pool, region pool, softmax) and the whole block's training path
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,D,H,W,K,dtype", [(2, 64, 64, 64, 2, torch.float32), (3, 8, 70, 75, 3, torch.float32),
+                                             (2, 64, 128, 96, 2, torch.bfloat16), (1, 16, 33, 47, 4, torch.float32)])
+def test_unpool_backward_vs_autograd(mg, B, D, H, W, K, dtype):
+    gen = torch.Generator().manual_seed(7)
+    hp, wp = O.grid_dims(H, W)
+    N = hp * wp
+    table = torch.randn(B, K, D, generator=gen)
+    labels = torch.randint(0, K, (B, N), generator=gen)
+    gout = torch.randn(B, D, H, W, generator=gen).to(dtype)
+    tr = table.clone().requires_grad_(True)
+    dense = torch.stack([O.unpool_nearest(tr[b][labels[b]], hp, wp, H, W) for b in range(B)])
+    (dense * gout.float()).sum().backward()
+    got = mg.ops.unpool_nearest_backward(gout.cuda(), labels.int().cuda(), K, hp, wp)
+    assert rel_err(got, tr.grad) <= (2e-6 if dtype == torch.float32 else 2e-6)     # bf16 grads are exact inputs, fp32 sums
+    # identity labels: per-patch sums
+    got2 = mg.ops.unpool_nearest_backward(gout.cuda(), None, N, hp, wp)
+    t2 = torch.randn(B, N, D, generator=gen).requires_grad_(True)
+    d2 = torch.stack([O.unpool_nearest(t2[b], hp, wp, H, W) for b in range(B)])
+    (d2 * gout.float()).sum().backward()
+    assert rel_err(got2, t2.grad) <= 2e-6
+
+
+def test_segment_mean_and_softmax_backward(mg):
+    from mingraph_unet_b200.autograd import segment_mean_apply, softmax_rows_with_labels
+    gen = torch.Generator().manual_seed(8)
+    B, N, D, K = 3, 50, 24, 4
+    h = torch.randn(B, N, D, generator=gen)
+    labels = torch.randint(0, K - 1, (B, N), generator=gen)              # region K-1 stays empty
+    w = torch.randn(B, K, D, generator=gen)
+    hr = h.clone().requires_grad_(True)
+    (torch.stack([O.region_mean_pool(hr[b], labels[b], K) for b in range(B)]) * w).sum().backward()
+    hg = h.cuda().requires_grad_(True)
+    R = segment_mean_apply(hg, labels.int().cuda(), K)
+    (R * w.cuda()).sum().backward()
+    assert rel_err(hg.grad, hr.grad) <= 1e-6
+    logits = torch.randn(200, 5, generator=gen)
+    gs = torch.randn(200, 5, generator=gen)
+    lr = logits.clone().requires_grad_(True)
+    (torch.softmax(lr, 1) * gs).sum().backward()
+    lg = logits.cuda().requires_grad_(True)
+    S, lab = softmax_rows_with_labels(lg)
+    assert torch.equal(lab.cpu().long(), torch.argmax(torch.softmax(logits, 1), 1))
+    (S * gs.cuda()).sum().backward()
+    assert rel_err(lg.grad, lr.grad) <= 2e-6
+
+
+@pytest.mark.parametrize("B,H,W,K", [(2, 64, 64, 2), (2, 70, 75, 3)])
+def test_block_training_step_grads_vs_oracle(mg, B, H, W, K):
+    """Whole block under autograd: dense-map loss + N-cut loss -> gradients of the node features and of all
+    three GAT nets, against torch autograd through the CPU restatement (per image, like the reference loop)."""
+    fin, D = 20, 64
+    gen = torch.Generator().manual_seed(11)
+    hp, wp = O.grid_dims(H, W)
+    N = hp * wp
+    P = {k: 0.5 * v for k, v in O.init_block_params(fin, D, 4, K, seed=5).items()}
+    x = 0.5 * torch.randn(B, N, fin, generator=gen)
+    wdense = torch.randn(B, D, H, W, generator=gen) / (H * W)
+    ps = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xr = x.clone().requires_grad_(True)
+    total = torch.zeros(())
+    hard_ref = []
+    for b in range(B):
+        o = O.graph_block_image(xr[b], H, W, ps, K=K)
+        total = total + (o["f_g"] * wdense[b]).sum() + 0.7 * o["loss"]
+        hard_ref.append(o["hard"])
+    total.backward()
+
+    blk = mg.GraphBlock(node_feature_dim=fin, num_segments=K, dropout_rate=0.0)
+    for name, net in (("patch", blk.patch_gat_model), ("pred", blk.segment_predictor.gnn_predictor),
+                      ("region", blk.region_gat_model)):
+        _load(net.gat_layers[0], P[f"{name}_W"], P[f"{name}_a"])
+        for m in net.modules():
+            if hasattr(m, "dropout_rate"):
+                m.dropout_rate = 0.0
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    blk = blk.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    out = blk(node_features=xg, image_size=(H, W))
+    assert torch.equal(out.hard_labels.cpu().long(), torch.stack(hard_ref))
+    tot = (out.f_g * wdense.cuda()).sum() + 0.7 * out.l_partition.sum()
+    assert float(tot.detach()) == pytest.approx(float(total.detach()), rel=2e-4, abs=1e-5)
+    tot.backward()
+    assert rel_err(xg.grad, xr.grad) <= 2e-4
+    for name, net in (("patch", blk.patch_gat_model), ("pred", blk.segment_predictor.gnn_predictor),
+                      ("region", blk.region_gat_model)):
+        heads = net.gat_layers[0].heads
+        gW = torch.stack([hd.W.weight.grad for hd in heads])
+        ga = torch.stack([hd.a.weight.grad.view(-1) for hd in heads])
+        assert rel_err(gW, ps[f"{name}_W"].grad) <= 3e-4, name
+        # K = 2 regions: every region node has ONE in-edge, alpha == 1 and d/da is identically ~0 (noise on both sides)
+        ref_a = ps[f"{name}_a"].grad
+        assert float((ga.cpu() - ref_a).abs().max()) <= 3e-4 * float(ref_a.abs().max()) + 1e-9, name
