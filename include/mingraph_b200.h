@@ -105,6 +105,10 @@ MG_API int mg_segment_mean(const float* h, const int32_t* labels, int B, int N, 
  *   head); statistically equivalent to torch's, not the same stream.
  * Empty graphs (E == 0) are rejected with MG_ERR_INVALID like the reference's RuntimeError. */
 MG_API int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int num_graphs);
+/* 1 if mg_gat_forward runs the node transform of this shape on the tensor pipe (tcgen05 tf32 MMA, csrc/gat_tc.cu:
+ * bf16 node features, inference, heads in {1,2,4}, in in {32,64,128,256} with heads*in <= 256, F % 16 == 0,
+ * 2*heads*F <= 512, N >= 4096), else 0 (FP32-pipe kernels). */
+MG_API int mg_gat_uses_tensor_pipe(int N, int in_dim, int out_dim, int heads, int concat, int x_dtype, int out_dtype);
 MG_API int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, int64_t E,
                    const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
                    int nodes_per_graph, float dropout_p, uint64_t seed, void* out, int out_dtype, void* work,

@@ -299,6 +299,10 @@ int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int num_gra
   return (int64_t)work_layout(N, in_dim, out_dim, heads, num_graphs > 0 ? num_graphs : 1, need_z).total;
 }
 
+int mg_gat_uses_tensor_pipe(int N, int in_dim, int out_dim, int heads, int concat, int x_dtype, int out_dtype) {
+  return (x_dtype == MG_BF16 && gat_tc_supported(N, in_dim, out_dim, heads, concat ? 1 : 0, out_dtype == MG_BF16 ? 1 : 0)) ? 1 : 0;
+}
+
 int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, int64_t E,
                    const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
                    int nodes_per_graph, float dropout_p, uint64_t seed, void* out, int out_dtype, void* work,
@@ -328,6 +332,12 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   float* u = reinterpret_cast<float*>(wb + wl.u_off);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+
+  // bf16 storage, inference: score pre-pass + transform on the tensor pipe (gat_tc.cu)
+  if (x_dtype == MG_BF16 && dropout_p == 0.f && !save_den && !save_z &&
+      gat_tc_supported(N, in_dim, out_dim, heads, concat ? 1 : 0, out_dtype == MG_BF16 ? 1 : 0))
+    return gat_tc_launch(x, rowptr, col, s, gmax, W, a, N, in_dim, out_dim, heads, concat ? 1 : 0, slope, nodes_per_graph, out,
+                         out_dtype == MG_BF16 ? 1 : 0, st);
 
   if ((rc = gat_scores_and_max(x, x_dtype, rowptr, col, N, W, a, in_dim, out_dim, heads, nodes_per_graph, s, gmax, u, st)))
     return rc;

@@ -1,0 +1,664 @@
+// K4 on the tensor pipe — fused multi-head GAT layer forward for bf16 node features
+// (MultiHeadGATLayer.forward, eval mode, model/gat/graph_attention.py:40-118,150-160).
+//
+// Same math as gat_fused_kernel (gat_kernels.cuh): one CSR gather of x_i serves every head,
+//   z_j^h = sum_i p_ij^h x_i / (den_j^h + 1e-10),  out_j = mean_h / concat_h ELU(W_h z_j^h),
+// but the per-head transform W_h z runs on the 5th-generation tensor cores:
+//   * a persistent CTA owns tiles of 128 destination nodes;
+//   * 16 gather warps (a group of in/8 lanes per destination, 16-byte bf16 row chunks, 4 rows in
+//     flight per group) accumulate z in registers and write it to shared memory as the UMMA A
+//     operand: K-major, 128-byte swizzle, one 16 KB block per (head, 32-wide K slice);
+//   * W_h sits in shared memory as the K-major B operand (staged once per CTA);
+//   * one elected thread issues tcgen05.mma (kind::tf32, M=128, N=F, K=8) into TMEM, one F-column
+//     accumulator block per head, double-buffered over tiles (2*heads*F <= 512 columns);
+//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), apply ELU and the head mean / concat and
+//     store the tile through a swizzled staging buffer with fully coalesced 16-byte writes,
+//     overlapping the next tile's gather.
+// Precision: x is bf16 (exact in tf32); z and W are read as tf32 (10-bit mantissa), accumulation
+// is fp32 in TMEM.  Used only for bf16 storage (tolerance 2e-2, north_star); the fp32 path stays
+// on the FP32 pipe to hold 1e-5.
+#include <stdlib.h>
+
+#include "gat_kernels.cuh"
+
+namespace mg {
+
+constexpr int kTcTile = 128;
+constexpr int kTcGatherWarps = 16;
+constexpr int kTcMmaWarp = kTcGatherWarps;
+constexpr int kTcEpiWarp0 = kTcGatherWarps + 1;
+constexpr int kTcThreads = (kTcGatherWarps + 1 + 4) * 32;   // 672
+constexpr int kTcHeader = 1024;                             // barriers + TMEM base pointer
+
+struct GatTcArgs {
+  const __nv_bfloat16* x;
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* s;          // (N, 2*heads)
+  const float* gmax;       // (G, heads)
+  const float* W;          // (heads, F, in)
+  void* out;
+  int N, F, concat, out_bf16, nodes_per_graph, tmem_cols;
+  float slope;
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TC_WAIT_DONE;\n"
+      "bra TC_WAIT_LOOP;\n"
+      "TC_WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// K-major operand, 128-byte swizzle: 8-row atoms of 1024 B (SBO), LBO unused for swizzled K-major (encoded 1)
+__device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (16 B units)
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tc_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ELU for the bf16 path: exp(v) - 1 through the hardware ex2 (abs. error ~1e-7, far inside the 2e-2 budget); the
+// accurate expm1f costs ~30 dependent instructions per element and made the 4 epilogue warps the bottleneck
+__device__ __forceinline__ float tc_elu(float v) { return v > 0.f ? v : tc_ex2(v * 1.4426950408889634f) - 1.f; }
+
+template <int NH>
+__device__ __forceinline__ void load_scores(const float* p, float (&o)[NH]);
+template <>
+__device__ __forceinline__ void load_scores<1>(const float* p, float (&o)[1]) { o[0] = __ldg(p); }
+template <>
+__device__ __forceinline__ void load_scores<2>(const float* p, float (&o)[2]) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  o[0] = v.x; o[1] = v.y;
+}
+template <>
+__device__ __forceinline__ void load_scores<4>(const float* p, float (&o)[4]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+
+// shared-memory carve-up (byte offsets from the 1024-aligned base)
+struct TcSmem {
+  int a_off, b_off, stage_off, total;
+  int a_block, b_block, kblocks;    // bytes per (head, k-slice) block of A / B; k-slices per head
+};
+__host__ __device__ inline TcSmem tc_smem_layout(int heads, int in_dim, int F, bool staged) {
+  TcSmem L;
+  L.kblocks = in_dim / 32;
+  L.a_block = kTcTile * 128;
+  L.b_block = F * 128;
+  int o = kTcHeader;
+  L.a_off = o;     o += heads * L.kblocks * L.a_block;
+  L.b_off = o;     o += heads * L.kblocks * L.b_block;
+  o = (o + 1023) & ~1023;
+  L.stage_off = o; o += staged ? kTcTile * F * 2 : 0;
+  L.total = o + 1024;               // slack for the manual 1024-byte alignment of the dynamic base
+  return L;
+}
+
+// ---- pre-pass 1: attention scalars s[n] = (x_n . u_src[h], x_n . u_tgt[h]) -------------------------------------
+// u_src[h] = W_h^T a_h[:F], u_tgt[h] = W_h^T a_h[F:] are recomputed per block (<= 512 x F MACs) into shared memory;
+// a group of LPN lanes owns a node (16 bytes of the bf16 row per lane).  Also resets the per-graph maxima.
+template <int NH, int LPN>
+__global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __restrict__ x, int N,
+                                                        const float* __restrict__ W, const float* __restrict__ a, int F,
+                                                        int num_graphs, float* __restrict__ s, float* __restrict__ gmax) {
+  constexpr int IN = LPN * 8, NQ = 2 * NH;
+  constexpr int FP = 256 / IN;                                 // f-partitions: thread = (f-partition, input column)
+  __shared__ float u_s[NQ * IN];
+  __shared__ float u_part[FP][NQ * IN];
+  {
+    const int i = threadIdx.x % IN, fp = threadIdx.x / IN;
+    float acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const float* Wh = W + (size_t)h * F * IN + i;
+      const float* ah = a + (size_t)h * 2 * F;
+#pragma unroll 8
+      for (int f = fp; f < F; f += FP) {                        // independent, coalesced loads: pipelined
+        const float w = __ldg(Wh + (size_t)f * IN);
+        acc[h] = fmaf(__ldg(ah + f), w, acc[h]);
+        acc[NH + h] = fmaf(__ldg(ah + F + f), w, acc[NH + h]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) u_part[fp][q * IN + i] = acc[q];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NQ * IN; idx += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int fp = 0; fp < FP; ++fp) v += u_part[fp][idx];
+    u_s[idx] = v;
+  }
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < num_graphs * NH; i += blockDim.x) gmax[i] = -INFINITY;
+  __syncthreads();
+  const int gl = threadIdx.x % LPN;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPN, ngroups = (gridDim.x * blockDim.x) / LPN;
+  for (int n0 = group; n0 - (group % (32 / LPN)) < N; n0 += ngroups) {       // warp-uniform trip count
+    const int n = n0 < N ? n0 : N - 1;
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + (size_t)n * IN) + gl);
+    float xf[8];
+    xf[0] = __uint_as_float(xv.x << 16); xf[1] = __uint_as_float(xv.x & 0xffff0000u);
+    xf[2] = __uint_as_float(xv.y << 16); xf[3] = __uint_as_float(xv.y & 0xffff0000u);
+    xf[4] = __uint_as_float(xv.z << 16); xf[5] = __uint_as_float(xv.z & 0xffff0000u);
+    xf[6] = __uint_as_float(xv.w << 16); xf[7] = __uint_as_float(xv.w & 0xffff0000u);
+    float part[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float4 u0 = *reinterpret_cast<const float4*>(u_s + q * IN + gl * 8);
+      const float4 u1 = *reinterpret_cast<const float4*>(u_s + q * IN + gl * 8 + 4);
+      float acc = xf[0] * u0.x;
+      acc = fmaf(xf[1], u0.y, acc); acc = fmaf(xf[2], u0.z, acc); acc = fmaf(xf[3], u0.w, acc);
+      acc = fmaf(xf[4], u1.x, acc); acc = fmaf(xf[5], u1.y, acc); acc = fmaf(xf[6], u1.z, acc); acc = fmaf(xf[7], u1.w, acc);
+      part[q] = acc;
+    }
+#pragma unroll
+    for (int o = 1; o < LPN; o <<= 1)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) part[q] += __shfl_xor_sync(kFull, part[q], o, LPN);
+#pragma unroll
+    for (int q0 = 0; q0 < NQ; q0 += LPN) {                      // lane gl stores scalars q0 + gl
+      float mine = part[q0];
+#pragma unroll
+      for (int q = 1; q < LPN; ++q)
+        if (q0 + q < NQ) mine = (gl == q) ? part[q0 + q] : mine;
+      if (n0 < N && q0 + gl < NQ) s[(size_t)n * NQ + q0 + gl] = mine;
+    }
+  }
+}
+
+// ---- pre-pass 2: exact per-graph maximum of s_src[i] + s_tgt[j] over the edges (graph_attention.py:86) ----------
+// 8 lanes per destination; each block owns a contiguous node range and issues one atomic max per head when the
+// range lies in one graph (order-independent, hence deterministic).
+template <int NH>
+__global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                          const float* __restrict__ s, int N, int nodes_per_graph,
+                                                          int nodes_per_block, float* __restrict__ gmax) {
+  constexpr int NQ = 2 * NH;
+  __shared__ float red[8][NH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = threadIdx.x & 7, gi = threadIdx.x >> 3;                       // 32 groups of 8 lanes
+  const int start = blockIdx.x * nodes_per_block, stop = min(N, start + nodes_per_block);
+  float m_run[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) m_run[h] = -INFINITY;
+  int g_run = -1;
+  for (int j = start + gi; j < stop; j += 32) {
+    const int g = nodes_per_graph > 0 ? j / nodes_per_graph : 0;
+    if (g != g_run) {
+      if (g_run >= 0 && gl == 0) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+          if (m_run[h] > -INFINITY) atomic_max_f32(gmax + (size_t)g_run * NH + h, m_run[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < NH; ++h) m_run[h] = -INFINITY;
+      g_run = g;
+    }
+    const int beg = __ldg(rowptr + j), end = __ldg(rowptr + j + 1);
+    float m[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) m[h] = -INFINITY;
+    for (int k = beg + gl; k < end; k += 8) {
+      float sv[NH];
+      load_scores<NH>(s + (size_t)__ldg(col + k) * NQ, sv);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) m[h] = fmaxf(m[h], sv[h]);
+    }
+    float st[NH];
+    load_scores<NH>(s + (size_t)j * NQ + NH, st);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      m[h] = fmaxf(m[h], __shfl_xor_sync(kFull, m[h], 1, 8));
+      m[h] = fmaxf(m[h], __shfl_xor_sync(kFull, m[h], 2, 8));
+      m[h] = fmaxf(m[h], __shfl_xor_sync(kFull, m[h], 4, 8));
+      m_run[h] = fmaxf(m_run[h], m[h] + st[h]);                                // -inf stays -inf for isolated nodes
+    }
+  }
+  const int g_first = nodes_per_graph > 0 ? start / nodes_per_graph : 0;
+  const bool uniform = __syncthreads_and(g_run < 0 || g_run == g_first) != 0;
+  if (uniform) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      float v = m_run[h];
+#pragma unroll
+      for (int o = 8; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+      if (lane == 0) red[warp][h] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NH) {
+      float v = red[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w][threadIdx.x]);
+      if (v > -INFINITY && start < N) atomic_max_f32(gmax + (size_t)g_first * NH + threadIdx.x, v);
+    }
+  } else if (g_run >= 0 && gl == 0) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+      if (m_run[h] > -INFINITY) atomic_max_f32(gmax + (size_t)g_run * NH + h, m_run[h]);
+  }
+}
+
+// NH heads (1, 2, 4), LPN lanes per destination node (in_dim = 8 * LPN bf16 = 16 B per lane)
+template <int NH, int LPN>
+__global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A) {
+  constexpr int IN = LPN * 8;
+  constexpr int NPW = 32 / LPN;                              // destination nodes per warp per pass
+  constexpr int NODES_PER_PASS = kTcGatherWarps * NPW;
+  constexpr int PASSES = kTcTile / NODES_PER_PASS;
+  constexpr int EPI = LPN < 8 ? LPN : 8;                     // edges (= source rows in flight) per group iteration
+  constexpr int KB = IN / 32;                                // 32-wide K slices per head
+  static_assert(PASSES >= 1 && NH * IN <= 256, "tile does not fit");
+
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  const bool staged = A.out_bf16 && !A.concat;
+  const TcSmem L = tc_smem_layout(NH, IN, A.F, staged);
+  const uint32_t bar_a_full = tc_smem_u32(sm + 0), bar_a_empty = tc_smem_u32(sm + 8);
+  const uint32_t bar_t_full0 = tc_smem_u32(sm + 16), bar_t_empty0 = tc_smem_u32(sm + 32);   // [2] each, 8 B apart
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + 64);
+  unsigned char* As = sm + L.a_off;
+  unsigned char* Bs = sm + L.b_off;
+  unsigned char* Ss = sm + L.stage_off;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = A.F;
+  const int ntiles = ceil_div(A.N, kTcTile);
+
+  if (tid == 0) {
+    tc_mbar_init(bar_a_full, kTcGatherWarps);
+    tc_mbar_init(bar_a_empty, 1);
+    tc_mbar_init(bar_t_full0, 1);
+    tc_mbar_init(bar_t_full0 + 8, 1);
+    tc_mbar_init(bar_t_empty0, 4);
+    tc_mbar_init(bar_t_empty0 + 8, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kTcMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_ptr_s)),
+                 "r"(A.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // W -> B operand blocks: element (h, f, i) -> block (h, i/32), row f, 16-byte chunk ((i%32)/4) ^ (f&7)
+  for (int idx = tid; idx < NH * F * (IN / 4); idx += kTcThreads) {
+    const int i4 = idx % (IN / 4);
+    const int f = (idx / (IN / 4)) % F;
+    const int h = idx / ((IN / 4) * F);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(A.W + ((size_t)h * F + f) * IN) + i4);
+    const int kb = i4 >> 3, chunk = i4 & 7;
+    *reinterpret_cast<float4*>(Bs + (size_t)(h * KB + kb) * L.b_block + f * 128 + ((chunk ^ (f & 7)) << 4)) = w;
+  }
+  tc_fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp < kTcGatherWarps) {
+    // =========================== gather warps: z tile -> A operand ===========================
+    // A group of LPN lanes owns one destination node; lane gl holds dims [8*gl, 8*gl+8) of every head's z.
+    // Score step: lane gl < EPI computes the attention numerators of edge slot gl for all heads; the group
+    // then streams the EPI source rows (16 bytes per lane per row, all in flight together).
+    const int gl = lane % LPN, grp = lane / LPN;
+    constexpr int two_h = 2 * NH;
+    constexpr float kLog2e = 1.4426950408889634f;
+    auto node_of = [&](int tile_base, int pass) { return tile_base + pass * NODES_PER_PASS + warp * NPW + grp; };
+    int nbeg = 0, nend = 0;                                   // row pointers of the NEXT (tile, pass), prefetched
+    {
+      const int j0 = node_of(blockIdx.x * kTcTile, 0);
+      if ((int)blockIdx.x < ntiles && j0 < A.N) { nbeg = __ldg(A.rowptr + j0); nend = __ldg(A.rowptr + j0 + 1); }
+    }
+    for (int it = 0, tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int tile_base = tile * kTcTile;
+#pragma unroll 1
+      for (int pass = 0; pass < PASSES; ++pass) {
+        const int q = pass * NODES_PER_PASS + warp * NPW + grp;
+        const int j = tile_base + q;
+        const bool node_ok = j < A.N;
+        const int beg = nbeg, end = nend;
+        {                                                     // prefetch the next pass's row pointers
+          const bool last = pass == PASSES - 1;
+          const int tb = last ? (tile + (int)gridDim.x) * kTcTile : tile_base;
+          const int jn = node_of(tb, last ? 0 : pass + 1);
+          nbeg = nend = 0;
+          if ((!last || tile + (int)gridDim.x < ntiles) && jn < A.N) { nbeg = __ldg(A.rowptr + jn); nend = __ldg(A.rowptr + jn + 1); }
+        }
+        const int g = (A.nodes_per_graph > 0 && node_ok) ? j / A.nodes_per_graph : 0;
+        float stgt[NH], Mh[NH], den[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          stgt[h] = 0.f; Mh[h] = 0.f; den[h] = 0.f;
+        }
+        if (node_ok && gl < EPI) {
+          load_scores<NH>(A.s + (size_t)j * two_h + NH, stgt);
+          load_scores<NH>(A.gmax + (size_t)g * NH, Mh);
+#pragma unroll
+          for (int h = 0; h < NH; ++h) Mh[h] = leaky_relu(Mh[h], A.slope);
+        }
+        float z[NH][8];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int d = 0; d < 8; ++d) z[h][d] = 0.f;
+        const int iters = (end - beg + EPI - 1) / EPI;
+        const int max_iters = __reduce_max_sync(kFull, iters);
+        for (int itr = 0; itr < max_iters; ++itr) {
+          const int k0 = beg + itr * EPI;
+          const int ke = k0 + gl;
+          const bool ev = gl < EPI && ke < end;
+          const int srcn = ev ? __ldg(A.col + ke) : 0;
+          // source rows first (their address only needs col), then the scores
+          uint4 xv[EPI];
+#pragma unroll
+          for (int e = 0; e < EPI; ++e) {
+            const int sn = __shfl_sync(kFull, srcn, e, LPN);
+            xv[e] = make_uint4(0u, 0u, 0u, 0u);
+            if (k0 + e < end) xv[e] = __ldg(reinterpret_cast<const uint4*>(A.x + (size_t)sn * IN) + gl);
+          }
+          float pv[NH];
+          {
+            float ssrc[NH];
+            load_scores<NH>(A.s + (size_t)srcn * two_h, ssrc);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              const float e = leaky_relu(ssrc[h] + stgt[h], A.slope);
+              pv[h] = ev ? tc_ex2((e - Mh[h]) * kLog2e) : 0.f;
+              den[h] += pv[h];
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < EPI; ++e) {
+            float xf[8];
+            xf[0] = __uint_as_float(xv[e].x << 16); xf[1] = __uint_as_float(xv[e].x & 0xffff0000u);
+            xf[2] = __uint_as_float(xv[e].y << 16); xf[3] = __uint_as_float(xv[e].y & 0xffff0000u);
+            xf[4] = __uint_as_float(xv[e].z << 16); xf[5] = __uint_as_float(xv[e].z & 0xffff0000u);
+            xf[6] = __uint_as_float(xv[e].w << 16); xf[7] = __uint_as_float(xv[e].w & 0xffff0000u);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              const float ph = __shfl_sync(kFull, pv[h], e, LPN);
+#pragma unroll
+              for (int d = 0; d < 8; ++d) z[h][d] = fmaf(ph, xf[d], z[h][d]);
+            }
+          }
+        }
+        // softmax denominators: sum over the EPI edge-slot lanes (lanes >= EPI hold 0), broadcast from lane 0
+        float inv[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+#pragma unroll
+          for (int o = 1; o < EPI; o <<= 1) den[h] += __shfl_xor_sync(kFull, den[h], o, LPN);
+          inv[h] = 1.f / (__shfl_sync(kFull, den[h], 0, LPN) + 1e-10f);                        // graph_attention.py:96
+        }
+        if (it > 0 && pass == 0) tc_mbar_wait(bar_a_empty, (uint32_t)((it - 1) & 1));          // previous tile's MMAs done
+        // row q of the A operand: head h, K columns [gl*8, gl*8+8) = 2 chunks of slice gl/4
+        const int kb = gl >> 2, c0 = (gl & 3) * 2, sw = q & 7;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          unsigned char* rowp = As + (size_t)(h * KB + kb) * L.a_block + q * 128;
+          const float iv = inv[h];
+          *reinterpret_cast<float4*>(rowp + (((c0) ^ sw) << 4)) =
+              make_float4(z[h][0] * iv, z[h][1] * iv, z[h][2] * iv, z[h][3] * iv);
+          *reinterpret_cast<float4*>(rowp + (((c0 + 1) ^ sw) << 4)) =
+              make_float4(z[h][4] * iv, z[h][5] * iv, z[h][6] * iv, z[h][7] * iv);
+        }
+      }
+      tc_fence_async_smem();                                  // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(bar_a_full);
+    }
+  } else if (warp == kTcMmaWarp) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=F, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+      for (int it = 0, tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int stg = it & 1, n = it >> 1;
+        tc_mbar_wait(bar_a_full, (uint32_t)(it & 1));
+        if (n > 0) tc_mbar_wait(bar_t_empty0 + 8 * stg, (uint32_t)((n - 1) & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(stg * NH * F + h * F);
+#pragma unroll 1
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t ad = tc_desc_sw128(tc_smem_u32(As + (size_t)(h * KB + kb) * L.a_block));
+            const uint64_t bd = tc_desc_sw128(tc_smem_u32(Bs + (size_t)(h * KB + kb) * L.b_block));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                       // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
+              tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+        }
+        tc_commit(bar_a_empty);                               // A may be overwritten once these MMAs retire
+        tc_commit(bar_t_full0 + 8 * stg);                     // accumulators of this tile are complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue warps: TMEM -> ELU -> mean/concat -> global ===========================
+    const int ew = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;
+    const int et = (warp - kTcEpiWarp0) * 32 + lane;          // 0..127 linear id among epilogue threads
+    const float inv_h = 1.f / (float)NH;
+    const int out_w = A.concat ? NH * F : F;
+    const int cpr = F / 8;                                    // 16-byte chunks per staged bf16 row
+    const int swz_mask = ((cpr & (cpr - 1)) == 0) ? (min(cpr, 8) - 1) : 0;
+    for (int it = 0, tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int stg = it & 1, n = it >> 1;
+      const int tile_base = tile * kTcTile;
+      const int node = tile_base + row;
+      tc_mbar_wait(bar_t_full0 + 8 * stg, (uint32_t)(n & 1));
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(stg * NH * F);
+      for (int c0 = 0; c0 < F; c0 += 32) {
+        const int ncol = min(32, F - c0);                     // 32 or 16 (F % 16 == 0)
+        float oacc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) oacc[i] = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+          uint32_t v[32];
+          if (ncol == 32) tc_tmem_ld32(t_row + (uint32_t)(h * F + c0), v);
+          else tc_tmem_ld16(t_row + (uint32_t)(h * F + c0), v);
+          tc_tmem_wait_ld();
+          if (A.concat) {
+            if (node < A.N) {
+              const size_t o = (size_t)node * out_w + (size_t)h * F + c0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (i >= ncol) break;
+                float e8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) e8[u] = tc_elu(__uint_as_float(v[i + u]));
+                if (A.out_bf16) {
+                  uint4 pk;
+                  __nv_bfloat162 b0 = __floats2bfloat162_rn(e8[0], e8[1]), b1 = __floats2bfloat162_rn(e8[2], e8[3]),
+                                 b2 = __floats2bfloat162_rn(e8[4], e8[5]), b3 = __floats2bfloat162_rn(e8[6], e8[7]);
+                  pk.x = *reinterpret_cast<unsigned*>(&b0); pk.y = *reinterpret_cast<unsigned*>(&b1);
+                  pk.z = *reinterpret_cast<unsigned*>(&b2); pk.w = *reinterpret_cast<unsigned*>(&b3);
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + o + i) = pk;
+                } else {
+                  float* op = reinterpret_cast<float*>(A.out) + o + i;
+                  *reinterpret_cast<float4*>(op) = make_float4(e8[0], e8[1], e8[2], e8[3]);
+                  *reinterpret_cast<float4*>(op + 4) = make_float4(e8[4], e8[5], e8[6], e8[7]);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncol) oacc[i] += tc_elu(__uint_as_float(v[i]));          // ELU per head, then mean (:118,158)
+          }
+        }
+        if (!A.concat) {
+          if (staged) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (i >= ncol) break;
+              uint4 pk;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(oacc[i] * inv_h, oacc[i + 1] * inv_h),
+                             b1 = __floats2bfloat162_rn(oacc[i + 2] * inv_h, oacc[i + 3] * inv_h),
+                             b2 = __floats2bfloat162_rn(oacc[i + 4] * inv_h, oacc[i + 5] * inv_h),
+                             b3 = __floats2bfloat162_rn(oacc[i + 6] * inv_h, oacc[i + 7] * inv_h);
+              pk.x = *reinterpret_cast<unsigned*>(&b0); pk.y = *reinterpret_cast<unsigned*>(&b1);
+              pk.z = *reinterpret_cast<unsigned*>(&b2); pk.w = *reinterpret_cast<unsigned*>(&b3);
+              const int chunk = (c0 + i) >> 3;
+              *reinterpret_cast<uint4*>(Ss + (size_t)row * F * 2 + ((chunk ^ (row & swz_mask)) << 4)) = pk;
+            }
+          } else if (node < A.N) {
+            float* op = reinterpret_cast<float*>(A.out) + (size_t)node * out_w + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              if (i < ncol)
+                *reinterpret_cast<float4*>(op + i) =
+                  make_float4(oacc[i] * inv_h, oacc[i + 1] * inv_h, oacc[i + 2] * inv_h, oacc[i + 3] * inv_h);
+          }
+        }
+      }
+      // TMEM stage drained: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(bar_t_empty0 + 8 * stg);
+      if (staged) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // the tile's rows are contiguous in the output: coalesced 16-byte stores
+        const int valid_rows = min(kTcTile, A.N - tile_base);
+        const int nchunks = valid_rows * cpr;
+        uint4* gdst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + (size_t)tile_base * F);
+        for (int idx = et; idx < nchunks; idx += 128) {
+          const int r = idx / cpr, c = idx - r * cpr;
+          gdst[idx] = *reinterpret_cast<const uint4*>(Ss + (size_t)r * F * 2 + ((c ^ (r & swz_mask)) << 4));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kTcMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(A.tmem_cols) : "memory");
+  }
+}
+
+template <int NH, int LPN>
+static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, size_t smem, int grid, cudaStream_t st) {
+  auto k = gat_tc_kernel<NH, LPN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("gat_tc_kernel: cannot raise dynamic shared memory");
+      return MG_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int G = A.nodes_per_graph > 0 ? A.N / A.nodes_per_graph : 1;
+  int rc;
+  const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)A.N * LPN, 256), (int64_t)num_sms() * 8);
+  tc_scores_kernel<NH, LPN><<<sgrid, 256, 0, st>>>(A.x, A.N, A.W, a, A.F, G, s, gmax);
+  if ((rc = check_launch("tc_scores_kernel"))) return rc;
+  const int mblocks = std::min(ceil_div(A.N, 32), num_sms() * 8);
+  const int npb = ceil_div(ceil_div(A.N, mblocks), 32) * 32;
+  tc_edge_max_kernel<NH><<<ceil_div(A.N, npb), 256, 0, st>>>(A.rowptr, A.col, s, A.N, A.nodes_per_graph, npb, gmax);
+  if ((rc = check_launch("tc_edge_max_kernel"))) return rc;
+  k<<<grid, kTcThreads, smem, st>>>(A);
+  return check_launch("gat_tc_kernel");
+}
+
+// Shapes the tensor-pipe kernel takes (everything else stays on the FP32-pipe kernels).
+bool gat_tc_supported(int N, int in_dim, int F, int heads, int concat, int out_bf16) {
+  static const int enabled = getenv("MG_GAT_TC") ? atoi(getenv("MG_GAT_TC")) : 1;
+  static const int min_nodes = getenv("MG_GAT_TC_MIN_NODES") ? atoi(getenv("MG_GAT_TC_MIN_NODES")) : 4096;
+  if (!enabled || N < min_nodes) return false;
+  if (!(heads == 1 || heads == 2 || heads == 4)) return false;
+  if (!(in_dim == 32 || in_dim == 64 || in_dim == 128 || in_dim == 256) || heads * in_dim > 256) return false;
+  if (F % 16 != 0 || F < 16 || F > 256 || 2 * heads * F > 512) return false;
+  const TcSmem L = tc_smem_layout(heads, in_dim, F, out_bf16 && !concat);
+  return L.total <= 227 * 1024;
+}
+
+int gat_tc_launch(const void* x, const int32_t* rowptr, const int32_t* col, float* s, float* gmax, const float* W,
+                  const float* a, int N, int in_dim, int F, int heads, int concat, float slope, int nodes_per_graph, void* out,
+                  int out_bf16, cudaStream_t st) {
+  GatTcArgs A;
+  A.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  A.rowptr = rowptr; A.col = col; A.s = s; A.gmax = gmax; A.W = W; A.out = out;
+  A.N = N; A.F = F; A.concat = concat; A.out_bf16 = out_bf16; A.nodes_per_graph = nodes_per_graph; A.slope = slope;
+  int cols = 32;
+  while (cols < 2 * heads * F) cols <<= 1;
+  A.tmem_cols = cols;
+  const TcSmem L = tc_smem_layout(heads, in_dim, F, out_bf16 && !concat);
+  const int grid = std::min(ceil_div(N, kTcTile), num_sms());
+  const int lpn = in_dim / 8;
+#define MG_TC(NHH, LL) \
+  if (heads == NHH && lpn == LL) return launch_tc<NHH, LL>(A, a, s, gmax, (size_t)L.total, grid, st);
+  MG_TC(4, 8) MG_TC(4, 4) MG_TC(2, 16) MG_TC(2, 8) MG_TC(2, 4) MG_TC(1, 32) MG_TC(1, 16) MG_TC(1, 8) MG_TC(1, 4)
+#undef MG_TC
+  set_error("gat_tc: no variant for heads=%d in=%d", heads, in_dim);
+  return MG_ERR_UNSUPPORTED;
+}
+
+}  // namespace mg
