@@ -25,9 +25,9 @@ namespace mg {
 
 constexpr int kTcTile = 128;
 constexpr int kTcGatherWarps = 16;
-constexpr int kTcMmaWarp = kTcGatherWarps;
-constexpr int kTcEpiWarp0 = kTcGatherWarps + 1;
-constexpr int kTcThreads = (kTcGatherWarps + 1 + 4) * 32;   // 672
+constexpr int kTcEpiWarp0 = kTcGatherWarps;                 // 4 epilogue warps; the first one also issues the MMAs
+constexpr int kTcMmaWarp = kTcEpiWarp0;
+constexpr int kTcThreads = (kTcGatherWarps + 4) * 32;       // 640 -> 96 registers per thread
 constexpr int kTcHeader = 1024;                             // barriers + TMEM base pointer
 
 struct GatTcArgs {
@@ -62,6 +62,23 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+// same, with a short back-off between polls (roles whose wait is long: they must not steal issue slots)
+__device__ __forceinline__ void tc_mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
 }
 __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -101,7 +118,7 @@ __device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tc_tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tc_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -119,7 +136,9 @@ __device__ __forceinline__ float tc_ex2(float x) {
 
 // ELU for the bf16 path: exp(v) - 1 through the hardware ex2 (abs. error ~1e-7, far inside the 2e-2 budget); the
 // accurate expm1f costs ~30 dependent instructions per element and made the 4 epilogue warps the bottleneck
-__device__ __forceinline__ float tc_elu(float v) { return v > 0.f ? v : tc_ex2(v * 1.4426950408889634f) - 1.f; }
+__device__ __forceinline__ float tc_elu(float v) {
+  return fmaxf(v, 0.f) + (tc_ex2(fminf(v, 0.f) * 1.4426950408889634f) - 1.f);      // branch-free
+}
 
 template <int NH>
 __device__ __forceinline__ void load_scores(const float* p, float (&o)[NH]);
@@ -195,37 +214,50 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < num_graphs * NH; i += blockDim.x) gmax[i] = -INFINITY;
   __syncthreads();
-  const int gl = threadIdx.x % LPN;
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / LPN, ngroups = (gridDim.x * blockDim.x) / LPN;
-  for (int n0 = group; n0 - (group % (32 / LPN)) < N; n0 += ngroups) {       // warp-uniform trip count
-    const int n = n0 < N ? n0 : N - 1;
-    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + (size_t)n * IN) + gl);
-    float xf[8];
-    xf[0] = __uint_as_float(xv.x << 16); xf[1] = __uint_as_float(xv.x & 0xffff0000u);
-    xf[2] = __uint_as_float(xv.y << 16); xf[3] = __uint_as_float(xv.y & 0xffff0000u);
-    xf[4] = __uint_as_float(xv.z << 16); xf[5] = __uint_as_float(xv.z & 0xffff0000u);
-    xf[6] = __uint_as_float(xv.w << 16); xf[7] = __uint_as_float(xv.w & 0xffff0000u);
-    float part[NQ];
+  // s = X U^T on mma.sync m16n8k16 (bf16 x bf16 -> f32): a warp takes 16 nodes per step.  x is bf16 already; u is split
+  // into bf16 hi + lo parts (two MMAs), so the products carry ~16 mantissa bits of u and the sums are fp32.  The k index
+  // of the MMA is a permutation of the feature index chosen so that every lane feeds whole 16-byte row chunks.
+  constexpr int CH = IN / 32;                                  // 16-byte chunks per lane per row
+  constexpr int STEPS = IN / 16;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t bhi[STEPS][2], blo[STEPS][2];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float4 u0 = *reinterpret_cast<const float4*>(u_s + q * IN + gl * 8);
-      const float4 u1 = *reinterpret_cast<const float4*>(u_s + q * IN + gl * 8 + 4);
-      float acc = xf[0] * u0.x;
-      acc = fmaf(xf[1], u0.y, acc); acc = fmaf(xf[2], u0.z, acc); acc = fmaf(xf[3], u0.w, acc);
-      acc = fmaf(xf[4], u1.x, acc); acc = fmaf(xf[5], u1.y, acc); acc = fmaf(xf[6], u1.z, acc); acc = fmaf(xf[7], u1.w, acc);
-      part[q] = acc;
+  for (int m = 0; m < STEPS; ++m)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int jj = 2 * m + r;                                // pair register jj of this lane: chunk (jj/4)*4 + t, pair jj%4
+      const int k = ((jj >> 2) * 4 + t) * 8 + 2 * (jj & 3);
+      const float u0 = g < NQ ? u_s[g * IN + k] : 0.f, u1 = g < NQ ? u_s[g * IN + k + 1] : 0.f;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(u0), h1 = __float2bfloat16_rn(u1);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(u0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(u1 - __bfloat162float(h1));
+      bhi[m][r] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      blo[m][r] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int base = wid * 16; base < N; base += nw * 16) {
+    const int r0 = min(base + g, N - 1), r1 = min(base + g + 8, N - 1);
+    uint4 x0[CH], x1[CH];
 #pragma unroll
-    for (int o = 1; o < LPN; o <<= 1)
+    for (int c = 0; c < CH; ++c) {
+      x0[c] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r0 * IN) + c * 4 + t);
+      x1[c] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r1 * IN) + c * 4 + t);
+    }
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) part[q] += __shfl_xor_sync(kFull, part[q], o, LPN);
-#pragma unroll
-    for (int q0 = 0; q0 < NQ; q0 += LPN) {                      // lane gl stores scalars q0 + gl
-      float mine = part[q0];
-#pragma unroll
-      for (int q = 1; q < LPN; ++q)
-        if (q0 + q < NQ) mine = (gl == q) ? part[q0 + q] : mine;
-      if (n0 < N && q0 + gl < NQ) s[(size_t)n * NQ + q0 + gl] = mine;
+    for (int m = 0; m < STEPS; ++m) {
+      const int c = m >> 1;
+      const uint32_t a0 = (m & 1) ? x0[c].z : x0[c].x, a2 = (m & 1) ? x0[c].w : x0[c].y;
+      const uint32_t a1 = (m & 1) ? x1[c].z : x1[c].x, a3 = (m & 1) ? x1[c].w : x1[c].y;
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bhi[m][0]), "r"(bhi[m][1]));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(blo[m][0]), "r"(blo[m][1]));
+    }
+    if (2 * t < NQ) {
+      if (base + g < N) *reinterpret_cast<float2*>(s + (size_t)(base + g) * NQ + 2 * t) = make_float2(c0, c1);
+      if (base + g + 8 < N) *reinterpret_cast<float2*>(s + (size_t)(base + g + 8) * NQ + 2 * t) = make_float2(c2, c3);
     }
   }
 }
@@ -366,26 +398,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
     const int gl = lane % LPN, grp = lane / LPN;
     constexpr int two_h = 2 * NH;
     constexpr float kLog2e = 1.4426950408889634f;
-    auto node_of = [&](int tile_base, int pass) { return tile_base + pass * NODES_PER_PASS + warp * NPW + grp; };
-    int nbeg = 0, nend = 0;                                   // row pointers of the NEXT (tile, pass), prefetched
+    // passes are numbered linearly over this CTA's tiles: pc = it * PASSES + pass
+    auto node_at = [&](int pc) {
+      const int t = (int)blockIdx.x + (pc / PASSES) * (int)gridDim.x;
+      const int j = t * kTcTile + (pc % PASSES) * NODES_PER_PASS + warp * NPW + grp;
+      return (t < ntiles && j < A.N) ? j : -1;
+    };
+    // software pipeline: row pointers two passes ahead, the first column chunk one pass ahead, so that a pass
+    // starts with its source-row loads instead of a rowptr -> col -> row chain of three dependent round trips
+    int beg = 0, end = 0, src0 = 0, nbeg = 0, nend = 0;
     {
-      const int j0 = node_of(blockIdx.x * kTcTile, 0);
-      if ((int)blockIdx.x < ntiles && j0 < A.N) { nbeg = __ldg(A.rowptr + j0); nend = __ldg(A.rowptr + j0 + 1); }
+      const int j0 = node_at(0), j1 = node_at(1);
+      if (j0 >= 0) { beg = __ldg(A.rowptr + j0); end = __ldg(A.rowptr + j0 + 1); }
+      if (j1 >= 0) { nbeg = __ldg(A.rowptr + j1); nend = __ldg(A.rowptr + j1 + 1); }
+      if (gl < EPI && beg + gl < end) src0 = __ldg(A.col + beg + gl);
     }
+    int pc = 0;
     for (int it = 0, tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int tile_base = tile * kTcTile;
 #pragma unroll 1
-      for (int pass = 0; pass < PASSES; ++pass) {
+      for (int pass = 0; pass < PASSES; ++pass, ++pc) {
         const int q = pass * NODES_PER_PASS + warp * NPW + grp;
         const int j = tile_base + q;
         const bool node_ok = j < A.N;
-        const int beg = nbeg, end = nend;
-        {                                                     // prefetch the next pass's row pointers
-          const bool last = pass == PASSES - 1;
-          const int tb = last ? (tile + (int)gridDim.x) * kTcTile : tile_base;
-          const int jn = node_of(tb, last ? 0 : pass + 1);
-          nbeg = nend = 0;
-          if ((!last || tile + (int)gridDim.x < ntiles) && jn < A.N) { nbeg = __ldg(A.rowptr + jn); nend = __ldg(A.rowptr + jn + 1); }
+        // prefetch: first column chunk of pass pc+1, row pointers of pass pc+2
+        int nsrc = 0, n2beg = 0, n2end = 0;
+        if (gl < EPI && nbeg + gl < nend) nsrc = __ldg(A.col + nbeg + gl);
+        {
+          const int j2 = node_at(pc + 2);
+          if (j2 >= 0) { n2beg = __ldg(A.rowptr + j2); n2end = __ldg(A.rowptr + j2 + 1); }
         }
         const int g = (A.nodes_per_graph > 0 && node_ok) ? j / A.nodes_per_graph : 0;
         float stgt[NH], Mh[NH], den[NH];
@@ -410,7 +451,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
           const int k0 = beg + itr * EPI;
           const int ke = k0 + gl;
           const bool ev = gl < EPI && ke < end;
-          const int srcn = ev ? __ldg(A.col + ke) : 0;
+          const int srcn = itr == 0 ? src0 : (ev ? __ldg(A.col + ke) : 0);
           // source rows first (their address only needs col), then the scores
           uint4 xv[EPI];
 #pragma unroll
@@ -465,40 +506,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
           *reinterpret_cast<float4*>(rowp + (((c0 + 1) ^ sw) << 4)) =
               make_float4(z[h][4] * iv, z[h][5] * iv, z[h][6] * iv, z[h][7] * iv);
         }
+        beg = nbeg; end = nend; src0 = nsrc; nbeg = n2beg; nend = n2end;
       }
       tc_fence_async_smem();                                  // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(bar_a_full);
     }
-  } else if (warp == kTcMmaWarp) {
-    // =========================== MMA issuer (one thread) ===========================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=F, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
-      for (int it = 0, tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int stg = it & 1, n = it >> 1;
-        tc_mbar_wait(bar_a_full, (uint32_t)(it & 1));
-        if (n > 0) tc_mbar_wait(bar_t_empty0 + 8 * stg, (uint32_t)((n - 1) & 1));
-        tc_fence_after();
-#pragma unroll 1
-        for (int h = 0; h < NH; ++h) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(stg * NH * F + h * F);
-#pragma unroll 1
-          for (int kb = 0; kb < KB; ++kb) {
-            const uint64_t ad = tc_desc_sw128(tc_smem_u32(As + (size_t)(h * KB + kb) * L.a_block));
-            const uint64_t bd = tc_desc_sw128(tc_smem_u32(Bs + (size_t)(h * KB + kb) * L.b_block));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)                       // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
-              tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          }
-        }
-        tc_commit(bar_a_empty);                               // A may be overwritten once these MMAs retire
-        tc_commit(bar_t_full0 + 8 * stg);                     // accumulators of this tile are complete
-      }
-    }
-    __syncwarp();
   } else {
-    // =========================== epilogue warps: TMEM -> ELU -> mean/concat -> global ===========================
+    // ============ epilogue warps (TMEM -> ELU -> mean/concat -> global); the first one also issues the MMAs ============
     const int ew = warp & 3;                                  // TMEM lane quarter this warp may access
     const int row = ew * 32 + lane;
     const int et = (warp - kTcEpiWarp0) * 32 + lane;          // 0..127 linear id among epilogue threads
@@ -506,75 +521,96 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
     const int out_w = A.concat ? NH * F : F;
     const int cpr = F / 8;                                    // 16-byte chunks per staged bf16 row
     const int swz_mask = ((cpr & (cpr - 1)) == 0) ? (min(cpr, 8) - 1) : 0;
-    for (int it = 0, tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    // instruction descriptor: D=f32, A=B=tf32, both K-major, N=F, M=128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+
+    auto issue_mma = [&](int it) {                            // one thread: tile `it` of this CTA
+      const int stg = it & 1, n = it >> 1;
+      tc_mbar_wait_relaxed(bar_a_full, (uint32_t)(it & 1));
+      if (n > 0) tc_mbar_wait(bar_t_empty0 + 8 * stg, (uint32_t)((n - 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < NH; ++h) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(stg * NH * F + h * F);
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t ad = tc_desc_sw128(tc_smem_u32(As + (size_t)(h * KB + kb) * L.a_block));
+          const uint64_t bd = tc_desc_sw128(tc_smem_u32(Bs + (size_t)(h * KB + kb) * L.b_block));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                         // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
+            tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        }
+      }
+      tc_commit(bar_a_empty);                                 // A may be overwritten once these MMAs retire
+      tc_commit(bar_t_full0 + 8 * stg);                       // accumulators of this tile are complete
+    };
+
+    auto epilogue_tile = [&](int it, int tile) {
       const int stg = it & 1, n = it >> 1;
       const int tile_base = tile * kTcTile;
       const int node = tile_base + row;
-      tc_mbar_wait(bar_t_full0 + 8 * stg, (uint32_t)(n & 1));
+      tc_mbar_wait_relaxed(bar_t_full0 + 8 * stg, (uint32_t)(n & 1));
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(stg * NH * F);
-      for (int c0 = 0; c0 < F; c0 += 32) {
-        const int ncol = min(32, F - c0);                     // 32 or 16 (F % 16 == 0)
-        float oacc[32];
+      // 16 accumulator columns at a time (F % 16 == 0): fully unrolled, no per-element guards, two heads' loads in flight
+      for (int c0 = 0; c0 < F; c0 += 16) {
+        float oacc[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) oacc[i] = 0.f;
-#pragma unroll 1
-        for (int h = 0; h < NH; ++h) {
-          uint32_t v[32];
-          if (ncol == 32) tc_tmem_ld32(t_row + (uint32_t)(h * F + c0), v);
-          else tc_tmem_ld16(t_row + (uint32_t)(h * F + c0), v);
+        for (int i = 0; i < 16; ++i) oacc[i] = 0.f;
+#pragma unroll
+        for (int h0 = 0; h0 < NH; h0 += 2) {
+          uint32_t v[2][16];
+          tc_tmem_ld16(t_row + (uint32_t)(h0 * F + c0), v[0]);
+          if (h0 + 1 < NH) tc_tmem_ld16(t_row + (uint32_t)((h0 + 1) * F + c0), v[1]);
           tc_tmem_wait_ld();
-          if (A.concat) {
-            if (node < A.N) {
-              const size_t o = (size_t)node * out_w + (size_t)h * F + c0;
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (i >= ncol) break;
-                float e8[8];
+          for (int hh = 0; hh < 2; ++hh) {
+            if (h0 + hh >= NH) break;
+            float e16[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) e8[u] = tc_elu(__uint_as_float(v[i + u]));
+            for (int i = 0; i < 16; ++i) e16[i] = tc_elu(__uint_as_float(v[hh][i]));          // ELU per head (:118)
+            if (A.concat) {
+              if (node < A.N) {
+                const size_t o = (size_t)node * out_w + (size_t)(h0 + hh) * F + c0;
                 if (A.out_bf16) {
-                  uint4 pk;
-                  __nv_bfloat162 b0 = __floats2bfloat162_rn(e8[0], e8[1]), b1 = __floats2bfloat162_rn(e8[2], e8[3]),
-                                 b2 = __floats2bfloat162_rn(e8[4], e8[5]), b3 = __floats2bfloat162_rn(e8[6], e8[7]);
-                  pk.x = *reinterpret_cast<unsigned*>(&b0); pk.y = *reinterpret_cast<unsigned*>(&b1);
-                  pk.z = *reinterpret_cast<unsigned*>(&b2); pk.w = *reinterpret_cast<unsigned*>(&b3);
-                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + o + i) = pk;
+                  uint4 pk[2];
+                  unsigned* pw = reinterpret_cast<unsigned*>(pk);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(e16[2 * i], e16[2 * i + 1]);
+                    pw[i] = *reinterpret_cast<unsigned*>(&b2);
+                  }
+                  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + o);
+                  op[0] = pk[0]; op[1] = pk[1];
                 } else {
-                  float* op = reinterpret_cast<float*>(A.out) + o + i;
-                  *reinterpret_cast<float4*>(op) = make_float4(e8[0], e8[1], e8[2], e8[3]);
-                  *reinterpret_cast<float4*>(op + 4) = make_float4(e8[4], e8[5], e8[6], e8[7]);
+                  float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(A.out) + o);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) op[i] = make_float4(e16[4 * i], e16[4 * i + 1], e16[4 * i + 2], e16[4 * i + 3]);
                 }
               }
-            }
-          } else {
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncol) oacc[i] += tc_elu(__uint_as_float(v[i]));          // ELU per head, then mean (:118,158)
+              for (int i = 0; i < 16; ++i) oacc[i] += e16[i];                                  // then the head mean (:158)
+            }
           }
         }
         if (!A.concat) {
           if (staged) {
+            uint4 pk[2];
+            unsigned* pw = reinterpret_cast<unsigned*>(pk);
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (i >= ncol) break;
-              uint4 pk;
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(oacc[i] * inv_h, oacc[i + 1] * inv_h),
-                             b1 = __floats2bfloat162_rn(oacc[i + 2] * inv_h, oacc[i + 3] * inv_h),
-                             b2 = __floats2bfloat162_rn(oacc[i + 4] * inv_h, oacc[i + 5] * inv_h),
-                             b3 = __floats2bfloat162_rn(oacc[i + 6] * inv_h, oacc[i + 7] * inv_h);
-              pk.x = *reinterpret_cast<unsigned*>(&b0); pk.y = *reinterpret_cast<unsigned*>(&b1);
-              pk.z = *reinterpret_cast<unsigned*>(&b2); pk.w = *reinterpret_cast<unsigned*>(&b3);
-              const int chunk = (c0 + i) >> 3;
-              *reinterpret_cast<uint4*>(Ss + (size_t)row * F * 2 + ((chunk ^ (row & swz_mask)) << 4)) = pk;
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(oacc[2 * i] * inv_h, oacc[2 * i + 1] * inv_h);
+              pw[i] = *reinterpret_cast<unsigned*>(&b2);
             }
+            const int chunk = c0 >> 3;
+            *reinterpret_cast<uint4*>(Ss + (size_t)row * F * 2 + ((chunk ^ (row & swz_mask)) << 4)) = pk[0];
+            *reinterpret_cast<uint4*>(Ss + (size_t)row * F * 2 + (((chunk + 1) ^ (row & swz_mask)) << 4)) = pk[1];
           } else if (node < A.N) {
-            float* op = reinterpret_cast<float*>(A.out) + (size_t)node * out_w + c0;
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(A.out) + (size_t)node * out_w + c0);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              if (i < ncol)
-                *reinterpret_cast<float4*>(op + i) =
-                  make_float4(oacc[i] * inv_h, oacc[i + 1] * inv_h, oacc[i + 2] * inv_h, oacc[i + 3] * inv_h);
+            for (int i = 0; i < 4; ++i)
+              op[i] = make_float4(oacc[4 * i] * inv_h, oacc[4 * i + 1] * inv_h, oacc[4 * i + 2] * inv_h, oacc[4 * i + 3] * inv_h);
           }
         }
       }
@@ -594,7 +630,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+    };
+
+    // tile t's MMAs are issued as soon as its A operand is complete; its epilogue runs one iteration later, i.e.
+    // concurrently with the gather of tile t+1 (the accumulators are double-buffered in TMEM)
+    int it = 0, tile = blockIdx.x;
+    for (; tile < ntiles; tile += gridDim.x, ++it) {
+      if (warp == kTcMmaWarp) {
+        if (lane == 0) issue_mma(it);
+        __syncwarp();
+      }
+      if (it > 0) epilogue_tile(it - 1, tile - (int)gridDim.x);
     }
+    if (it > 0) epilogue_tile(it - 1, tile - (int)gridDim.x);
     tc_fence_before();
   }
   __syncthreads();
@@ -617,7 +665,7 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
   }
   const int G = A.nodes_per_graph > 0 ? A.N / A.nodes_per_graph : 1;
   int rc;
-  const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)A.N * LPN, 256), (int64_t)num_sms() * 8);
+  const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)A.N * 2, 256), (int64_t)num_sms() * 8);   // 16 nodes per warp step
   tc_scores_kernel<NH, LPN><<<sgrid, 256, 0, st>>>(A.x, A.N, A.W, a, A.F, G, s, gmax);
   if ((rc = check_launch("tc_scores_kernel"))) return rc;
   const int mblocks = std::min(ceil_div(A.N, 32), num_sms() * 8);
