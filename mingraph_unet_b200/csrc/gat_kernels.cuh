@@ -15,7 +15,7 @@ static constexpr int64_t kSmemBudget = 200 * 1024;
 // tensor-pipe variant (gat_tc.cu): bf16 node features, transform on tcgen05 (tf32), inference only
 bool gat_tc_supported(int N, int in_dim, int F, int heads, int concat, int out_bf16);
 // (runs its own score / edge-max pre-pass into s (N, 2*heads) and gmax (G, heads))
-int gat_tc_launch(const void* x, const int32_t* rowptr, const int32_t* col, float* s, float* gmax, const float* W,
+int gat_tc_launch(const void* x, const int32_t* rowptr, const int32_t* col, float* s, float* gmax, float* u, const float* W,
                   const float* a, int N, int in_dim, int F, int heads, int concat, float slope, int nodes_per_graph, void* out,
                   int out_bf16, cudaStream_t st);
 

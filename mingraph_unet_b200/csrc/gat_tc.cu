@@ -175,45 +175,46 @@ __host__ __device__ inline TcSmem tc_smem_layout(int heads, int in_dim, int F, b
 }
 
 // ---- pre-pass 1: attention scalars s[n] = (x_n . u_src[h], x_n . u_tgt[h]) -------------------------------------
-// u_src[h] = W_h^T a_h[:F], u_tgt[h] = W_h^T a_h[F:] are recomputed per block (<= 512 x F MACs) into shared memory;
-// a group of LPN lanes owns a node (16 bytes of the bf16 row per lane).  Also resets the per-graph maxima.
+// u_src[h] = W_h^T a_h[:F], u_tgt[h] = W_h^T a_h[F:] come from a one-block kernel (which also resets the per-graph maxima).
 template <int NH, int LPN>
-__global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __restrict__ x, int N,
-                                                        const float* __restrict__ W, const float* __restrict__ a, int F,
-                                                        int num_graphs, float* __restrict__ s, float* __restrict__ gmax) {
-  constexpr int IN = LPN * 8, NQ = 2 * NH;
-  constexpr int FP = 256 / IN;                                 // f-partitions: thread = (f-partition, input column)
-  __shared__ float u_s[NQ * IN];
-  __shared__ float u_part[FP][NQ * IN];
+__global__ void __launch_bounds__(256) tc_u_kernel(const float* __restrict__ W, const float* __restrict__ a, int F,
+                                                   int num_graphs, float* __restrict__ u, float* __restrict__ gmax) {
+  // one block per head: thread = (f-partition, input column); all of a thread's loads are independent
+  constexpr int IN = LPN * 8;
+  constexpr int FP = 256 / IN;
+  __shared__ float u_part[FP][2 * IN];
+  const int h = blockIdx.x;
   {
     const int i = threadIdx.x % IN, fp = threadIdx.x / IN;
-    float acc[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
-#pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      const float* Wh = W + (size_t)h * F * IN + i;
-      const float* ah = a + (size_t)h * 2 * F;
-#pragma unroll 8
-      for (int f = fp; f < F; f += FP) {                        // independent, coalesced loads: pipelined
-        const float w = __ldg(Wh + (size_t)f * IN);
-        acc[h] = fmaf(__ldg(ah + f), w, acc[h]);
-        acc[NH + h] = fmaf(__ldg(ah + F + f), w, acc[NH + h]);
-      }
+    const float* Wh = W + (size_t)h * F * IN + i;
+    const float* ah = a + (size_t)h * 2 * F;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 16
+    for (int f = fp; f < F; f += FP) {
+      const float w = __ldg(Wh + (size_t)f * IN);
+      acc0 = fmaf(__ldg(ah + f), w, acc0);
+      acc1 = fmaf(__ldg(ah + F + f), w, acc1);
     }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) u_part[fp][q * IN + i] = acc[q];
+    u_part[fp][i] = acc0;
+    u_part[fp][IN + i] = acc1;
   }
+  if (h == 0)
+    for (int i = threadIdx.x; i < num_graphs * NH; i += blockDim.x) gmax[i] = -INFINITY;
   __syncthreads();
-  for (int idx = threadIdx.x; idx < NQ * IN; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < 2 * IN; idx += blockDim.x) {
     float v = 0.f;
 #pragma unroll
     for (int fp = 0; fp < FP; ++fp) v += u_part[fp][idx];
-    u_s[idx] = v;
+    const int half = idx / IN, i = idx - half * IN;
+    u[(size_t)(half * NH + h) * IN + i] = v;                    // rows: u_src[0..NH) then u_tgt[0..NH)
   }
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < num_graphs * NH; i += blockDim.x) gmax[i] = -INFINITY;
-  __syncthreads();
+}
+
+template <int NH, int LPN>
+__global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __restrict__ x, int N,
+                                                        const float* __restrict__ u, float* __restrict__ s) {
+  constexpr int IN = LPN * 8, NQ = 2 * NH;
+  const float* u_s = u;                                        // (2*NH, IN) fp32, 2 KB at most: L1/L2 resident
   // s = X U^T on mma.sync m16n8k16 (bf16 x bf16 -> f32): a warp takes 16 nodes per step.  x is bf16 already; u is split
   // into bf16 hi + lo parts (two MMAs), so the products carry ~16 mantissa bits of u and the sums are fp32.  The k index
   // of the MMA is a permutation of the feature index chosen so that every lane feeds whole 16-byte row chunks.
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
     for (int r = 0; r < 2; ++r) {
       const int jj = 2 * m + r;                                // pair register jj of this lane: chunk (jj/4)*4 + t, pair jj%4
       const int k = ((jj >> 2) * 4 + t) * 8 + 2 * (jj & 3);
-      const float u0 = g < NQ ? u_s[g * IN + k] : 0.f, u1 = g < NQ ? u_s[g * IN + k + 1] : 0.f;
+      const float u0 = g < NQ ? __ldg(u_s + g * IN + k) : 0.f, u1 = g < NQ ? __ldg(u_s + g * IN + k + 1) : 0.f;
       const __nv_bfloat16 h0 = __float2bfloat16_rn(u0), h1 = __float2bfloat16_rn(u1);
       const __nv_bfloat16 l0 = __float2bfloat16_rn(u0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(u1 - __bfloat162float(h1));
       bhi[m][r] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
 // 8 lanes per destination; each block owns a contiguous node range and issues one atomic max per head when the
 // range lies in one graph (order-independent, hence deterministic).
 template <int NH>
-__global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+__global__ void __launch_bounds__(256, 8) tc_edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                           const float* __restrict__ s, int N, int nodes_per_graph,
                                                           int nodes_per_block, float* __restrict__ gmax) {
   constexpr int NQ = 2 * NH;
@@ -349,9 +350,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
   unsigned char* sm = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   const bool staged = A.out_bf16 && !A.concat;
   const TcSmem L = tc_smem_layout(NH, IN, A.F, staged);
-  const uint32_t bar_a_full = tc_smem_u32(sm + 0), bar_a_empty = tc_smem_u32(sm + 8);
+  const uint32_t bar_a_empty = tc_smem_u32(sm + 8);
   const uint32_t bar_t_full0 = tc_smem_u32(sm + 16), bar_t_empty0 = tc_smem_u32(sm + 32);   // [2] each, 8 B apart
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + 64);
+  int* arrive_cnt = reinterpret_cast<int*>(sm + 72);        // gather warps that finished their share of a tile
   unsigned char* As = sm + L.a_off;
   unsigned char* Bs = sm + L.b_off;
   unsigned char* Ss = sm + L.stage_off;
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
   const int ntiles = ceil_div(A.N, kTcTile);
 
   if (tid == 0) {
-    tc_mbar_init(bar_a_full, kTcGatherWarps);
+    *arrive_cnt = 0;
     tc_mbar_init(bar_a_empty, 1);
     tc_mbar_init(bar_t_full0, 1);
     tc_mbar_init(bar_t_full0 + 8, 1);
@@ -389,6 +391,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+
+  // instruction descriptor: D=f32, A=B=tf32, both K-major, N=F, M=128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+
+  auto issue_mma = [&](int it) {                            // one thread: tile `it` of this CTA, A operand complete
+    const int stg = it & 1, n = it >> 1;
+    if (n > 0) tc_mbar_wait(bar_t_empty0 + 8 * stg, (uint32_t)((n - 1) & 1));
+    tc_fence_after();
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h) {
+      const uint32_t d_tmem = tmem_base + (uint32_t)(stg * NH * F + h * F);
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint64_t ad = tc_desc_sw128(tc_smem_u32(As + (size_t)(h * KB + kb) * L.a_block));
+        const uint64_t bd = tc_desc_sw128(tc_smem_u32(Bs + (size_t)(h * KB + kb) * L.b_block));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)                         // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
+          tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+      }
+    }
+    tc_commit(bar_a_empty);                                 // A may be overwritten once these MMAs retire
+    tc_commit(bar_t_full0 + 8 * stg);                       // accumulators of this tile are complete
+  };
+
 
   if (warp < kTcGatherWarps) {
     // =========================== gather warps: z tile -> A operand ===========================
@@ -510,7 +536,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
       }
       tc_fence_async_smem();                                  // generic-proxy writes -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) tc_mbar_arrive(bar_a_full);
+      // the LAST gather warp to finish the tile issues its MMAs (no hand-off to another warp on the critical path)
+      int last = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        last = atomicAdd(arrive_cnt, 1) == kTcGatherWarps * (it + 1) - 1;
+        __threadfence_block();
+        if (last) issue_mma(it);
+      }
+      __syncwarp();
     }
   } else {
     // ============ epilogue warps (TMEM -> ELU -> mean/concat -> global); the first one also issues the MMAs ============
@@ -521,30 +555,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
     const int out_w = A.concat ? NH * F : F;
     const int cpr = F / 8;                                    // 16-byte chunks per staged bf16 row
     const int swz_mask = ((cpr & (cpr - 1)) == 0) ? (min(cpr, 8) - 1) : 0;
-    // instruction descriptor: D=f32, A=B=tf32, both K-major, N=F, M=128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
-
-    auto issue_mma = [&](int it) {                            // one thread: tile `it` of this CTA
-      const int stg = it & 1, n = it >> 1;
-      tc_mbar_wait_relaxed(bar_a_full, (uint32_t)(it & 1));
-      if (n > 0) tc_mbar_wait(bar_t_empty0 + 8 * stg, (uint32_t)((n - 1) & 1));
-      tc_fence_after();
-#pragma unroll 1
-      for (int h = 0; h < NH; ++h) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(stg * NH * F + h * F);
-#pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint64_t ad = tc_desc_sw128(tc_smem_u32(As + (size_t)(h * KB + kb) * L.a_block));
-          const uint64_t bd = tc_desc_sw128(tc_smem_u32(Bs + (size_t)(h * KB + kb) * L.b_block));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)                         // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
-            tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-        }
-      }
-      tc_commit(bar_a_empty);                                 // A may be overwritten once these MMAs retire
-      tc_commit(bar_t_full0 + 8 * stg);                       // accumulators of this tile are complete
-    };
-
     auto epilogue_tile = [&](int it, int tile) {
       const int stg = it & 1, n = it >> 1;
       const int tile_base = tile * kTcTile;
@@ -632,17 +642,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
       }
     };
 
-    // tile t's MMAs are issued as soon as its A operand is complete; its epilogue runs one iteration later, i.e.
-    // concurrently with the gather of tile t+1 (the accumulators are double-buffered in TMEM)
-    int it = 0, tile = blockIdx.x;
-    for (; tile < ntiles; tile += gridDim.x, ++it) {
-      if (warp == kTcMmaWarp) {
-        if (lane == 0) issue_mma(it);
-        __syncwarp();
-      }
-      if (it > 0) epilogue_tile(it - 1, tile - (int)gridDim.x);
-    }
-    if (it > 0) epilogue_tile(it - 1, tile - (int)gridDim.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) epilogue_tile(it, tile);
     tc_fence_before();
   }
   __syncthreads();
@@ -653,7 +654,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
 }
 
 template <int NH, int LPN>
-static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, size_t smem, int grid, cudaStream_t st) {
+static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, float* u, size_t smem, int grid,
+                     cudaStream_t st) {
   auto k = gat_tc_kernel<NH, LPN>;
   static bool configured = false;
   if (!configured) {
@@ -666,7 +668,9 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
   const int G = A.nodes_per_graph > 0 ? A.N / A.nodes_per_graph : 1;
   int rc;
   const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)A.N * 2, 256), (int64_t)num_sms() * 8);   // 16 nodes per warp step
-  tc_scores_kernel<NH, LPN><<<sgrid, 256, 0, st>>>(A.x, A.N, A.W, a, A.F, G, s, gmax);
+  tc_u_kernel<NH, LPN><<<NH, 256, 0, st>>>(A.W, a, A.F, G, u, gmax);
+  if ((rc = check_launch("tc_u_kernel"))) return rc;
+  tc_scores_kernel<NH, LPN><<<sgrid, 256, 0, st>>>(A.x, A.N, u, s);
   if ((rc = check_launch("tc_scores_kernel"))) return rc;
   const int mblocks = std::min(ceil_div(A.N, 32), num_sms() * 8);
   const int npb = ceil_div(ceil_div(A.N, mblocks), 32) * 32;
@@ -688,7 +692,7 @@ bool gat_tc_supported(int N, int in_dim, int F, int heads, int concat, int out_b
   return L.total <= 227 * 1024;
 }
 
-int gat_tc_launch(const void* x, const int32_t* rowptr, const int32_t* col, float* s, float* gmax, const float* W,
+int gat_tc_launch(const void* x, const int32_t* rowptr, const int32_t* col, float* s, float* gmax, float* u, const float* W,
                   const float* a, int N, int in_dim, int F, int heads, int concat, float slope, int nodes_per_graph, void* out,
                   int out_bf16, cudaStream_t st) {
   GatTcArgs A;
@@ -702,7 +706,7 @@ int gat_tc_launch(const void* x, const int32_t* rowptr, const int32_t* col, floa
   const int grid = std::min(ceil_div(N, kTcTile), num_sms());
   const int lpn = in_dim / 8;
 #define MG_TC(NHH, LL) \
-  if (heads == NHH && lpn == LL) return launch_tc<NHH, LL>(A, a, s, gmax, (size_t)L.total, grid, st);
+  if (heads == NHH && lpn == LL) return launch_tc<NHH, LL>(A, a, s, gmax, u, (size_t)L.total, grid, st);
   MG_TC(4, 8) MG_TC(4, 4) MG_TC(2, 16) MG_TC(2, 8) MG_TC(2, 4) MG_TC(1, 32) MG_TC(1, 16) MG_TC(1, 8) MG_TC(1, 4)
 #undef MG_TC
   set_error("gat_tc: no variant for heads=%d in=%d", heads, in_dim);
