@@ -77,6 +77,14 @@ MG_API int64_t mg_csr_work_bytes(int N, int64_t E);
 MG_API int mg_csr_from_coo(const int64_t* edge_index, int64_t E, int N, int by_target, int32_t* rowptr, int32_t* col,
                     int32_t* eid, void* work, int32_t* status, mg_stream_t stream);
 
+/* ---- kNN graph (north_star kernel (2); NOT in the reference, see csrc/knn.cu) -------------------------------
+ * For every node j the k nearest OTHER nodes of its graph under squared Euclidean distance accumulated in fp32 in
+ * feature order (rounded sub, mul, add; no FMA), ties to the lower id, sorted by (distance, id).  Outputs (each
+ * nullable): edge_index (2, N*k) int64 (row 0 = neighbour = source, row 1 = j = target), in-CSR rowptr (N+1) /
+ * col (N*k) int32, dist (N*k) f32.  nodes_per_graph > 0: block-diagonal batch of equal-size graphs.  k <= 32. */
+MG_API int mg_knn_graph(const float* x, int N, int D, int k, int nodes_per_graph, int64_t* edge_index, int32_t* rowptr,
+                 int32_t* col, float* dist, mg_stream_t stream);
+
 /* ---- pooling ---------------------------------------------------------------------------
  * Patch mean pooling (B,C,Hf,Wf) -> (B, Hp*Wp, C): the documented intent of
  * PatchGraphConstructor.get_patch_features_from_unet_encoder (patch_graph_construction.py:

@@ -41,6 +41,7 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_complete_csr": (_i, [_i, _i, _p, _p, _p]),
     "mg_csr_work_bytes": (_i64, [_i, _i64]),
     "mg_csr_from_coo": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "mg_knn_graph": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "mg_pool_patches": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "mg_segment_mean": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "mg_gat_work_bytes": (_i64, [_i, _i, _i, _i, _i]),

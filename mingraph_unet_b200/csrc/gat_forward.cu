@@ -295,7 +295,9 @@ int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int num_gra
   if (N <= 0 || in_dim <= 0 || out_dim <= 0 || heads <= 0) return 0;
   DimCfg d;
   bool need_z = true;
-  if (pick_dims(in_dim, &d)) need_z = !plan_fused(in_dim, out_dim, heads, d).ok;
+  if (pick_dims(in_dim, &d))
+    need_z = !plan_fused(in_dim, out_dim, heads, d).ok || gat_transform_tc_supported(N, in_dim, out_dim, heads, 1) ||
+             gat_transform_tc_supported(N, in_dim, out_dim, heads, 3);
   return (int64_t)work_layout(N, in_dim, out_dim, heads, num_graphs > 0 ? num_graphs : 1, need_z).total;
 }
 
@@ -324,8 +326,13 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
              "feature dimension with zero columns otherwise)", in_dim);
   const int G = nodes_per_graph > 0 ? N / nodes_per_graph : 1;
   const int NH = heads <= 1 ? 1 : (heads <= 2 ? 2 : (heads <= 4 ? 4 : 8));
-  const FusedPlan plan = plan_fused(in_dim, out_dim, heads, d);
-  const WorkLayout wl = work_layout(N, in_dim, out_dim, heads, G, !plan.ok);
+  FusedPlan plan = plan_fused(in_dim, out_dim, heads, d);
+  // large transforms go to the tensor pipe: aggregate to z, then a tcgen05 GEMM (tf32 for bf16 storage, 3xTF32 for fp32)
+  const int tc_passes = x_dtype == MG_BF16 ? 1 : 3;
+  const bool tc_gemm = gat_transform_tc_supported(N, in_dim, out_dim, heads, tc_passes);
+  const bool any_tc_gemm = gat_transform_tc_supported(N, in_dim, out_dim, heads, 1) || gat_transform_tc_supported(N, in_dim, out_dim, heads, 3);
+  const WorkLayout wl = work_layout(N, in_dim, out_dim, heads, G, !plan.ok || any_tc_gemm);
+  if (tc_gemm) plan.ok = false;
   unsigned char* wb = reinterpret_cast<unsigned char*>(work);
   float* s = reinterpret_cast<float*>(wb + wl.s_off);
   float* gmax = reinterpret_cast<float*>(wb + wl.gmax_off);
@@ -364,6 +371,8 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   if (x_dtype == MG_F32) rc = gat_launch_agg_f32(ag, NH, d, z, save_den, grid, st);
   else rc = gat_launch_agg_bf16(ag, NH, d, z, save_den, grid, st);
   if (rc) return rc;
+  if (tc_gemm)
+    return gat_transform_tc_launch(z, W, N, in_dim, out_dim, heads, concat ? 1 : 0, out, out_dtype == MG_BF16 ? 1 : 0, tc_passes, st);
   dim3 g2(ceil_div(N, kTM), ceil_div(out_dim, kTN));
   gat_transform_kernel<<<g2, 256, 0, st>>>(z, W, N, in_dim, out_dim, heads, concat ? 1 : 0, out,
                                            out_dtype == MG_BF16 ? 1 : 0);

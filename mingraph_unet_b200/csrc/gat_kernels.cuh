@@ -12,6 +12,11 @@ int gat_scores_and_max(const void* x, int x_dtype, const int32_t* rowptr, const 
                        float* u, cudaStream_t st);
 static constexpr int64_t kSmemBudget = 200 * 1024;
 
+// tensor-pipe node transform for spilled z (gat_tc_gemm.cu): passes = 1 (tf32, bf16-storage path) or 3 (3xTF32, fp32 path)
+bool gat_transform_tc_supported(int N, int in_dim, int F, int heads, int passes);
+int gat_transform_tc_launch(const float* z, const float* W, int N, int in_dim, int F, int heads, int concat, void* out,
+                            int out_bf16, int passes, cudaStream_t st);
+
 // tensor-pipe variant (gat_tc.cu): bf16 node features, transform on tcgen05 (tf32), inference only
 bool gat_tc_supported(int N, int in_dim, int F, int heads, int concat, int out_bf16);
 // (runs its own score / edge-max pre-pass into s (N, 2*heads) and gmax (G, heads))

@@ -119,6 +119,25 @@ def csr_from_coo(edge_index: torch.Tensor, N: int, by_target: bool = True, check
     return rowptr, col[:E], eid[:E]
 
 
+def knn_graph(x: torch.Tensor, k: int, nodes_per_graph: int = 0, with_dist: bool = False):
+    """k nearest neighbours of every node within its graph (squared Euclidean, fp32, ties to the lower id, self
+    excluded).  Returns ``edge_index (2, N*k) int64`` (row 0 = neighbour/source, row 1 = node/target), ``rowptr``,
+    ``col`` (in-CSR, int32) and optionally the distances ``(N, k)``.  Not part of the reference (csrc/knn.cu)."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.dtype != torch.float32:
+        raise RuntimeError("knn_graph expects float32 node features (N, D)")
+    x = x.contiguous()
+    N, D = x.shape
+    ei = torch.empty((2, N * k), dtype=torch.int64, device=x.device)
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=x.device)
+    col = torch.empty(N * k, dtype=torch.int32, device=x.device)
+    dist = torch.empty((N, k), dtype=torch.float32, device=x.device) if with_dist else None
+    with torch.cuda.device(x.device):
+        call("mg_knn_graph", x.data_ptr(), N, D, int(k), int(nodes_per_graph), ei.data_ptr(), rowptr.data_ptr(), col.data_ptr(),
+             _ptr(dist), _stream())
+    return (ei, rowptr, col, dist) if with_dist else (ei, rowptr, col)
+
+
 # ---------------------------------------------------------------------------------------------
 # pooling / un-pooling
 # ---------------------------------------------------------------------------------------------

@@ -229,6 +229,45 @@ def graph_block_image(x, H: int, W: int, params: Dict[str, torch.Tensor], K: int
 
 
 # ----------------------------------------------------------------------------
+# kNN graph (NOT in the reference — parity unpinned by it; this restatement IS the definition)
+# ----------------------------------------------------------------------------
+def knn_sqdist(x: np.ndarray) -> np.ndarray:
+    """All-pairs squared Euclidean distances, fp32, accumulated in FEATURE ORDER with separately rounded
+    subtract / multiply / add (numpy float32 ops never fuse), so a CUDA kernel that uses
+    ``__fsub_rn/__fmul_rn/__fadd_rn`` in the same order reproduces every bit.  The nearest reference
+    arithmetic is the per-edge ``sum((f_src - f_tgt)**2)`` of mincut_refinement.py:43-46."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = x.shape[0]
+    acc = np.zeros((n, n), dtype=np.float32)
+    for d in range(x.shape[1]):
+        t = x[:, None, d] - x[None, :, d]
+        acc = acc + t * t
+    return acc
+
+
+def knn_graph(x: np.ndarray, k: int, nodes_per_graph: int = 0):
+    """k nearest OTHER nodes of every node within its graph; ties to the lower node id; neighbours sorted by
+    (distance, id).  Returns ``edge_index (2, N*k) int64`` (row 0 = neighbour = source, row 1 = node = target)
+    and the distances ``(N, k) float32``."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    N = x.shape[0]
+    npg = nodes_per_graph if nodes_per_graph > 0 else N
+    if N % npg or npg <= k:
+        raise ValueError("bad graph size for kNN")
+    src = np.empty((N, k), dtype=np.int64)
+    dist = np.empty((N, k), dtype=np.float32)
+    for g0 in range(0, N, npg):
+        d = knn_sqdist(x[g0:g0 + npg])
+        np.fill_diagonal(d, np.inf)                                   # self excluded
+        ids = np.arange(npg)
+        order = np.lexsort((np.broadcast_to(ids, d.shape), d), axis=1)[:, :k]     # primary key d, then id
+        src[g0:g0 + npg] = order + g0
+        dist[g0:g0 + npg] = np.take_along_axis(d, order, 1)
+    tgt = np.repeat(np.arange(N, dtype=np.int64), k)
+    return np.stack([src.reshape(-1), tgt]), dist
+
+
+# ----------------------------------------------------------------------------
 # weight helpers (reference init, graph_attention.py:36-37)
 # ----------------------------------------------------------------------------
 def init_gat_params(in_dim: int, out_dim: int, heads: int, gen: Optional[torch.Generator] = None):

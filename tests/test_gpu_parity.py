@@ -448,3 +448,47 @@ def test_block_errors(mg):
         blk(node_features=torch.randn(1, 1, 20, device="cuda"), image_size=(16, 16))      # 1x1 grid: no edges
     with pytest.raises(ValueError):
         blk()
+
+
+# ---------------------------------------------------------------------------------------------
+# kNN graph build (north_star kernel (2); oracle-pinned: the reference has no kNN code)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,D,k,npg", [(256, 64, 8, 0), (1000, 20, 16, 0), (4096, 64, 8, 1024), (2048, 128, 32, 512),
+                                       (96, 7, 5, 32), (1500, 200, 8, 0), (40, 3, 32, 0)])
+def test_knn_graph_bit_exact_vs_oracle(mg, N, D, k, npg):
+    gen = torch.Generator().manual_seed(N + D + k)
+    x = torch.randn(N, D, generator=gen)
+    x[5] = x[2]                                        # exact ties
+    if N > 64:
+        x[40:48] = x[33]
+    x = (x * 8).round() / 8 if D <= 7 else x           # low-dimensional lattice: many equal distances
+    ei_ref, dist_ref = O.knn_graph(x.numpy(), k, npg)
+    ei, rowptr, col, dist = mg.ops.knn_graph(x.cuda(), k, nodes_per_graph=npg, with_dist=True)
+    assert ei.dtype == torch.int64 and tuple(ei.shape) == (2, N * k)
+    assert np.array_equal(ei.cpu().numpy(), ei_ref)                                  # neighbour sets AND order: bit-exact
+    assert np.array_equal(dist.cpu().numpy(), dist_ref)                              # distances: bit-exact fp32
+    assert np.array_equal(col.cpu().numpy(), ei_ref[0].astype(np.int32))
+    assert np.array_equal(rowptr.cpu().numpy(), np.arange(N + 1, dtype=np.int32) * k)
+
+
+def test_knn_graph_feeds_gat_layer(mg):
+    """The kNN CSR is directly the in-CSR of the GAT kernels: layer output equals the oracle on the kNN edge_index."""
+    N, D, k, F, H = 512, 64, 8, 64, 4
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(N, D, generator=gen)
+    ei, rowptr, col = mg.ops.knn_graph(x.cuda(), k)
+    Ws, As = O.init_gat_params(D, F, H, gen)
+    y = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), concat=False)
+    ref = O.gat_layer(x, ei.cpu(), Ws, As, 0.2, concat=False)
+    assert maxabs(y, ref) <= 1e-5
+
+
+def test_knn_errors(mg):
+    from mingraph_unet_b200._lib import MinGraphError
+    x = torch.randn(16, 4).cuda()
+    with pytest.raises(MinGraphError):
+        mg.ops.knn_graph(x, 33)
+    with pytest.raises(MinGraphError):
+        mg.ops.knn_graph(x, 16)                        # needs k other nodes
+    with pytest.raises(MinGraphError):
+        mg.ops.knn_graph(x, 2, nodes_per_graph=5)      # N not a multiple

@@ -91,3 +91,32 @@ def test_tc_matches_fp32_pipe_path(mg):
     y_tc = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), out_dtype=torch.float32)
     y_f32 = mg.ops.gat_forward(x.float().cuda(), rowptr, col, Ws.cuda(), As.cuda(), out_dtype=torch.float32)
     assert float((y_tc - y_f32).abs().max()) <= 5e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-pipe node transform for spilled z (csrc/gat_tc_gemm.cu): 3xTF32 holds the fp32 tolerance
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,heads,fin,fout,concat,dtype", [
+    (8192, 4, 128, 128, False, torch.float32),
+    (4096, 4, 256, 256, False, torch.float32),
+    (9000, 2, 128, 256, True, torch.float32),          # ragged last tile, concat
+    (4096, 1, 512, 512, False, torch.float32),
+    (8192, 4, 64, 64, False, torch.float32),           # shape the FP32-pipe fused kernel also takes: TC path preferred when large
+    (8192, 4, 128, 128, False, torch.bfloat16),
+    (4096, 4, 512, 512, False, torch.bfloat16),
+    (8200, 8, 64, 48, True, torch.bfloat16),
+])
+def test_tc_gemm_transform_vs_oracle(mg, N, heads, fin, fout, concat, dtype):
+    gen = torch.Generator().manual_seed(N + heads + fin + fout)
+    ei = _random_graph(N, 1, 10, gen)
+    x = torch.randn(N, fin, generator=gen)
+    if dtype == torch.bfloat16 and (concat or heads == 1):
+        x *= 0.5
+    x = x.to(dtype)
+    Ws, As = O.init_gat_params(fin, fout, heads, gen)
+    ref = O.gat_layer(x.float(), ei, Ws, As, 0.2, concat=concat)
+    rowptr, col, _ = mg.ops.csr_from_coo(ei.cuda(), N, by_target=True)
+    y = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), concat=concat, slope=0.2, out_dtype=dtype)
+    torch.cuda.synchronize()
+    err = float((y.float().cpu() - ref).abs().max())
+    assert err <= (1e-5 if dtype == torch.float32 else TOL_BF16), err

@@ -128,3 +128,31 @@ def test_live_reference_agrees():
     Ws, As = O.stack_from_state_dict(net.state_dict())
     with torch.no_grad():
         assert same(net(x, ei), O.gat_network(x, ei, Ws, As))
+
+
+def test_knn_oracle_matches_pure_python_definition():
+    """The vectorised kNN restatement equals a literal per-pair loop (sequential fp32 sub/mul/add, lexicographic
+    (distance, id) order, self excluded) — including exact ties from duplicated points."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((24, 5)).astype(np.float32)
+    x[7] = x[3]                      # duplicate point -> zero distance, ties
+    x[11] = x[3]
+    k = 4
+    ei, dist = O.knn_graph(x, k, nodes_per_graph=12)
+    assert ei.shape == (2, 24 * k) and ei.dtype == np.int64
+    for j in range(24):
+        g0 = (j // 12) * 12
+        cands = []
+        for i in range(g0, g0 + 12):
+            if i == j:
+                continue
+            acc = np.float32(0)
+            for d in range(5):
+                t = np.float32(x[j, d] - x[i, d])
+                acc = np.float32(acc + np.float32(t * t))
+            cands.append((acc, i))
+        cands.sort()
+        want = cands[:k]
+        assert [int(v) for v in ei[0, j * k:(j + 1) * k]] == [i for _, i in want]
+        assert all(int(t) == j for t in ei[1, j * k:(j + 1) * k])
+        assert [float(v) for v in dist[j]] == [float(d) for d, _ in want]
