@@ -110,7 +110,8 @@ MG_API int mg_segment_mean(const float* h, const int32_t* labels, int B, int N, 
  *   save_den (N,heads) f32 and save_z (N,heads,in) f32 are optional (nullable) outputs kept
  *   for mg_gat_backward.
  *   dropout_p > 0 (training): attention dropout (:97) with a counter-based mask keyed on (seed, in-CSR slot,
- *   head); statistically equivalent to torch's, not the same stream.
+ *   head); statistically equivalent to torch's, not the same stream.  seed_dev (nullable DEVICE pointer): its value is
+ *   added to `seed` when the kernel runs, so a captured CUDA graph draws a fresh mask per replay.
  * Empty graphs (E == 0) are rejected with MG_ERR_INVALID like the reference's RuntimeError. */
 MG_API int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int num_graphs);
 /* 1 if mg_gat_forward runs the node transform of this shape on the tensor pipe (tcgen05 tf32 MMA, csrc/gat_tc.cu:
@@ -119,8 +120,8 @@ MG_API int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int 
 MG_API int mg_gat_uses_tensor_pipe(int N, int in_dim, int out_dim, int heads, int concat, int x_dtype, int out_dtype);
 MG_API int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, int64_t E,
                    const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
-                   int nodes_per_graph, float dropout_p, uint64_t seed, void* out, int out_dtype, void* work,
-                   float* save_den, float* save_z, mg_stream_t stream);
+                   int nodes_per_graph, float dropout_p, uint64_t seed, const uint64_t* seed_dev, void* out, int out_dtype,
+                   void* work, float* save_den, float* save_z, mg_stream_t stream);
 
 /* MultiHeadGATLayer backward (the reference relies on autograd: IndexBackward / ScatterAddBackward / MmBackward
  * over graph_attention.py:53-118).  Needs both CSR views and, per out-CSR slot, the in-CSR slot of the same edge
@@ -134,8 +135,9 @@ MG_API int64_t mg_gat_backward_work_bytes(int N, int64_t E, int in_dim, int out_
 MG_API int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in, const int32_t* col_in,
                     const int32_t* rowptr_out, const int32_t* col_out, const int32_t* slot_out2in, int N, int64_t E,
                     const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
-                    int nodes_per_graph, float dropout_p, uint64_t seed, const float* den, const float* z,
-                    const float* grad_out, float* grad_x, float* grad_W, float* grad_a, void* work, mg_stream_t stream);
+                    int nodes_per_graph, float dropout_p, uint64_t seed, const uint64_t* seed_dev, const float* den,
+                    const float* z, const float* grad_out, float* grad_x, float* grad_W, float* grad_a, void* work,
+                    mg_stream_t stream);
 
 /* Row softmax + argmax of the predictor logits — mincut_refinement.py:193 and
  * train_end_to_end.py:356.  logits (N,K) f32 -> S (N,K) f32, labels (N) int32 (first max). */

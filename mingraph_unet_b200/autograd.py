@@ -8,6 +8,25 @@ from . import ops
 from .graph import Graph
 
 
+_DROPOUT_COUNTERS = {}
+
+
+def dropout_counter(device) -> torch.Tensor:
+    """Persistent device-side counter added to every attention-dropout seed when the kernels run.  A captured training
+    step advances it inside the graph (:func:`advance_dropout_counter`), so each replay draws fresh masks while the
+    backward of the same replay regenerates exactly the forward's."""
+    key = str(device)
+    t = _DROPOUT_COUNTERS.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device=device)
+        _DROPOUT_COUNTERS[key] = t
+    return t
+
+
+def advance_dropout_counter(device) -> None:
+    dropout_counter(device).add_(1)
+
+
 def _wants_grad(*ts) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
 
@@ -16,11 +35,12 @@ class _GATLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, a, g: Graph, concat: bool, slope: float, att_dropout: float, out_dtype=None):
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if att_dropout > 0.0 else 0     # CPU generator: no device sync
+        seed_dev = dropout_counter(x.device) if att_dropout > 0.0 else None
         out, den, z = ops.gat_forward(x, g.rowptr_in, g.col_in, W, a, concat=concat, slope=slope,
                                       nodes_per_graph=g.nodes_per_graph, save=True, dropout_p=att_dropout, seed=seed,
-                                      out_dtype=out_dtype)
+                                      out_dtype=out_dtype, seed_dev=seed_dev)
         ctx.save_for_backward(x, W, a, den, z)
-        ctx.g, ctx.concat, ctx.slope, ctx.p, ctx.seed = g, concat, slope, att_dropout, seed
+        ctx.g, ctx.concat, ctx.slope, ctx.p, ctx.seed, ctx.seed_dev = g, concat, slope, att_dropout, seed, seed_dev
         return out
 
     @staticmethod
@@ -30,7 +50,7 @@ class _GATLayerFn(torch.autograd.Function):
         g.need_backward_maps()
         gx, gW, ga = ops.gat_backward(x, g.rowptr_in, g.col_in, g.rowptr_out, g.col_out, g.slot_out2in, W, a, den, z,
                                       grad_out, concat=ctx.concat, slope=ctx.slope, nodes_per_graph=g.nodes_per_graph,
-                                      dropout_p=ctx.p, seed=ctx.seed)
+                                      dropout_p=ctx.p, seed=ctx.seed, seed_dev=ctx.seed_dev)
         return gx.to(x.dtype), gW.to(W.dtype), ga.to(a.dtype), None, None, None, None, None
 
 
@@ -41,7 +61,8 @@ def gat_layer_apply(x: torch.Tensor, g: Graph, W: torch.Tensor, a: torch.Tensor,
         return _GATLayerFn.apply(x, W, a, g, concat, slope, att_dropout, out_dtype)
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if att_dropout > 0.0 else 0
     return ops.gat_forward(x, g.rowptr_in, g.col_in, W.detach(), a.detach(), concat=concat, slope=slope,
-                           nodes_per_graph=g.nodes_per_graph, dropout_p=att_dropout, seed=seed, out_dtype=out_dtype)
+                           nodes_per_graph=g.nodes_per_graph, dropout_p=att_dropout, seed=seed, out_dtype=out_dtype,
+                           seed_dev=dropout_counter(x.device) if att_dropout > 0.0 else None)
 
 
 class _SoftmaxFn(torch.autograd.Function):

@@ -51,6 +51,7 @@ struct BwdArgs {
   int N, in_dim, F, heads, concat, nodes_per_graph, splits;
   float slope, dropout_p;
   unsigned long long seed;
+  const unsigned long long* seed_dev;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) gat_bwd_target_kernel(const BwdArgs A) {
         dot = warp_sum(dot);
         const float pre = __ldg(A.s + (size_t)src * twoH + h) + stgt;
         const float alpha = expf(leaky_relu(pre, A.slope) - M) / dn;
-        const float m = A.dropout_p > 0.f ? dropout_keep_scale(A.seed, (unsigned)k, (unsigned)h, A.dropout_p) : 1.f;
+        const float m = A.dropout_p > 0.f ? dropout_keep_scale(A.seed + (A.seed_dev ? __ldg(A.seed_dev) : 0ull), (unsigned)k, (unsigned)h, A.dropout_p) : 1.f;
         const float ge = alpha * (m * dot - cj) + (pre == raw ? gM_share : 0.f);
         const float gpre = pre > 0.f ? ge : ge * A.slope;
         if (lane == 0) {
@@ -375,7 +376,7 @@ int64_t mg_gat_backward_work_bytes(int N, int64_t E, int in_dim, int out_dim, in
 int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in, const int32_t* col_in, const int32_t* rowptr_out,
                     const int32_t* col_out, const int32_t* slot_out2in, int N, int64_t E, const float* W, const float* a,
                     int in_dim, int out_dim, int heads, int concat, float slope, int nodes_per_graph, float dropout_p,
-                    uint64_t seed, const float* den, const float* z, const float* grad_out, float* grad_x, float* grad_W,
+                    uint64_t seed, const uint64_t* seed_dev, const float* den, const float* z, const float* grad_out, float* grad_x, float* grad_W,
                     float* grad_a, void* work, mg_stream_t stream) {
   MG_REQUIRE(x && rowptr_in && col_in && rowptr_out && col_out && slot_out2in && W && a && den && z && grad_out && grad_x &&
                  grad_W && grad_a && work,
@@ -405,6 +406,7 @@ int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in, const 
   A.gW = grad_W; A.ga = grad_a;
   A.N = N; A.in_dim = in_dim; A.F = out_dim; A.heads = heads; A.concat = concat ? 1 : 0;
   A.nodes_per_graph = nodes_per_graph; A.splits = L.splits; A.slope = slope; A.dropout_p = dropout_p; A.seed = seed;
+  A.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   float* gu = reinterpret_cast<float*>(wb + L.gu);
   int rc;
   // recompute the attention scalars and the per-graph shift (cheaper than saving them)

@@ -30,6 +30,7 @@ struct GatAggArgs {
   float slope;
   float dropout_p;        // attention dropout (graph_attention.py:97); 0 in eval mode
   unsigned long long seed;
+  const unsigned long long* seed_dev;   // optional device-side addend (CUDA-graph replays draw fresh masks)
 };
 
 // Counter-based Bernoulli mask for attention dropout: a pure function of (seed, in-CSR slot, head), so the
@@ -92,7 +93,8 @@ __device__ __forceinline__ void gat_aggregate_node(const GatAggArgs& a, int j, i
       }
     }
     den_lane += pv;                                  // the softmax denominator is taken before dropout (:94-97)
-    if (a.dropout_p > 0.f && valid && head_ok) pv *= dropout_keep_scale(a.seed, (unsigned)k, (unsigned)hl, a.dropout_p);
+    if (a.dropout_p > 0.f && valid && head_ok)
+      pv *= dropout_keep_scale(a.seed + (a.seed_dev ? __ldg(a.seed_dev) : 0ull), (unsigned)k, (unsigned)hl, a.dropout_p);
     __syncwarp();
     sc->p[lane] = pv;
     if (hl == 0) sc->src[el] = srcn;

@@ -307,7 +307,8 @@ int mg_gat_uses_tensor_pipe(int N, int in_dim, int out_dim, int heads, int conca
 
 int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, int64_t E,
                    const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
-                   int nodes_per_graph, float dropout_p, uint64_t seed, void* out, int out_dtype, void* work,
+                   int nodes_per_graph, float dropout_p, uint64_t seed, const uint64_t* seed_dev, void* out, int out_dtype,
+                   void* work,
                    float* save_den, float* save_z, mg_stream_t stream) {
   MG_REQUIRE(x && rowptr && W && a && out && work, MG_ERR_INVALID, "mg_gat_forward: null pointer");
   MG_REQUIRE(N > 0 && in_dim > 0 && out_dim > 0, MG_ERR_INVALID, "mg_gat_forward: bad sizes N=%d in=%d out=%d", N, in_dim,
@@ -352,7 +353,7 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   GatAggArgs ag;
   ag.x = x; ag.rowptr = rowptr; ag.col = col; ag.s = s; ag.gmax = gmax;
   ag.N = N; ag.in_dim = in_dim; ag.heads = heads; ag.nodes_per_graph = nodes_per_graph; ag.slope = slope;
-  ag.dropout_p = dropout_p; ag.seed = seed;
+  ag.dropout_p = dropout_p; ag.seed = seed; ag.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
 
   if (plan.ok) {
     GatFusedArgs A;

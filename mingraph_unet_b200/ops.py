@@ -200,7 +200,8 @@ def unpool_nearest(table: torch.Tensor, labels: Optional[torch.Tensor], Hp: int,
 # ---------------------------------------------------------------------------------------------
 def gat_forward(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, W: torch.Tensor, a: torch.Tensor,
                 concat: bool = False, slope: float = 0.2, nodes_per_graph: int = 0,
-                out_dtype: Optional[torch.dtype] = None, save: bool = False, dropout_p: float = 0.0, seed: int = 0):
+                out_dtype: Optional[torch.dtype] = None, save: bool = False, dropout_p: float = 0.0, seed: int = 0,
+                seed_dev: Optional[torch.Tensor] = None):
     """Multi-head GAT layer forward (eval semantics).  ``x (N,in)`` f32|bf16, ``W (H,F,in)``,
     ``a (H,2F)`` f32, in-CSR ``rowptr/col`` int32.  Returns ``out`` or ``(out, den, z)`` if ``save``."""
     _need_cuda(x, rowptr, col, W, a)
@@ -227,8 +228,8 @@ def gat_forward(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, W: tor
     with torch.cuda.device(x.device):
         call("mg_gat_forward", x.data_ptr(), _dtype_code(x.dtype), rowptr.data_ptr(), col.data_ptr(), N, E,
              W.data_ptr(), a.data_ptr(), in_dim, F, heads, int(concat), float(slope), int(nodes_per_graph),
-             float(dropout_p), int(seed), out.data_ptr(), _dtype_code(out_dtype), work.data_ptr(), _ptr(den), _ptr(z),
-             _stream())
+             float(dropout_p), int(seed), _ptr(seed_dev), out.data_ptr(), _dtype_code(out_dtype), work.data_ptr(), _ptr(den),
+             _ptr(z), _stream())
     return (out, den, z) if save else out
 
 
@@ -244,7 +245,8 @@ def edge_slot_map(eid_in: torch.Tensor, eid_out: torch.Tensor) -> torch.Tensor:
 
 
 def gat_backward(x, rowptr_in, col_in, rowptr_out, col_out, slot_out2in, W, a, den, z, grad_out, concat: bool = False,
-                 slope: float = 0.2, nodes_per_graph: int = 0, dropout_p: float = 0.0, seed: int = 0):
+                 slope: float = 0.2, nodes_per_graph: int = 0, dropout_p: float = 0.0, seed: int = 0,
+                 seed_dev: Optional[torch.Tensor] = None):
     """Backward of ``gat_forward``: returns ``grad_x (N,in) f32, grad_W (H,F,in), grad_a (H,2F)``."""
     _need_cuda(x, W, a, den, z, grad_out)
     N, in_dim = x.shape
@@ -264,7 +266,7 @@ def gat_backward(x, rowptr_in, col_in, rowptr_out, col_out, slot_out2in, W, a, d
     with torch.cuda.device(dev):
         call("mg_gat_backward", x.data_ptr(), _dtype_code(x.dtype), rowptr_in.data_ptr(), col_in.data_ptr(),
              rowptr_out.data_ptr(), col_out.data_ptr(), slot_out2in.data_ptr(), N, E, W.data_ptr(), a.data_ptr(), in_dim, F,
-             heads, int(concat), float(slope), int(nodes_per_graph), float(dropout_p), int(seed), den.data_ptr(),
+             heads, int(concat), float(slope), int(nodes_per_graph), float(dropout_p), int(seed), _ptr(seed_dev), den.data_ptr(),
              z.data_ptr(), grad_out.data_ptr(), gx.data_ptr(), gW.data_ptr(), ga.data_ptr(), work.data_ptr(), _stream())
     return gx, gW, ga
 

@@ -41,7 +41,7 @@ def test_argument_validation_without_device(mg):
         _lib.call("mg_grid_edge_index", 0, 4, 1, 0, None, None)
     assert e.value.code == _lib.MG_ERR_INVALID and "bad grid" in e.value.text
     with pytest.raises(_lib.MinGraphError) as e:
-        _lib.call("mg_gat_forward", 1, 0, 1, None, 4, 0, 1, 1, 8, 8, 1, 0, 0.2, 0, 0.0, 0, 1, 0, 1, None, None, None)
+        _lib.call("mg_gat_forward", 1, 0, 1, None, 4, 0, 1, 1, 8, 8, 1, 0, 0.2, 0, 0.0, 0, None, 1, 0, 1, None, None, None)
     assert "empty edge_index" in e.value.text
 
 
