@@ -95,9 +95,11 @@ MG_API int mg_pool_patches(const void* x, int x_dtype, int B, int C, int Hf, int
                     int out_dtype, mg_stream_t stream);
 /* Region mean pool — train_end_to_end.py:368-373: out[b,k,:] = mean(h[b, labels[b]==k, :]),
  * zero for empty regions.  h (B,N,D) f32, labels (B,N) int32, out (B,K,D) f32,
- * counts (B,K) int32 (nullable). */
+ * counts (B,K) int32 (nullable); work: mg_segment_work_bytes() bytes.  Two deterministic stages (per-chunk partials,
+ * then a fixed-order sum), no atomics. */
+MG_API int64_t mg_segment_work_bytes(int B, int N, int D, int K);
 MG_API int mg_segment_mean(const float* h, const int32_t* labels, int B, int N, int D, int K, float* out,
-                    int32_t* counts, mg_stream_t stream);
+                    int32_t* counts, void* work, mg_stream_t stream);
 
 /* ---- graph attention ---------------------------------------------------------------------
  * MultiHeadGATLayer.forward (eval) — model/gat/graph_attention.py:40-118,150-160.
@@ -176,7 +178,7 @@ MG_API int mg_unpool_nearest(const float* table, const int32_t* labels, int B, i
  * mg_unpool_nearest_backward: grad_out (B,D,H,W) planes f32|bf16 (image b at grad_out + b*grad_batch_stride
  * elements) -> grad_table (B,K,D) f32 = sum of the gradient over the pixels whose patch carries label k
  * (labels NULL: K == Hp*Wp, per-patch sums).  work: mg_unpool_backward_work_bytes() bytes. */
-MG_API int64_t mg_unpool_backward_work_bytes(int B, int D, int Hp, int Wp);
+MG_API int64_t mg_unpool_backward_work_bytes(int B, int D, int Hp, int Wp, int K);
 MG_API int mg_unpool_nearest_backward(const void* grad_out, int grad_dtype, int64_t grad_batch_stride, const int32_t* labels,
                                int B, int K, int D, int Hp, int Wp, int H, int W, void* work, float* grad_table,
                                mg_stream_t stream);

@@ -43,7 +43,8 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_csr_from_coo": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mg_knn_graph": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "mg_pool_patches": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
-    "mg_segment_mean": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "mg_segment_work_bytes": (_i64, [_i, _i, _i, _i]),
+    "mg_segment_mean": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "mg_gat_work_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "mg_gat_uses_tensor_pipe": (_i, [_i] * 7),
     "mg_gat_forward": (_i, [_p, _i, _p, _p, _i, _i64, _p, _p, _i, _i, _i, _i, _f, _i, _f, C.c_uint64, _p, _p, _i, _p, _p, _p, _p]),
@@ -57,7 +58,7 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_ncut_loss": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "mg_ncut_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "mg_unpool_nearest": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i64, _p]),
-    "mg_unpool_backward_work_bytes": (_i64, [_i, _i, _i, _i]),
+    "mg_unpool_backward_work_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "mg_unpool_nearest_backward": (_i, [_p, _i, _i64, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mg_segment_mean_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "mg_softmax_backward": (_i, [_p, _p, _i, _i, _p, _p]),

@@ -54,29 +54,6 @@ __global__ void unpool_bwd_window_kernel(const TG* __restrict__ g, int64_t batch
   }
 }
 
-// per image: out[b,k,:] = scale * sum_{n: labels[b,n]==k} gp[b,n,:]; warp-private shared accumulators, fixed order
-__global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ gp, const int32_t* __restrict__ labels,
-                                                          int N, int D, int K, float scale, float* __restrict__ out) {
-  extern __shared__ float acc[];                       // [8][K][D]
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 8 * K * D; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
-  float* mine = acc + (size_t)warp * K * D;
-  for (int n = warp; n < N; n += 8) {
-    const int k = labels ? __ldg(labels + (size_t)b * N + n) : n;
-    if (k < 0 || k >= K) continue;
-    const float* row = gp + ((size_t)b * N + n) * D;
-    for (int d = lane; d < D; d += 32) mine[k * D + d] += __ldg(row + d);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += acc[(size_t)w * K * D + i];
-    out[(size_t)b * K * D + i] = s * scale;
-  }
-}
-
 // grad_h[b,n,:] (+)= grad_R[b, l, :] / count[b, l]
 __global__ void segment_mean_bwd_kernel(const float* __restrict__ gR, const int32_t* __restrict__ labels,
                                         const int32_t* __restrict__ counts, int B, int N, int D, int K, int accumulate,
@@ -113,9 +90,9 @@ using namespace mg;
 
 extern "C" {
 
-int64_t mg_unpool_backward_work_bytes(int B, int D, int Hp, int Wp) {
-  if (B <= 0 || D <= 0 || Hp <= 0 || Wp <= 0) return 0;
-  return (int64_t)B * Hp * Wp * D * 4 + 256;
+int64_t mg_unpool_backward_work_bytes(int B, int D, int Hp, int Wp, int K) {
+  if (B <= 0 || D <= 0 || Hp <= 0 || Wp <= 0 || K <= 0) return 0;
+  return (((int64_t)B * Hp * Wp * D * 4 + 255) & ~(int64_t)255) + segment_work_bytes(B, Hp * Wp, D, K);
 }
 
 int mg_unpool_nearest_backward(const void* grad_out, int grad_dtype, int64_t grad_batch_stride, const int32_t* labels, int B,
@@ -162,9 +139,8 @@ int mg_unpool_nearest_backward(const void* grad_out, int grad_dtype, int64_t gra
     }
     return MG_OK;
   }
-  if (smem > 48 * 1024) cudaFuncSetAttribute(segment_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  segment_sum_kernel<<<B, 256, smem, st>>>(gp, labels, N, D, K, scale, grad_table);
-  return check_launch("segment_sum_kernel");
+  unsigned char* seg_work = reinterpret_cast<unsigned char*>(work) + (((size_t)B * N * D * 4 + 255) & ~(size_t)255);
+  return segment_reduce_launch(gp, labels, B, N, D, K, 0, scale, grad_table, nullptr, seg_work, st);
 }
 
 int mg_segment_mean_backward(const float* grad_out, const int32_t* labels, const int32_t* counts, int B, int N, int D, int K,

@@ -23,6 +23,11 @@ int check_launch(const char* what);   // cudaGetLastError() -> MG_ERR_CUDA
 
 int num_sms();                        // cached cudaDevAttrMultiProcessorCount (148 on B200)
 
+// deterministic two-stage per-label row reduction (pool_unpool.cu): out (B,K,D) = mean or scale*sum of h (B,N,D) rows by label
+int64_t segment_work_bytes(int B, int N, int D, int K);
+int segment_reduce_launch(const float* h, const int32_t* labels, int B, int N, int D, int K, int mean, float scale, float* out,
+                          int32_t* counts, void* work, cudaStream_t st);
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

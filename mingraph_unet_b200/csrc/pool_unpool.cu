@@ -162,21 +162,26 @@ __global__ void pool_patches_generic_kernel(const TX* __restrict__ x, int B, int
 }
 
 // ------------------------------------------------------------------------------------------
-// a11: region mean pool.  One block per image; warp-private shared accumulators, fixed
-// reduction order (deterministic, no atomics).
+// a11: region mean pool.  Two deterministic stages (no atomics, fixed reduction order):
+//   partial: block (chunk, image) reduces its chunk of nodes with warp-private shared accumulators;
+//   finalize: thread per (image, k, d) sums the chunk partials in chunk order and divides by the count.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ h, const int32_t* __restrict__ labels,
-                                                           int N, int D, int K, float* __restrict__ out,
-                                                           int32_t* __restrict__ counts) {
+constexpr int kSegChunkNodes = 64;
+
+__global__ void __launch_bounds__(256) segment_partial_kernel(const float* __restrict__ h, const int32_t* __restrict__ labels,
+                                                              int N, int D, int K, float* __restrict__ part,
+                                                              int32_t* __restrict__ part_cnt) {
   extern __shared__ float acc[];                       // [8][K][D] then int cnt[8][K]
   int* cnt = reinterpret_cast<int*>(acc + (size_t)8 * K * D);
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 8 * K * D; i += blockDim.x) acc[i] = 0.f;
   for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
   float* mine = acc + (size_t)warp * K * D;
-  for (int n = warp; n < N; n += 8) {
-    const int k = __ldg(labels + (size_t)b * N + n);
+  const int n0 = chunk * kSegChunkNodes, n1 = min(N, n0 + kSegChunkNodes);
+  for (int n = n0 + warp; n < n1; n += 8) {
+    const int k = labels ? __ldg(labels + (size_t)b * N + n) : n;
     if (k < 0 || k >= K) continue;
     const float* row = h + ((size_t)b * N + n) * D;
     for (int d = lane; d < D; d += 32) mine[k * D + d] += __ldg(row + d);
@@ -184,14 +189,58 @@ __global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restri
   }
   __syncthreads();
   for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
-    const int k = i / D;
     float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += acc[(size_t)w * K * D + i];
+    part[((size_t)b * nchunks + chunk) * K * D + i] = s;
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
     int c = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { s += acc[(size_t)w * K * D + i]; c += cnt[w * K + k]; }
-    out[(size_t)b * K * D + i] = c > 0 ? s / (float)c : 0.f;       // train_end_to_end.py:372-373
-    if (counts && (i % D) == 0) counts[b * K + k] = c;
+    for (int w = 0; w < 8; ++w) c += cnt[w * K + k];
+    part_cnt[((size_t)b * nchunks + chunk) * K + k] = c;
   }
+}
+
+// mean != 0: out = sum / count (0 for empty regions, train_end_to_end.py:372-373); else out = scale * sum
+__global__ void segment_finalize_kernel(const float* __restrict__ part, const int32_t* __restrict__ part_cnt, int B, int nchunks,
+                                        int K, int D, int mean, float scale, float* __restrict__ out,
+                                        int32_t* __restrict__ counts) {
+  const int total = B * K * D;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int d = t % D, k = (t / D) % K, b = t / (D * K);
+    float s = 0.f;
+    int c = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      s += part[((size_t)b * nchunks + ch) * K * D + k * D + d];
+      c += part_cnt[((size_t)b * nchunks + ch) * K + k];
+    }
+    out[t] = mean ? (c > 0 ? s / (float)c : 0.f) : s * scale;
+    if (counts && d == 0) counts[b * K + k] = c;
+  }
+}
+
+// shared by mg_segment_mean and the un-pool backward (block_backward.cu).  work: segment_work_bytes().
+int64_t segment_work_bytes(int B, int N, int D, int K) {
+  const int nchunks = ceil_div(N, kSegChunkNodes);
+  return (int64_t)B * nchunks * K * (D + 1) * 4 + 256;
+}
+int segment_reduce_launch(const float* h, const int32_t* labels, int B, int N, int D, int K, int mean, float scale, float* out,
+                          int32_t* counts, void* work, cudaStream_t st) {
+  const size_t smem = (size_t)8 * K * D * 4 + (size_t)8 * K * 4;
+  MG_REQUIRE(smem <= 200 * 1024, MG_ERR_UNSUPPORTED, "segment reduce: K*D=%d too large for shared accumulators", K * D);
+  const int nchunks = ceil_div(N, kSegChunkNodes);
+  float* part = reinterpret_cast<float*>(work);
+  int32_t* part_cnt = reinterpret_cast<int32_t*>(part + (size_t)B * nchunks * K * D);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(segment_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  dim3 grid(nchunks, B);
+  MG_REQUIRE(B <= 65535, MG_ERR_INVALID, "segment reduce: batch too large");
+  segment_partial_kernel<<<grid, 256, smem, st>>>(h, labels, N, D, K, part, part_cnt);
+  int rc = check_launch("segment_partial_kernel");
+  if (rc) return rc;
+  segment_finalize_kernel<<<std::min(ceil_div(B * K * D, 256), num_sms() * 4), 256, 0, st>>>(part, part_cnt, B, nchunks, K, D, mean,
+                                                                                       scale, out, counts);
+  return check_launch("segment_finalize_kernel");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -394,14 +443,15 @@ int mg_pool_patches(const void* x, int x_dtype, int B, int C, int Hf, int Wf, in
   return MG_ERR_INVALID;
 }
 
-int mg_segment_mean(const float* h, const int32_t* labels, int B, int N, int D, int K, float* out, int32_t* counts,
+int64_t mg_segment_work_bytes(int B, int N, int D, int K) {
+  if (B <= 0 || N <= 0 || D <= 0 || K <= 0) return 0;
+  return segment_work_bytes(B, N, D, K);
+}
+
+int mg_segment_mean(const float* h, const int32_t* labels, int B, int N, int D, int K, float* out, int32_t* counts, void* work,
                     mg_stream_t stream) {
-  MG_REQUIRE(h && labels && out && B > 0 && N > 0 && D > 0 && K > 0, MG_ERR_INVALID, "mg_segment_mean: bad arguments");
-  const size_t smem = (size_t)8 * K * D * 4 + (size_t)8 * K * 4;
-  MG_REQUIRE(smem <= 200 * 1024, MG_ERR_UNSUPPORTED, "mg_segment_mean: K*D=%d too large for shared accumulators", K * D);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(segment_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  segment_mean_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(h, labels, N, D, K, out, counts);
-  return check_launch("segment_mean_kernel");
+  MG_REQUIRE(h && labels && out && work && B > 0 && N > 0 && D > 0 && K > 0, MG_ERR_INVALID, "mg_segment_mean: bad arguments");
+  return segment_reduce_launch(h, labels, B, N, D, K, 1, 1.f, out, counts, work, (cudaStream_t)stream);
 }
 
 int mg_unpool_nearest(const float* table, const int32_t* labels, int B, int K, int D, int Hp, int Wp, int H, int W,

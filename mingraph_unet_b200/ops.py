@@ -167,8 +167,10 @@ def segment_mean(h: torch.Tensor, labels: torch.Tensor, K: int, with_counts: boo
     B, N, D = h.shape
     out = torch.empty((B, K, D), dtype=torch.float32, device=h.device)
     counts = torch.empty((B, K), dtype=torch.int32, device=h.device) if with_counts else None
+    work = torch.empty(int(_lib.load().mg_segment_work_bytes(B, N, D, K)), dtype=torch.uint8, device=h.device)
     with torch.cuda.device(h.device):
-        call("mg_segment_mean", h.data_ptr(), labels.data_ptr(), B, N, D, K, out.data_ptr(), _ptr(counts), _stream())
+        call("mg_segment_mean", h.data_ptr(), labels.data_ptr(), B, N, D, K, out.data_ptr(), _ptr(counts), work.data_ptr(),
+             _stream())
     return (out, counts) if with_counts else out
 
 
@@ -353,7 +355,7 @@ def unpool_nearest_backward(grad_out: torch.Tensor, labels: Optional[torch.Tenso
     B, D, H, W = grad_out.shape
     if labels is not None:
         labels = labels.contiguous()
-    work = torch.empty(int(_lib.load().mg_unpool_backward_work_bytes(B, D, Hp, Wp)), dtype=torch.uint8, device=grad_out.device)
+    work = torch.empty(int(_lib.load().mg_unpool_backward_work_bytes(B, D, Hp, Wp, K)), dtype=torch.uint8, device=grad_out.device)
     gt = torch.empty((B, K, D), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
         call("mg_unpool_nearest_backward", grad_out.data_ptr(), _dtype_code(grad_out.dtype),

@@ -54,3 +54,85 @@ class CapturedGraphBlock:
             self.block._prepared()            # refresh the weight blob in place if a parameter changed
         self.graph.replay()
         return self.outputs
+
+
+class CapturedTrainStep:
+    """One training step of a :class:`GraphBlock` recorded into CUDA graphs and replayed with one or two driver calls.
+
+    The eager step is host-launch bound (~60 kernels of a few microseconds each plus autograd/optimizer glue).  Recorded:
+
+    * graph A: advance the device-side dropout counter -> patch-mean pool of the static feature map -> block forward
+      (training branch, differentiable ops of ``autograd.py``) -> ``loss_fn(out)`` -> ``backward()`` accumulating into ONE
+      flat fp32 gradient buffer (every ``p.grad`` is a view of it);
+    * between the graphs, with more than one rank: ONE NCCL all-reduce of the flat buffer (22 792 floats for the default
+      block), issued eagerly on the same stream;
+    * graph B: ``optimizer.step()`` (the optimizer must be built with ``capturable=True``).
+
+    With a single rank A and B are recorded as one graph.  ``loss_fn`` maps a :class:`GraphBlockOutput` to a scalar and may
+    close over other static tensors.  Attention-dropout masks differ from replay to replay (device-side seed addend) and
+    are regenerated exactly by the backward of the same replay."""
+
+    def __init__(self, block: GraphBlock, optimizer: torch.optim.Optimizer, example_feature_map: torch.Tensor,
+                 image_size: Tuple[int, int], loss_fn, out_dtype: Optional[torch.dtype] = None, group=None, warmup: int = 3):
+        import torch.distributed as dist
+        from . import ops
+        from .autograd import advance_dropout_counter
+        if not example_feature_map.is_cuda:
+            raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        self.block, self.opt, self.group = block, optimizer, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        dev = example_feature_map.device
+        self.static_in = example_feature_map.clone()
+        params = [p for p in block.parameters() if p.requires_grad]
+        self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        ph = block.patch_size
+
+        def fwd_bwd():
+            advance_dropout_counter(dev)
+            self.flat_grad.zero_()
+            x = ops.pool_patches(self.static_in, ph, ph)
+            out = block(node_features=x, image_size=image_size, out_dtype=out_dtype)
+            loss = loss_fn(out)
+            loss.backward()
+            return loss.detach()
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 3)):          # also fills the graph caches (CSR, backward slot maps)
+                fwd_bwd()
+                self._allreduce()
+                optimizer.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph_a = torch.cuda.CUDAGraph()
+        self.graph_b = None
+        if self.world == 1:
+            with torch.cuda.graph(self.graph_a):
+                self.loss = fwd_bwd()
+                optimizer.step()
+        else:
+            with torch.cuda.graph(self.graph_a):
+                self.loss = fwd_bwd()
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+                optimizer.step()
+
+    def _allreduce(self) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat_grad.div_(self.world)
+
+    def __call__(self, feature_map: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Copies ``feature_map`` into the static input (skipped when None), runs one step, returns the static loss tensor."""
+        if feature_map is not None and feature_map.data_ptr() != self.static_in.data_ptr():
+            self.static_in.copy_(feature_map, non_blocking=True)
+        self.graph_a.replay()
+        if self.graph_b is not None:
+            self._allreduce()
+            self.graph_b.replay()
+        return self.loss

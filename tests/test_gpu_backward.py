@@ -305,3 +305,59 @@ def test_block_training_step_grads_vs_oracle(mg, B, H, W, K):
         # K = 2 regions: every region node has ONE in-edge, alpha == 1 and d/da is identically ~0 (noise on both sides)
         ref_a = ps[f"{name}_a"].grad
         assert float((ga.cpu() - ref_a).abs().max()) <= 3e-4 * float(ref_a.abs().max()) + 1e-9, name
+
+
+def test_captured_train_step_matches_eager(mg):
+    """CapturedTrainStep (CUDA-graph replay of pool -> fwd -> loss -> bwd -> Adam) takes the same optimizer steps as the
+    eager loop (dropout off), and with dropout on every replay draws a different mask."""
+    import copy
+    B, C, H, W, K = 2, 20, 64, 64, 2
+    gen = torch.Generator().manual_seed(3)
+    fm = torch.randn(B, C, H, W, generator=gen).cuda()
+    wd = (torch.randn(B, 64, H, W, generator=gen) / (H * W)).cuda()
+
+    def make(p_drop):
+        torch.manual_seed(0)
+        blk = mg.GraphBlock(node_feature_dim=C, num_segments=K, dropout_rate=p_drop)
+        for m in blk.modules():
+            if hasattr(m, "dropout_rate"):
+                m.dropout_rate = p_drop
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0                        # output dropout is torch's (not replayable by seed); keep the kernel's
+        return blk.cuda().train()
+
+    def loss_fn(out):
+        return (out.f_g * wd).sum() + out.l_partition.mean()
+
+    eager = make(0.0)
+    captured = copy.deepcopy(eager)
+    opt_e = torch.optim.Adam(eager.parameters(), lr=1e-2, capturable=True)
+    opt_c = torch.optim.Adam(captured.parameters(), lr=1e-2, capturable=True)
+    start = [p.detach().clone() for p in captured.parameters()]
+    trainer = mg.CapturedTrainStep(captured, opt_c, fm, (H, W), loss_fn, warmup=3)
+    # the warm-up steps already moved the captured copy: rewind weights and optimizer state
+    with torch.no_grad():
+        for p, s0 in zip(captured.parameters(), start):
+            p.copy_(s0)
+    for st in opt_c.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    losses_c, losses_e = [], []
+    for _ in range(3):
+        losses_c.append(float(trainer()))
+        x = mg.ops.pool_patches(fm, 16, 16)
+        opt_e.zero_grad(set_to_none=True)
+        le = loss_fn(eager(node_features=x, image_size=(H, W)))
+        le.backward()
+        opt_e.step()
+        losses_e.append(float(le.detach()))
+    assert losses_c == pytest.approx(losses_e, rel=2e-4, abs=1e-6)
+    for pc, pe in zip(captured.parameters(), eager.parameters()):
+        assert rel_err(pc, pe) <= 2e-3
+    # dropout on: consecutive replays differ (fresh masks from the device-side counter)
+    drop = make(0.3)
+    opt_d = torch.optim.SGD(drop.parameters(), lr=0.0)
+    tr = mg.CapturedTrainStep(drop, opt_d, fm, (H, W), loss_fn, warmup=3)
+    vals = {round(float(tr()), 7) for _ in range(4)}
+    assert len(vals) >= 3
