@@ -36,8 +36,11 @@ __global__ void gat_u_kernel(const float* __restrict__ W, const float* __restric
   compute_u(W, a, in_dim, F, heads, u, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
-// warp per node; u in shared memory; also resets gmax (consumed by the next kernel on the stream)
-template <typename TX, int V, int T>
+// warp per node; u in shared memory; also resets gmax (consumed by the next kernel on the stream).
+// The 2*heads dot products of a node are reduced over the warp TOGETHER: each butterfly step halves the number of
+// values a lane carries (NQP-1 + log2(32/NQP) shuffles instead of 5 per value), after which lane L holds the total of
+// scalar q(L) given by the lane bits consumed by the halving steps.
+template <typename TX, int V, int T, int NQP>
 __global__ void __launch_bounds__(256) gat_scores_kernel(const TX* __restrict__ x, int N, int in_dim,
                                                          const float* __restrict__ W, const float* __restrict__ a,
                                                          const float* __restrict__ u_global, int F, int heads,
@@ -56,6 +59,17 @@ __global__ void __launch_bounds__(256) gat_scores_kernel(const TX* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // scalar index this lane ends up holding, and the lane that stores it
+  int my_q = 0;
+  {
+    int n = NQP, bit = 0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      if (n > 1) { n >>= 1; if (lane & o) my_q += n; bit |= o; }
+    }
+    (void)bit;
+  }
+  constexpr int kTail = 32 / NQP;                  // lanes sharing one scalar after the halving steps
   for (int n = warp_global; n < N; n += nwarps) {
     float xv[V * T];
 #pragma unroll
@@ -68,21 +82,43 @@ __global__ void __launch_bounds__(256) gat_scores_kernel(const TX* __restrict__ 
         for (int v = 0; v < V; ++v) xv[t * V + v] = 0.f;
       }
     }
-    float mine = 0.f;
-    for (int q = 0; q < nq; ++q) {
+    float vals[NQP];
+#pragma unroll
+    for (int q = 0; q < NQP; ++q) {
       float acc = 0.f;
+      if (q < nq) {
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int d = LaneDims<V, T>::dim(lane, t);
-        if (d < in_dim) {
+        for (int t = 0; t < T; ++t) {
+          const int d = LaneDims<V, T>::dim(lane, t);
+          if (d < in_dim) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) acc = fmaf(xv[t * V + v], u_s[q * in_dim + d + v], acc);
+            for (int v = 0; v < V; ++v) acc = fmaf(xv[t * V + v], u_s[q * in_dim + d + v], acc);
+          }
         }
       }
-      acc = warp_sum(acc);
-      if (lane == q) mine = acc;
+      vals[q] = acc;
     }
-    if (lane < nq) s[(size_t)n * nq + lane] = mine;
+    {
+      int cnt = NQP;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        if (cnt > 1) {
+          cnt >>= 1;
+          const bool upper = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < NQP / 2; ++i) {
+            if (i < cnt) {
+              const float send = upper ? vals[i] : vals[i + cnt];
+              const float keep = upper ? vals[i + cnt] : vals[i];
+              vals[i] = keep + __shfl_xor_sync(kFull, send, o);
+            }
+          }
+        } else {
+          vals[0] += __shfl_xor_sync(kFull, vals[0], o);
+        }
+      }
+    }
+    if ((lane & (kTail - 1)) == 0 && my_q < nq) s[(size_t)n * nq + my_q] = vals[0];
   }
 }
 
@@ -232,10 +268,15 @@ static int launch_scores(const void* x, int N, int in_dim, const float* W, const
   const size_t smem = (size_t)2 * heads * in_dim * 4;
   const int grid = (int)std::min<int64_t>(ceil_div64((int64_t)N * 32, 256), (int64_t)num_sms() * 8);
   const TX* xx = reinterpret_cast<const TX*>(x);
-#define MG_SC(VV, TT)                                                                                             \
-  if (d.V == VV && d.T == TT) {                                                                                   \
-    gat_scores_kernel<TX, VV, TT><<<grid, 256, smem, st>>>(xx, N, in_dim, W, a, u_global, F, heads, G, s, gmax);  \
-    return check_launch("gat_scores_kernel");                                                                     \
+  const int nq = 2 * heads;
+  const int nqp = nq <= 2 ? 2 : (nq <= 4 ? 4 : (nq <= 8 ? 8 : 16));
+#define MG_SC(VV, TT)                                                                                                  \
+  if (d.V == VV && d.T == TT) {                                                                                        \
+    if (nqp == 2) gat_scores_kernel<TX, VV, TT, 2><<<grid, 256, smem, st>>>(xx, N, in_dim, W, a, u_global, F, heads, G, s, gmax);        \
+    else if (nqp == 4) gat_scores_kernel<TX, VV, TT, 4><<<grid, 256, smem, st>>>(xx, N, in_dim, W, a, u_global, F, heads, G, s, gmax);   \
+    else if (nqp == 8) gat_scores_kernel<TX, VV, TT, 8><<<grid, 256, smem, st>>>(xx, N, in_dim, W, a, u_global, F, heads, G, s, gmax);   \
+    else gat_scores_kernel<TX, VV, TT, 16><<<grid, 256, smem, st>>>(xx, N, in_dim, W, a, u_global, F, heads, G, s, gmax);               \
+    return check_launch("gat_scores_kernel");                                                                          \
   }
   MG_SC(1, 1) MG_SC(2, 1) MG_SC(4, 1) MG_SC(4, 2) MG_SC(4, 4)
 #undef MG_SC
