@@ -492,3 +492,76 @@ def test_knn_errors(mg):
         mg.ops.knn_graph(x, 16)                        # needs k other nodes
     with pytest.raises(MinGraphError):
         mg.ops.knn_graph(x, 2, nodes_per_graph=5)      # N not a multiple
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties (the oracle is too slow at these sizes)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,dtype", [(16, 512, 512, torch.bfloat16), (2, 1024, 1024, torch.bfloat16),
+                                          (4, 512, 512, torch.float32)])
+def test_full_size_block_properties(mg, B, H, W, dtype):
+    """cfg 2 (512^2, batch 16, bf16) and a cfg-3 shard (1024^2): (i) the one-launch cluster kernel and the composed
+    stand-alone kernels agree (labels bit-exact); (ii) the dense map IS region_out gathered by label and nearest
+    up-sampled (bit-exact vs torch); (iii) an image computed alone equals the same image inside the batch (bit-exact:
+    graphs are independent, the softmax shift is per image); (iv) pooling the dense map back returns the per-patch
+    rows (un-pool -> pool round trip)."""
+    import torch.nn.functional as F
+    C, K, D = 20, 2, 64
+    gen = torch.Generator().manual_seed(B * 7 + H)
+    fm = torch.randn(B, C, H, W, generator=gen).to(dtype).cuda()
+    P = O.init_block_params(C, D, 4, K, seed=1234)
+    blk = mg.GraphBlock(node_feature_dim=C, num_segments=K)
+    for name, net in (("patch", blk.patch_gat_model), ("pred", blk.segment_predictor.gnn_predictor),
+                      ("region", blk.region_gat_model)):
+        load_heads(net, P[f"{name}_W"], P[f"{name}_a"])
+    blk = blk.cuda().eval()
+    with torch.no_grad():
+        blk.fused = True
+        a = blk(feature_map=fm, out_dtype=torch.float32)
+        blk.fused = False
+        b = blk(feature_map=fm, out_dtype=torch.float32)
+        blk.fused = True
+        one = blk(feature_map=fm[1:2].contiguous(), out_dtype=torch.float32)
+    nph, npw = a.grid
+    N = nph * npw
+    # (i)
+    assert torch.equal(a.hard_labels, b.hard_labels)
+    assert maxabs(a.patch_features, b.patch_features) <= 1e-5 and maxabs(a.region_features, b.region_features) <= 1e-5
+    assert maxabs(a.l_partition, b.l_partition) <= 1e-5 * max(1.0, float(b.l_partition.abs().max()))
+    # (ii)
+    idx = a.hard_labels.long().unsqueeze(-1).expand(-1, -1, D)
+    per_patch = torch.gather(a.region_features, 1, idx)                       # (B, N, D) = region[labels]
+    want = F.interpolate(per_patch.transpose(1, 2).reshape(B, D, nph, npw), size=(H, W), mode="nearest")
+    assert torch.equal(a.f_g, want)
+    # (iii)
+    assert torch.equal(one.hard_labels[0], a.hard_labels[1])
+    assert torch.equal(one.patch_features[0], a.patch_features[1]) and torch.equal(one.region_features[0], a.region_features[1])
+    assert torch.equal(one.f_g[0], a.f_g[1])
+    # (iv)
+    back = mg.ops.pool_patches(a.f_g, 16, 16)
+    assert maxabs(back, per_patch) <= 1e-6 * max(1.0, float(per_patch.abs().max()))
+    # edge count of the implied graph (closed form, patch_graph_construction.py:78-97)
+    assert mg.ops.grid_num_edges(nph, npw) == 2 * (nph * (npw - 1) + npw * (nph - 1))
+
+
+def test_full_size_gat_linearity_in_values(mg):
+    """N = 262 144 (largest sweep size): with the attention weights fixed (a = 0 => uniform alpha per destination) the
+    layer is ELU(W * mean of neighbours): check against a torch segment mean at full size, fp32 and bf16 (tensor pipe)."""
+    N, k, Fd, H = 262144, 8, 64, 4
+    gen = torch.Generator().manual_seed(0)
+    tgt = torch.arange(N).repeat_interleave(k)
+    src = torch.randint(0, N, (N * k,), generator=gen)
+    ei = torch.stack([src, tgt]).cuda()
+    rowptr, col, _ = mg.ops.csr_from_coo(ei, N, by_target=True)
+    x = torch.randn(N, Fd, generator=gen).cuda()
+    Ws, _ = O.init_gat_params(Fd, Fd, H, gen)
+    Wg, Ag = Ws.cuda(), torch.zeros(H, 2 * Fd).cuda()
+    mean_nb = x[ei[0]].view(N, k, Fd).mean(1)                                  # tgt is sorted: rows of k neighbours
+    ref = torch.stack([torch.nn.functional.elu(mean_nb @ Wg[h].t()) for h in range(H)]).mean(0)
+    y32 = mg.ops.gat_forward(x, rowptr, col, Wg, Ag, concat=False)
+    assert maxabs(y32, ref) <= 2e-5                                            # torch's own GEMM is TF32-free fp32 here
+    xb = x.to(torch.bfloat16)
+    mean_b = xb.float()[ei[0]].view(N, k, Fd).mean(1)
+    refb = torch.stack([torch.nn.functional.elu(mean_b @ Wg[h].t()) for h in range(H)]).mean(0)
+    yb = mg.ops.gat_forward(xb, rowptr, col, Wg, Ag, concat=False, out_dtype=torch.float32)
+    assert maxabs(yb, refb) <= 5e-3
