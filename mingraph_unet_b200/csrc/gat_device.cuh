@@ -31,6 +31,7 @@ struct GatAggArgs {
   float dropout_p;        // attention dropout (graph_attention.py:97); 0 in eval mode
   unsigned long long seed;
   const unsigned long long* seed_dev;   // optional device-side addend (CUDA-graph replays draw fresh masks)
+  int z_bf16;             // gat_aggregate_kernel: spill z as bf16 (operand of the TMA-fed tensor-pipe transform)
 };
 
 // Counter-based Bernoulli mask for attention dropout: a pure function of (seed, in-CSR slot, head), so the

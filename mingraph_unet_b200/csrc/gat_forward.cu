@@ -312,7 +312,7 @@ int gat_scores_and_max(const void* x, int x_dtype, const int32_t* rowptr, const 
   return check_launch("gat_edge_max_kernel");
 }
 
-struct WorkLayout { size_t s_off, gmax_off, u_off, z_off, total; };
+struct WorkLayout { size_t s_off, gmax_off, u_off, wb_off, z_off, total; };
 static WorkLayout work_layout(int N, int in_dim, int out_dim, int heads, int G, bool need_z) {
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   WorkLayout w;
@@ -320,9 +320,9 @@ static WorkLayout work_layout(int N, int in_dim, int out_dim, int heads, int G, 
   w.s_off = o;    o = al(o + (size_t)N * 2 * heads * 4);
   w.gmax_off = o; o = al(o + (size_t)G * heads * 4);
   w.u_off = o;    o = al(o + (size_t)2 * heads * in_dim * 4);
+  w.wb_off = o;   o = al(o + (size_t)gat_transform_tma_wbytes(in_dim, out_dim, heads));     // bf16 copy of W (TMA transform)
   w.z_off = o;    if (need_z) o = al(o + (size_t)N * heads * in_dim * 4);
   w.total = o;
-  (void)out_dim;
   return w;
 }
 
@@ -338,7 +338,7 @@ int64_t mg_gat_work_bytes(int N, int in_dim, int out_dim, int heads, int num_gra
   bool need_z = true;
   if (pick_dims(in_dim, &d))
     need_z = !plan_fused(in_dim, out_dim, heads, d).ok || gat_transform_tc_supported(N, in_dim, out_dim, heads, 1) ||
-             gat_transform_tc_supported(N, in_dim, out_dim, heads, 3);
+             gat_transform_tc_supported(N, in_dim, out_dim, heads, 3) || gat_transform_tma_supported(N, in_dim, out_dim, heads);
   return (int64_t)work_layout(N, in_dim, out_dim, heads, num_graphs > 0 ? num_graphs : 1, need_z).total;
 }
 
@@ -372,9 +372,12 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   // large transforms go to the tensor pipe: aggregate to z, then a tcgen05 GEMM (tf32 for bf16 storage, 3xTF32 for fp32)
   const int tc_passes = x_dtype == MG_BF16 ? 1 : 3;
   const bool tc_gemm = gat_transform_tc_supported(N, in_dim, out_dim, heads, tc_passes);
-  const bool any_tc_gemm = gat_transform_tc_supported(N, in_dim, out_dim, heads, 1) || gat_transform_tc_supported(N, in_dim, out_dim, heads, 3);
+  const bool any_tc_gemm = gat_transform_tc_supported(N, in_dim, out_dim, heads, 1) || gat_transform_tc_supported(N, in_dim, out_dim, heads, 3) ||
+                           gat_transform_tma_supported(N, in_dim, out_dim, heads);
+  // bf16 storage, inference: z spilled as bf16 and transformed by the persistent TMA-fed kernel (gat_tma_gemm.cu)
+  const bool tma_gemm = x_dtype == MG_BF16 && !save_z && gat_transform_tma_supported(N, in_dim, out_dim, heads);
   const WorkLayout wl = work_layout(N, in_dim, out_dim, heads, G, !plan.ok || any_tc_gemm);
-  if (tc_gemm) plan.ok = false;
+  if (tc_gemm || tma_gemm) plan.ok = false;
   unsigned char* wb = reinterpret_cast<unsigned char*>(work);
   float* s = reinterpret_cast<float*>(wb + wl.s_off);
   float* gmax = reinterpret_cast<float*>(wb + wl.gmax_off);
@@ -395,6 +398,7 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   ag.x = x; ag.rowptr = rowptr; ag.col = col; ag.s = s; ag.gmax = gmax;
   ag.N = N; ag.in_dim = in_dim; ag.heads = heads; ag.nodes_per_graph = nodes_per_graph; ag.slope = slope;
   ag.dropout_p = dropout_p; ag.seed = seed; ag.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+  ag.z_bf16 = tma_gemm ? 1 : 0;
 
   if (plan.ok) {
     GatFusedArgs A;
@@ -413,6 +417,8 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   if (x_dtype == MG_F32) rc = gat_launch_agg_f32(ag, NH, d, z, save_den, grid, st);
   else rc = gat_launch_agg_bf16(ag, NH, d, z, save_den, grid, st);
   if (rc) return rc;
+  if (tma_gemm)
+    return gat_transform_tma_launch(z, W, wb + wl.wb_off, N, in_dim, out_dim, heads, concat ? 1 : 0, out, out_dtype == MG_BF16 ? 1 : 0, st);
   if (tc_gemm)
     return gat_transform_tc_launch(z, W, N, in_dim, out_dim, heads, concat ? 1 : 0, out, out_dtype == MG_BF16 ? 1 : 0, tc_passes, st);
   dim3 g2(ceil_div(N, kTM), ceil_div(out_dim, kTN));

@@ -17,6 +17,12 @@ bool gat_transform_tc_supported(int N, int in_dim, int F, int heads, int passes)
 int gat_transform_tc_launch(const float* z, const float* W, int N, int in_dim, int F, int heads, int concat, void* out,
                             int out_bf16, int passes, cudaStream_t st);
 
+// persistent TMA-fed bf16 tensor-pipe transform (gat_tma_gemm.cu): z spilled as bf16, W converted to bf16 into w_bf16
+bool gat_transform_tma_supported(int N, int in_dim, int F, int heads);
+int64_t gat_transform_tma_wbytes(int in_dim, int F, int heads);
+int gat_transform_tma_launch(const void* z_bf16, const float* W, void* w_bf16, int N, int in_dim, int F, int heads, int concat,
+                             void* out, int out_bf16, cudaStream_t st);
+
 // tensor-pipe variant (gat_tc.cu): bf16 node features, transform on tcgen05 (tf32), inference only
 bool gat_tc_supported(int N, int in_dim, int F, int heads, int concat, int out_bf16);
 // (runs its own score / edge-max pre-pass into s (N, 2*heads) and gmax (G, heads))
@@ -219,7 +225,12 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatAggArgs a, 
           const int d = LaneDims<V, T>::dim(lane, t);
           if (d < a.in_dim) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) zout[((size_t)j * a.heads + h) * a.in_dim + d + v] = z[h][t * V + v] / dn;
+            for (int v = 0; v < V; ++v) {
+              const size_t o = ((size_t)j * a.heads + h) * a.in_dim + d + v;
+              const float zn = z[h][t * V + v] / dn;
+              if (a.z_bf16) reinterpret_cast<__nv_bfloat16*>(zout)[o] = __float2bfloat16_rn(zn);
+              else zout[o] = zn;
+            }
           }
         }
         if (save_den && lane == 0) save_den[(size_t)j * a.heads + h] = den[h];
@@ -231,13 +242,11 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatAggArgs a, 
 template <typename TX, int NH, int V, int T>
 static int launch_fused(const GatFusedArgs& A, size_t smem, int grid, cudaStream_t st) {
   auto k = gat_fused_kernel<TX, NH, V, T>;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {          // per launch: function attributes are per device
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess) {
       set_error("gat_fused_kernel: cannot raise dynamic shared memory to %d", (int)kSmemBudget);
       return MG_ERR_CUDA;
     }
-    configured = kSmemBudget;
   }
   k<<<grid, 256, smem, st>>>(A);
   return check_launch("gat_fused_kernel");

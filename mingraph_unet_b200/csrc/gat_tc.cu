@@ -134,6 +134,21 @@ __device__ __forceinline__ float tc_ex2(float x) {
   return y;
 }
 
+// packed fp32x2 FMA (sm_100 FFMA2): d = a * b + d on two fp32 lanes held in one 64-bit register
+__device__ __forceinline__ unsigned long long tc_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+  return r;
+}
+__device__ __forceinline__ void tc_unpack2(unsigned long long v, float& lo, float& hi) {
+  unsigned a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  lo = __uint_as_float(a); hi = __uint_as_float(b);
+}
+__device__ __forceinline__ void tc_fma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
 // ELU for the bf16 path: exp(v) - 1 through the hardware ex2 (abs. error ~1e-7, far inside the 2e-2 budget); the
 // accurate expm1f costs ~30 dependent instructions per element and made the 4 epilogue warps the bottleneck
 __device__ __forceinline__ float tc_elu(float v) {
@@ -466,11 +481,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
 #pragma unroll
           for (int h = 0; h < NH; ++h) Mh[h] = leaky_relu(Mh[h], A.slope);
         }
-        float z[NH][8];
+        unsigned long long z2[NH][4];                          // z[h][2i], z[h][2i+1] packed: accumulated with FFMA2
 #pragma unroll
         for (int h = 0; h < NH; ++h)
 #pragma unroll
-          for (int d = 0; d < 8; ++d) z[h][d] = 0.f;
+          for (int d = 0; d < 4; ++d) z2[h][d] = 0ull;
         const int iters = (end - beg + EPI - 1) / EPI;
         const int max_iters = __reduce_max_sync(kFull, iters);
         for (int itr = 0; itr < max_iters; ++itr) {
@@ -499,19 +514,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
           }
 #pragma unroll
           for (int e = 0; e < EPI; ++e) {
-            float xf[8];
-            xf[0] = __uint_as_float(xv[e].x << 16); xf[1] = __uint_as_float(xv[e].x & 0xffff0000u);
-            xf[2] = __uint_as_float(xv[e].y << 16); xf[3] = __uint_as_float(xv[e].y & 0xffff0000u);
-            xf[4] = __uint_as_float(xv[e].z << 16); xf[5] = __uint_as_float(xv[e].z & 0xffff0000u);
-            xf[6] = __uint_as_float(xv[e].w << 16); xf[7] = __uint_as_float(xv[e].w & 0xffff0000u);
+            unsigned long long xf2[4];                          // bf16 pairs -> fp32 pairs (a shift and a mask per word)
+            xf2[0] = tc_pack2(__uint_as_float(xv[e].x << 16), __uint_as_float(xv[e].x & 0xffff0000u));
+            xf2[1] = tc_pack2(__uint_as_float(xv[e].y << 16), __uint_as_float(xv[e].y & 0xffff0000u));
+            xf2[2] = tc_pack2(__uint_as_float(xv[e].z << 16), __uint_as_float(xv[e].z & 0xffff0000u));
+            xf2[3] = tc_pack2(__uint_as_float(xv[e].w << 16), __uint_as_float(xv[e].w & 0xffff0000u));
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
               const float ph = __shfl_sync(kFull, pv[h], e, LPN);
+              const unsigned long long ph2 = tc_pack2(ph, ph);
 #pragma unroll
-              for (int d = 0; d < 8; ++d) z[h][d] = fmaf(ph, xf[d], z[h][d]);
+              for (int d = 0; d < 4; ++d) tc_fma2(z2[h][d], ph2, xf2[d]);
             }
           }
         }
+        float z[NH][8];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int d = 0; d < 4; ++d) tc_unpack2(z2[h][d], z[h][2 * d], z[h][2 * d + 1]);
         // softmax denominators: sum over the EPI edge-slot lanes (lanes >= EPI hold 0), broadcast from lane 0
         float inv[NH];
 #pragma unroll
@@ -657,13 +678,10 @@ template <int NH, int LPN>
 static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, float* u, size_t smem, int grid,
                      cudaStream_t st) {
   auto k = gat_tc_kernel<NH, LPN>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-      set_error("gat_tc_kernel: cannot raise dynamic shared memory");
-      return MG_ERR_CUDA;
-    }
-    configured = true;
+  // per launch (cheap, and correct when one process drives several devices: function attributes are per device)
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    set_error("gat_tc_kernel: cannot raise dynamic shared memory");
+    return MG_ERR_CUDA;
   }
   const int G = A.nodes_per_graph > 0 ? A.N / A.nodes_per_graph : 1;
   int rc;

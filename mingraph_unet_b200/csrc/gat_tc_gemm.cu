@@ -348,14 +348,10 @@ int gat_transform_tc_launch(const float* z, const float* W, int N, int in_dim, i
     set_error("gat_transform_tc: N=%d too large", N);
     return MG_ERR_UNSUPPORTED;
   }
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gat_transform_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(gat_transform_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-      set_error("gat_transform_tc_kernel: cannot raise dynamic shared memory");
-      return MG_ERR_CUDA;
-    }
-    configured = true;
+  if (cudaFuncSetAttribute(passes == 3 ? (const void*)gat_transform_tc_kernel<3> : (const void*)gat_transform_tc_kernel<1>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    set_error("gat_transform_tc_kernel: cannot raise dynamic shared memory");
+    return MG_ERR_CUDA;
   }
   if (passes == 3) gat_transform_tc_kernel<3><<<grid, kGmThreads, p.smem, st>>>(A);
   else gat_transform_tc_kernel<1><<<grid, kGmThreads, p.smem, st>>>(A);

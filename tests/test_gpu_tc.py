@@ -105,6 +105,8 @@ def test_tc_matches_fp32_pipe_path(mg):
     (8192, 4, 128, 128, False, torch.bfloat16),
     (4096, 4, 512, 512, False, torch.bfloat16),
     (8200, 8, 64, 48, True, torch.bfloat16),
+    (20000, 4, 128, 64, False, torch.bfloat16),        # TMA-fed kernel, 64-column tiles, ragged last row tile
+    (9000, 2, 256, 256, True, torch.bfloat16),         # TMA-fed kernel, concat
 ])
 def test_tc_gemm_transform_vs_oracle(mg, N, heads, fin, fout, concat, dtype):
     gen = torch.Generator().manual_seed(N + heads + fin + fout)
@@ -120,3 +122,17 @@ def test_tc_gemm_transform_vs_oracle(mg, N, heads, fin, fout, concat, dtype):
     torch.cuda.synchronize()
     err = float((y.float().cpu() - ref).abs().max())
     assert err <= (1e-5 if dtype == torch.float32 else TOL_BF16), err
+
+
+def test_tma_gemm_fp32_output_and_error_level(mg):
+    """bf16 features, fp32 output through the TMA-fed transform (z and W rounded to bf16): error level ~1e-3."""
+    N, heads, fin, fout = 8192, 4, 128, 128
+    gen = torch.Generator().manual_seed(77)
+    ei = _random_graph(N, 2, 10, gen)
+    x = torch.randn(N, fin, generator=gen).to(torch.bfloat16)
+    Ws, As = O.init_gat_params(fin, fout, heads, gen)
+    ref = O.gat_layer(x.float(), ei, Ws, As, 0.2, concat=False)
+    rowptr, col, _ = mg.ops.csr_from_coo(ei.cuda(), N, by_target=True)
+    y = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), concat=False, out_dtype=torch.float32)
+    err = float((y.cpu() - ref).abs().max())
+    assert err <= 8e-3, err
