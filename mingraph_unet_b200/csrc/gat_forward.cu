@@ -31,9 +31,35 @@ __device__ __forceinline__ void compute_u(const float* __restrict__ W, const flo
   }
 }
 
-__global__ void gat_u_kernel(const float* __restrict__ W, const float* __restrict__ a, int in_dim, int F, int heads,
-                             float* __restrict__ u) {
-  compute_u(W, a, in_dim, F, heads, u, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+// block = (head, 32 input columns); thread = (f-partition of 8, column): every thread's loads are independent and
+// coalesced along the input dimension, the 8 partial sums are combined in a fixed order through shared memory
+__global__ void __launch_bounds__(256) gat_u_kernel(const float* __restrict__ W, const float* __restrict__ a, int in_dim, int F,
+                                                    int heads, float* __restrict__ u) {
+  __shared__ float part[8][2][32];
+  const int h = blockIdx.y, i0 = blockIdx.x * 32;
+  const int il = threadIdx.x & 31, fp = threadIdx.x >> 5;
+  const int i = i0 + il;
+  float acc0 = 0.f, acc1 = 0.f;
+  if (i < in_dim) {
+    const float* Wh = W + (size_t)h * F * in_dim + i;
+    const float* ah = a + (size_t)h * 2 * F;
+#pragma unroll 8
+    for (int f = fp; f < F; f += 8) {
+      const float w = __ldg(Wh + (size_t)f * in_dim);
+      acc0 = fmaf(__ldg(ah + f), w, acc0);
+      acc1 = fmaf(__ldg(ah + F + f), w, acc1);
+    }
+  }
+  part[fp][0][il] = acc0;
+  part[fp][1][il] = acc1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int half = threadIdx.x >> 5, c = threadIdx.x & 31;
+    float v = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) v += part[p][half][c];
+    if (i0 + c < in_dim) u[(size_t)(half * heads + h) * in_dim + i0 + c] = v;
+  }
 }
 
 // warp per node; u in shared memory; also resets gmax (consumed by the next kernel on the stream).
@@ -91,8 +117,20 @@ __global__ void __launch_bounds__(256) gat_scores_kernel(const TX* __restrict__ 
         for (int t = 0; t < T; ++t) {
           const int d = LaneDims<V, T>::dim(lane, t);
           if (d < in_dim) {
+            if (V == 4) {
+              const float4 u4 = *reinterpret_cast<const float4*>(u_s + q * in_dim + d);
+              acc = fmaf(xv[t * V], u4.x, acc);
+              acc = fmaf(xv[t * V + 1], u4.y, acc);
+              acc = fmaf(xv[t * V + 2], u4.z, acc);
+              acc = fmaf(xv[t * V + 3], u4.w, acc);
+            } else if (V == 2) {
+              const float2 u2 = *reinterpret_cast<const float2*>(u_s + q * in_dim + d);
+              acc = fmaf(xv[t * V], u2.x, acc);
+              acc = fmaf(xv[t * V + 1], u2.y, acc);
+            } else {
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc = fmaf(xv[t * V + v], u_s[q * in_dim + d + v], acc);
+              for (int v = 0; v < V; ++v) acc = fmaf(xv[t * V + v], u_s[q * in_dim + d + v], acc);
+            }
           }
         }
       }
@@ -299,7 +337,7 @@ int gat_scores_and_max(const void* x, int x_dtype, const int32_t* rowptr, const 
   // attention vectors: recomputed per block when cheap, otherwise one small kernel
   const float* u_global = nullptr;
   if ((int64_t)in_dim * out_dim * heads > 32768 || u != nullptr) {
-    gat_u_kernel<<<ceil_div(2 * heads * in_dim, 128), 128, 0, st>>>(W, a, in_dim, out_dim, heads, u);
+    gat_u_kernel<<<dim3(ceil_div(in_dim, 32), heads), 256, 0, st>>>(W, a, in_dim, out_dim, heads, u);
     if ((rc = check_launch("gat_u_kernel"))) return rc;
     u_global = u;
   }

@@ -225,11 +225,27 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatAggArgs a, 
           const int d = LaneDims<V, T>::dim(lane, t);
           if (d < a.in_dim) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const size_t o = ((size_t)j * a.heads + h) * a.in_dim + d + v;
-              const float zn = z[h][t * V + v] / dn;
-              if (a.z_bf16) reinterpret_cast<__nv_bfloat16*>(zout)[o] = __float2bfloat16_rn(zn);
-              else zout[o] = zn;
+            const size_t o = ((size_t)j * a.heads + h) * a.in_dim + d;
+            float zn[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) zn[v] = z[h][t * V + v] / dn;
+            if (a.z_bf16) {
+              __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(zout) + o;
+              if (V == 4) {                         // one 8-byte store per lane: 256 contiguous bytes per warp
+                __nv_bfloat162 lo = __floats2bfloat162_rn(zn[0], zn[1]), hi = __floats2bfloat162_rn(zn[2 % V], zn[3 % V]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
+                *reinterpret_cast<uint2*>(zb) = pk;
+              } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) zb[v] = __float2bfloat16_rn(zn[v]);
+              }
+            } else if (V == 4) {
+              *reinterpret_cast<float4*>(zout + o) = make_float4(zn[0], zn[1 % V], zn[2 % V], zn[3 % V]);
+            } else if (V == 2) {
+              *reinterpret_cast<float2*>(zout + o) = make_float2(zn[0], zn[1 % V]);
+            } else {
+              zout[o] = zn[0];
             }
           }
         }
