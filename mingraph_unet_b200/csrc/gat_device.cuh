@@ -32,6 +32,7 @@ struct GatAggArgs {
   unsigned long long seed;
   const unsigned long long* seed_dev;   // optional device-side addend (CUDA-graph replays draw fresh masks)
   int z_bf16;             // gat_aggregate_kernel: spill z as bf16 (operand of the TMA-fed tensor-pipe transform)
+  int dim_parts;          // gat_aggregate_kernel: warps per destination, each owning 32*V*T consecutive input dims
 };
 
 // Counter-based Bernoulli mask for attention dropout: a pure function of (seed, in-CSR slot, head), so the
@@ -56,7 +57,7 @@ struct WarpScratch {
 //   returns den[h] in den_out[h] (identical on every lane)
 template <typename TX, int NH, int V, int T>
 __device__ __forceinline__ void gat_aggregate_node(const GatAggArgs& a, int j, int lane, WarpScratch* sc,
-                                                   float (&z)[NH][V * T], float (&den_out)[NH]) {
+                                                   float (&z)[NH][V * T], float (&den_out)[NH], int dim0 = 0) {
   constexpr int EPC = 32 / NH;                      // edges per chunk (one (edge,head) pair per lane)
   constexpr int U = (V * T >= 8) ? 2 : ((V * T >= 4) ? 4 : 8);   // edges whose rows are in flight together
   static_assert(EPC % U == 0 || U > EPC, "chunk/unroll mismatch");
@@ -79,7 +80,7 @@ __device__ __forceinline__ void gat_aggregate_node(const GatAggArgs& a, int j, i
   float den_lane = 0.f;
   bool dim_ok[T];
 #pragma unroll
-  for (int t = 0; t < T; ++t) dim_ok[t] = LaneDims<V, T>::dim(lane, t) < a.in_dim;
+  for (int t = 0; t < T; ++t) dim_ok[t] = dim0 + LaneDims<V, T>::dim(lane, t) < a.in_dim;
 
   for (int c = beg; c < end; c += EPC) {
     const int k = c + el;
@@ -114,7 +115,7 @@ __device__ __forceinline__ void gat_aggregate_node(const GatAggArgs& a, int j, i
 #pragma unroll
           for (int t = 0; t < T; ++t) {
             if (ok[u] && dim_ok[t]) {
-              VecLoad<TX, V>::ld(row + LaneDims<V, T>::dim(lane, t), &xv[u][t * V]);
+              VecLoad<TX, V>::ld(row + dim0 + LaneDims<V, T>::dim(lane, t), &xv[u][t * V]);
             } else {
 #pragma unroll
               for (int v = 0; v < V; ++v) xv[u][t * V + v] = 0.f;

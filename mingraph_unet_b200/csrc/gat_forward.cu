@@ -437,6 +437,7 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   ag.N = N; ag.in_dim = in_dim; ag.heads = heads; ag.nodes_per_graph = nodes_per_graph; ag.slope = slope;
   ag.dropout_p = dropout_p; ag.seed = seed; ag.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   ag.z_bf16 = tma_gemm ? 1 : 0;
+  ag.dim_parts = 1;
 
   if (plan.ok) {
     GatFusedArgs A;
@@ -451,9 +452,12 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   }
   // unfused: z -> global (also serves as save_z when the caller wants it)
   float* z = save_z ? save_z : reinterpret_cast<float*>(wb + wl.z_off);
-  const int grid = (int)std::min<int64_t>(ceil_div64((int64_t)N * 32, 256), (int64_t)num_sms() * 8);
-  if (x_dtype == MG_F32) rc = gat_launch_agg_f32(ag, NH, d, z, save_den, grid, st);
-  else rc = gat_launch_agg_bf16(ag, NH, d, z, save_den, grid, st);
+  // wide rows: one warp per 128 input dims of a destination (16 accumulators per lane, 4 source rows in flight per warp)
+  DimCfg dagg = d;
+  if (in_dim > 128 && in_dim % 128 == 0) { dagg = DimCfg{4, 1}; ag.dim_parts = in_dim / 128; }
+  const int grid = (int)std::min<int64_t>(ceil_div64((int64_t)N * ag.dim_parts * 32, 256), (int64_t)num_sms() * 16);
+  if (x_dtype == MG_F32) rc = gat_launch_agg_f32(ag, NH, dagg, z, save_den, grid, st);
+  else rc = gat_launch_agg_bf16(ag, NH, dagg, z, save_den, grid, st);
   if (rc) return rc;
   if (tma_gemm)
     return gat_transform_tma_launch(z, W, wb + wl.wb_off, N, in_dim, out_dim, heads, concat ? 1 : 0, out, out_dtype == MG_BF16 ? 1 : 0, st);

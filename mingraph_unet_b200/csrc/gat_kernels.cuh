@@ -213,18 +213,21 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatAggArgs a, 
   __shared__ WarpScratch scratch[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (int j = wg; j < a.N; j += nw) {
+  const int parts = a.dim_parts > 0 ? a.dim_parts : 1;
+  const int64_t ntasks = (int64_t)a.N * parts;
+  for (int64_t task = wg; task < ntasks; task += nw) {
+    const int j = (int)(task / parts), part = (int)(task - (int64_t)j * parts);
+    const int dim0 = part * 32 * V * T;              // wide rows: several warps per destination, 32*V*T dims each
     float z[NH][V * T], den[NH];
-    gat_aggregate_node<TX, NH, V, T>(a, j, lane, scratch + warp, z, den);
+    gat_aggregate_node<TX, NH, V, T>(a, j, lane, scratch + warp, z, den, dim0);
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
       if (h < a.heads) {
         const float dn = den[h] + 1e-10f;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-          const int d = LaneDims<V, T>::dim(lane, t);
+          const int d = dim0 + LaneDims<V, T>::dim(lane, t);
           if (d < a.in_dim) {
-#pragma unroll
             const size_t o = ((size_t)j * a.heads + h) * a.in_dim + d;
             float zn[V];
 #pragma unroll
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatAggArgs a, 
             }
           }
         }
-        if (save_den && lane == 0) save_den[(size_t)j * a.heads + h] = den[h];
+        if (save_den && lane == 0 && part == 0) save_den[(size_t)j * a.heads + h] = den[h];
       }
     }
   }
