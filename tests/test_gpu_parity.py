@@ -565,3 +565,34 @@ def test_full_size_gat_linearity_in_values(mg):
     refb = torch.stack([torch.nn.functional.elu(mean_b @ Wg[h].t()) for h in range(H)]).mean(0)
     yb = mg.ops.gat_forward(xb, rowptr, col, Wg, Ag, concat=False, out_dtype=torch.float32)
     assert maxabs(yb, refb) <= 5e-3
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_block_on_bottleneck_features_in512(mg, dtype, tol):
+    """Row f2: node features = the U-Net bottleneck (512 channels at stride 16 = one pixel per patch,
+    configs/model.yaml patch_size 16 == 2**depth).  in = 512 takes the composed kernels (aggregation + transform; bf16:
+    TMA-fed tensor-pipe GEMM), checked per image against the oracle."""
+    B, C, H, W, K, D = 4, 512, 512, 512, 2, 64
+    gen = torch.Generator().manual_seed(42)
+    bott = (0.25 * torch.randn(B, C, H // 16, W // 16, generator=gen)).to(dtype)
+    P = O.init_block_params(C, D, 4, K, seed=7)
+    blk = mg.GraphBlock(node_feature_dim=C, num_segments=K)
+    for name, net in (("patch", blk.patch_gat_model), ("pred", blk.segment_predictor.gnn_predictor),
+                      ("region", blk.region_gat_model)):
+        load_heads(net, P[f"{name}_W"], P[f"{name}_a"])
+    blk = blk.cuda().eval()
+    with torch.no_grad():
+        out = blk(feature_map=bott.cuda(), image_size=(H, W), out_dtype=torch.float32, want_dense=False)
+    assert out.grid == (32, 32)
+    worst = 0.0
+    for b in range(B):
+        x = bott[b].float().reshape(C, -1).t().contiguous()                 # (N, 512): pooling window 1x1 = transpose
+        ref = O.graph_block_image(x, H, W, P, K=K, want_dense=False)
+        worst = max(worst, maxabs(out.patch_features[b], ref["h"]))
+        if torch.equal(out.hard_labels[b].cpu().long(), ref["hard"]):
+            worst = max(worst, maxabs(out.region_features[b], ref["region_out"]))
+        else:
+            # bf16 rounding may flip an argmax whose two probabilities are (almost) equal: only there
+            flips = out.hard_labels[b].cpu().long() != ref["hard"]
+            assert dtype == torch.bfloat16 and float((ref["S"][flips, 0] - 0.5).abs().max()) < 5e-2
+    assert worst <= tol, worst
