@@ -452,9 +452,11 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   }
   // unfused: z -> global (also serves as save_z when the caller wants it)
   float* z = save_z ? save_z : reinterpret_cast<float*>(wb + wl.z_off);
-  // wide rows: one warp per 128 input dims of a destination (16 accumulators per lane, 4 source rows in flight per warp)
+  // wide rows: one warp per 256 input dims of a destination.  Measured at in = 512, N = 262 144, k = 8 (ncu): one warp per
+  // row (T=4) is latency-bound (1.2 ms), one warp per 128 dims is issue-bound (842 M warp instructions: every part
+  // recomputes the attention numerators); 256 dims per warp sits between the two.
   DimCfg dagg = d;
-  if (in_dim > 128 && in_dim % 128 == 0) { dagg = DimCfg{4, 1}; ag.dim_parts = in_dim / 128; }
+  if (in_dim > 256 && in_dim % 256 == 0) { dagg = DimCfg{4, 2}; ag.dim_parts = in_dim / 256; }
   const int grid = (int)std::min<int64_t>(ceil_div64((int64_t)N * ag.dim_parts * 32, 256), (int64_t)num_sms() * 16);
   if (x_dtype == MG_F32) rc = gat_launch_agg_f32(ag, NH, dagg, z, save_den, grid, st);
   else rc = gat_launch_agg_bf16(ag, NH, dagg, z, save_den, grid, st);
