@@ -60,7 +60,7 @@ class GraphBlock(nn.Module):
 
     def forward(self, node_features: Optional[torch.Tensor] = None, image_size: Optional[Tuple[int, int]] = None,
                 feature_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                out_dtype: Optional[torch.dtype] = None, want_dense: bool = True) -> GraphBlockOutput:
+                out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, _block_outs=None) -> GraphBlockOutput:
         """Either ``node_features (B,N,in)`` + ``image_size (H,W)`` or a per-pixel ``feature_map
         (B,in,H,W)`` (patch-mean pooled to node features).  ``out`` may be a channel slice of a fusion
         buffer ``(B,Ctot,H,W)[:, c0:c0+D]``; the dense map is written there directly."""
@@ -106,7 +106,7 @@ class GraphBlock(nn.Module):
             # ONE launch: patch GAT -> predictor GAT -> softmax/argmax -> N-cut -> region pool -> region GAT
             h, S, labels, loss, _, G = ops.block_forward(
                 node_features, nph, npw, self._prepared(), D, layers[0].num_heads, layers[1].num_heads,
-                layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers))
+                layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers), outs=_block_outs)
         elif needs_autograd or (self.training and any(l.dropout_rate > 0 for l in layers)):
             # training: the same stages as differentiable ops (csrc/gat_backward.cu, ncut.cu, block_backward.cu)
             g = Graph.grid(nph, npw, dev, B)

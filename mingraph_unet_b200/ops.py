@@ -410,7 +410,7 @@ def block_prepare(W1, a1, W2, a2, W3, a3, out: Optional[torch.Tensor] = None) ->
 
 
 def block_forward(x: torch.Tensor, Hp: int, Wp: int, prep: torch.Tensor, D: int, H1: int, H2: int, H3: int, K: int,
-                  slopes=(0.2, 0.2, 0.2), want_region_in: bool = False):
+                  slopes=(0.2, 0.2, 0.2), want_region_in: bool = False, outs=None):
     """One launch for the whole per-image pipeline.  ``x (B,N,in)`` f32|bf16.  Returns
     ``h (B,N,D), S (B,N,K), labels (B,N) int32, loss (B,), region_in|None, region_out (B,K,D)``."""
     _need_cuda(x, prep)
@@ -418,13 +418,21 @@ def block_forward(x: torch.Tensor, Hp: int, Wp: int, prep: torch.Tensor, D: int,
     B, N, in_dim = x.shape
     dev = x.device
     f32 = dict(dtype=torch.float32, device=dev)
-    h = torch.empty((B, N, D), **f32)
+    if outs is not None:
+        # caller-owned (contiguous, fp32 / int32) output buffers, e.g. batch slices shared by several shards
+        h, S, labels, loss, rout = outs
+        if tuple(h.shape) != (B, N, D) or tuple(S.shape) != (B, N, K) or tuple(labels.shape) != (B, N) or \
+                tuple(loss.shape) != (B,) or tuple(rout.shape) != (B, K, D) or \
+                not all(t.is_contiguous() for t in outs) or labels.dtype != torch.int32:
+            raise ValueError("block_forward: bad output buffers")
+    else:
+        h = torch.empty((B, N, D), **f32)
+        S = torch.empty((B, N, K), **f32)
+        labels = torch.empty((B, N), dtype=torch.int32, device=dev)
+        loss = torch.empty(B, **f32)
+        rout = torch.empty((B, K, D), **f32)
     q = torch.empty((B, N, 2 * H2 + H2 * K), **f32)
-    S = torch.empty((B, N, K), **f32)
-    labels = torch.empty((B, N), dtype=torch.int32, device=dev)
-    loss = torch.empty(B, **f32)
     rin = torch.empty((B, K, D), **f32) if want_region_in else None
-    rout = torch.empty((B, K, D), **f32)
     with torch.cuda.device(dev):
         call("mg_block_forward", x.data_ptr(), _dtype_code(x.dtype), B, Hp, Wp, in_dim, D, H1, H2, H3, K,
              float(slopes[0]), float(slopes[1]), float(slopes[2]), prep.data_ptr(), h.data_ptr(), q.data_ptr(),

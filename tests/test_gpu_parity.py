@@ -596,3 +596,24 @@ def test_block_on_bottleneck_features_in512(mg, dtype, tol):
             flips = out.hard_labels[b].cpu().long() != ref["hard"]
             assert dtype == torch.bfloat16 and float((ref["S"][flips, 0] - 0.5).abs().max()) < 5e-2
     assert worst <= tol, worst
+
+
+def test_captured_graph_block_shards_match_single(mg):
+    """CapturedGraphBlock with parallel shard branches writes the same full-batch outputs as the single-branch graph."""
+    B, C, H, W, D = 6, 20, 128, 96, 64
+    gen = torch.Generator().manual_seed(12)
+    fm = torch.randn(B, C, H, W, generator=gen).cuda()
+    blk = mg.GraphBlock(node_feature_dim=C, num_segments=2).cuda().eval()
+    buf1 = torch.zeros(B, 32 + D, H, W, device="cuda")
+    buf2 = torch.zeros(B, 32 + D, H, W, device="cuda")
+    r1 = mg.CapturedGraphBlock(blk, fm, image_size=(H, W), out=buf1[:, 32:])
+    r2 = mg.CapturedGraphBlock(blk, fm, image_size=(H, W), out=buf2[:, 32:], shards=4)      # 6 images over 4 shards: 2,2,1,1
+    assert r2.shards == 4
+    fm2 = torch.randn(B, C, H, W, generator=gen).cuda()
+    for x in (None, fm2):
+        a, b = r1(x), r2(x)
+        torch.cuda.synchronize()
+        assert torch.equal(a.hard_labels, b.hard_labels) and torch.equal(a.l_partition, b.l_partition)
+        assert torch.equal(a.patch_features, b.patch_features) and torch.equal(a.region_features, b.region_features)
+        assert torch.equal(a.soft_assignments, b.soft_assignments)
+        assert torch.equal(buf1, buf2) and float(buf1[:, :32].abs().max()) == 0.0
