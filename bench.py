@@ -292,17 +292,20 @@ def run_ours(args):
         e.record()
         return e
 
+    # launch shape = what the graph launches: one shard (B / shards images) per kernel
+    Bs = runner._ranges[0][1] if runner.shards > 1 else B
+    fm_shard, out_shard = fm_dev[:Bs], f_g_slice[:Bs]
     with torch.no_grad():
         prep = blk._prepared()
         for i in range(args.steps + 3):
             torch.cuda._sleep(400_000)      # ~0.2 ms spin so the host runs ahead and the three launches queue back to back
             e0 = ev()
-            x = mg.ops.pool_patches(fm_dev, PATCH, PATCH)
+            x = mg.ops.pool_patches(fm_shard, PATCH, PATCH)
             e1 = ev()
             hh, SS, ll, lo, _, GG = mg.ops.block_forward(x, nph, npw, prep, D_OUT, layers[0].num_heads, layers[1].num_heads,
                                                          layers[2].num_heads, K_SEG)
             e2 = ev()
-            mg.ops.unpool_nearest(GG, ll, nph, npw, H, W, out=f_g_slice)
+            mg.ops.unpool_nearest(GG, ll, nph, npw, H, W, out=out_shard)
             e3 = ev()
             if i >= 3:
                 kern_ev["pool"].append((e0, e1)); kern_ev["block"].append((e1, e2)); kern_ev["unpool"].append((e2, e3))
@@ -340,13 +343,14 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         b = 2 if dtype == torch.bfloat16 else 4
-        unpool_bytes = B * (D_OUT * H * W * b + 4 * N + K_SEG * D_OUT * 4)
-        pool_bytes = B * (IN_DIM * H * W * b + N * IN_DIM * b)
+        unpool_bytes = Bs * (D_OUT * H * W * b + 4 * N + K_SEG * D_OUT * 4)          # per launch (one shard)
+        pool_bytes = Bs * (IN_DIM * H * W * b + N * IN_DIM * b)
+        step_bytes = (unpool_bytes + pool_bytes) * B // Bs
         achieved = unpool_bytes / (unpool_ms * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("unpool_dram_bytes_per_launch")
+                traffic = json.load(f).get(args.workload, {}).get("unpool_dram_bytes_per_launch_shards%d" % runner.shards)
         except Exception:
             pass
         ms_step = ms_total / args.steps
@@ -356,14 +360,15 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if dtype == torch.float32 else "bf16 storage / f32 math", "data": "synthetic", "config": cfg,
             "edges_per_s": B * world * E * args.steps / (ms_total * 1e-3),
-            "step_hbm_gbs": (unpool_bytes + pool_bytes) / (ms_step * 1e-3) / 1e9,
+            "step_hbm_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
             "gpu_launches": int(launches), "launch_mode": "CUDA graph replay (%d kernels of libmingraph_b200.so per step, %d parallel shard branches)" % (per_step_kernels, runner.shards),
             "roofline": {"kernel": "unpool_vec_kernel (K7 nearest un-pool)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": unpool_bytes,
                          "kernel_ms": unpool_ms, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "timing": "CUDA events around each eager launch of the same K steps (graph replays cannot "
-                                   "carry timing events)",
+                         "images_per_launch": Bs,
+                         "timing": "CUDA events around eager launches of the same kernels with the graph's launch shape "
+                                   "(one shard of %d images; graph replays cannot carry timing events)" % Bs,
                          "other_kernels": {
                              "pool_patches_vec_kernel": {"ms": kern_ms["pool"], "algorithmic_bytes": pool_bytes,
                                                          "achieved_gbs": pool_bytes / (kern_ms["pool"] * 1e-3) / 1e9,

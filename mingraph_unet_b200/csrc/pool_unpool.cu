@@ -34,7 +34,13 @@ struct Vec16<__nv_bfloat16> {
   }
 };
 
-constexpr int kPoolCC = 32;   // max channels per block
+// channels per block = warps per block, one channel strip per warp.  Measured at cfg 2 (B200, two shard branches):
+// 32 / 16 / 8 / 4 / 2 channels per block -> 169.2 / 168.5 / 171.2 / 164.4 / 163.9 us per step: many short blocks ramp the
+// HBM pipeline faster than few long ones.
+static int pool_cc() {
+  static const int v = getenv("MG_POOL_CC") ? atoi(getenv("MG_POOL_CC")) : 4;
+  return v < 1 ? 1 : (v > 32 ? 32 : v);
+}
 constexpr int kPoolRows = 16; // rows whose 16-byte loads are issued together
 
 // fast path: pw % VEC == 0, Wf % VEC == 0, lpp = pw/VEC a power of two <= 32.
@@ -381,7 +387,7 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
     return check_launch("pool_patches_strip_kernel");
   }
   if (fast) {
-    const int cg = std::min(C, kPoolCC);
+    const int cg = std::min(C, pool_cc());
     // warps per block: the count in 4..8 that wastes the fewest channel slots (ties -> more warps)
     int nw = std::min(cg, 8), best_waste = 1 << 30;
     for (int w = std::min(cg, 8); w >= std::min(cg, 4); --w) {
