@@ -851,12 +851,55 @@ static bool shape_supported(const BlockShape& s, const char** why) {
   return *why == nullptr;
 }
 
+template <typename TX>
+__global__ void block_forward_kernel(const BlockArgs A);
+
+// How many clusters of `c` CTAs (kBT threads, `smem` bytes each) the device keeps resident at once.  A cluster needs its
+// CTAs inside one GPC, so this is NOT num_sms / c: on B200 only 15 clusters of 8 fit (measured: the kernel takes 38.9 us
+// for 1..15 images and 67.6 us for 16, a second wave).  Cached per (cluster size, smem size class).
+static int max_active_clusters(int c, size_t smem) {
+  static int cache[9][8];
+  static bool have[9][8];
+  const int sc = (int)std::min<size_t>(7, smem / (32 * 1024));
+  if (have[c][sc]) return cache[c][sc];
+  auto kern = block_forward_kernel<float>;
+  int n = 0;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(c * 64), 1, 1);
+  cfg.blockDim = dim3(kBT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)c;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = num_sms() / c;                  // no device / query failed: optimistic estimate
+  }
+  cache[c][sc] = n;
+  have[c][sc] = true;
+  return n;
+}
+
 static int plan_cluster(BlockShape* s) {
   // smallest cluster (power of two <= 8) with <= 256 nodes per CTA, else 8
   int c = 1;
   while (c < kMaxCluster && ceil_div(s->N, c) > 256) c <<= 1;
   // prefer filling the machine when the batch is small
   while (c < kMaxCluster && s->B * c * 2 <= num_sms() && ceil_div(s->N, c * 2) >= 64) c <<= 1;
+  // ... but never at the price of a second wave: all B clusters must be resident together
+  const int c_min = c;
+  (void)c_min;
+  while (c > 1 && ceil_div(s->N, c / 2) <= 256) {
+    BlockShape t = *s;
+    t.cluster = c; t.npc = ceil_div(s->N, c);
+    if (s->B <= max_active_clusters(c, (size_t)smem_layout(t).total * 4)) break;
+    c >>= 1;
+  }
   s->cluster = c;
   s->npc = ceil_div(s->N, c);
   return c;

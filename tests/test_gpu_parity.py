@@ -502,8 +502,8 @@ def test_knn_errors(mg):
 def test_full_size_block_properties(mg, B, H, W, dtype):
     """cfg 2 (512^2, batch 16, bf16) and a cfg-3 shard (1024^2): (i) the one-launch cluster kernel and the composed
     stand-alone kernels agree (labels bit-exact); (ii) the dense map IS region_out gathered by label and nearest
-    up-sampled (bit-exact vs torch); (iii) an image computed alone equals the same image inside the batch (bit-exact:
-    graphs are independent, the softmax shift is per image); (iv) pooling the dense map back returns the per-patch
+    up-sampled (bit-exact vs torch); (iii) an image computed alone equals the same image inside the batch (labels and
+    patch features bit-exact: graphs are independent, the softmax shift is per image); (iv) pooling the dense map back returns the per-patch
     rows (un-pool -> pool round trip)."""
     import torch.nn.functional as F
     C, K, D = 20, 2, 64
@@ -535,8 +535,11 @@ def test_full_size_block_properties(mg, B, H, W, dtype):
     assert torch.equal(a.f_g, want)
     # (iii)
     assert torch.equal(one.hard_labels[0], a.hard_labels[1])
-    assert torch.equal(one.patch_features[0], a.patch_features[1]) and torch.equal(one.region_features[0], a.region_features[1])
-    assert torch.equal(one.f_g[0], a.f_g[1])
+    assert torch.equal(one.patch_features[0], a.patch_features[1])
+    # the per-image reductions (region means, N-cut sums) are split over a cluster whose size depends on the batch
+    # (all clusters must be co-resident: 8 CTAs per image up to 15 images, 4 beyond), so their rounding may differ
+    assert maxabs(one.region_features[0], a.region_features[1]) <= 1e-6
+    assert maxabs(one.f_g[0], a.f_g[1]) <= 1e-6
     # (iv)
     back = mg.ops.pool_patches(a.f_g, 16, 16)
     assert maxabs(back, per_patch) <= 1e-6 * max(1.0, float(per_patch.abs().max()))
