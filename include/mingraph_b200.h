@@ -43,6 +43,8 @@ extern "C" {
 
 #define MG_F32 0
 #define MG_BF16 1
+#define MG_I32 2                  /* label arrays only (mg_feature_consistency_loss) */
+#define MG_I64 3
 
 typedef void* mg_stream_t;        /* cudaStream_t */
 
@@ -208,6 +210,34 @@ MG_API int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, i
                             int K, float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work,
                             float* S, int32_t* labels, float* loss, float* region_in, float* region_out,
                             mg_stream_t stream);
+
+/* ---- losses on tensors the block already holds (scope row f4) -----------------------------------
+ * FeatureConsistencyLoss.forward — model/unet/feature_loss.py:103-123, called per image at
+ * scripts/train_end_to_end.py:344 with the patch-GAT output as f_graph:
+ *   dist_sq = sum_d (f_unet - f_graph)^2 ; dist = sqrt(dist_sq + 1e-8)
+ *   loss    = mean_b sum_n [ y*dist_sq + (1-y)*max(0, margin - dist)^2 ]
+ * f_unet, f_graph (B,N,D) f32|bf16; y (B,N) of dtype MG_F32 | MG_BF16 | MG_I32 | MG_I64 (the reference
+ * calls .float() on it).  work: mg_feature_loss_work_bytes(B,N) bytes.  per_image (B, nullable)
+ * receives the per-image sums, loss (1) their mean.  Deterministic (fixed-order reductions). */
+MG_API int64_t mg_feature_loss_work_bytes(int B, int N);
+MG_API int mg_feature_consistency_loss(const void* f_unet, int fu_dtype, const void* f_graph, int fg_dtype, const void* y,
+                                       int y_dtype, int B, int N, int D, float margin, void* work, float* per_image,
+                                       float* loss, mg_stream_t stream);
+/* grad_f_unet = grad_loss/B * (2y - (1-y)*2*hinge/dist) * (f_unet - f_graph); grad_f_graph = -grad_f_unet
+ * (either may be NULL); grad_loss is a DEVICE scalar. */
+MG_API int mg_feature_consistency_loss_backward(const void* f_unet, int fu_dtype, const void* f_graph, int fg_dtype,
+                                                const void* y, int y_dtype, int B, int N, int D, float margin,
+                                                const float* grad_loss, float* grad_f_unet, float* grad_f_graph,
+                                                mg_stream_t stream);
+/* TVLoss.forward — scripts/train_end_to_end.py:73-89:
+ *   weight * ( sum (x[:,:,1:,:]-x[:,:,:-1,:])^2 / ((H-1)*W) + sum (x[:,:,:,1:]-x[:,:,:,:-1])^2 / (H*(W-1)) ) / B
+ * x (B,C,H,W) f32|bf16, read once.  out3 (3 floats): {loss, h_tv, w_tv}.  H == 1 or W == 1 gives NaN like
+ * the reference (0/0).  work: mg_tv_loss_work_bytes() bytes. */
+MG_API int64_t mg_tv_loss_work_bytes(int dtype, int B, int C, int H, int W);
+MG_API int mg_tv_loss(const void* x, int dtype, int B, int C, int H, int W, float weight, void* work, float* out3,
+                      mg_stream_t stream);
+MG_API int mg_tv_loss_backward(const void* x, int dtype, int B, int C, int H, int W, float weight, const float* grad_loss,
+                               float* grad_x, mg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MINGRAPH_B200_LIB", os.path.join(_HERE, "lib", "libmingraph_b200.so"))
 HEADER_PATH = os.path.abspath(os.path.join(_HERE, "..", "include", "mingraph_b200.h"))
 
-MG_F32, MG_BF16 = 0, 1
+MG_F32, MG_BF16, MG_I32, MG_I64 = 0, 1, 2, 3
 MG_OK, MG_ERR_INVALID, MG_ERR_CUDA, MG_ERR_UNSUPPORTED = 0, -1, -2, -3
 
 
@@ -66,6 +66,12 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_block_supported": (_i, [_i] * 9),
     "mg_block_prepare": (_i, [_p] * 6 + [_i] * 6 + [_p, _p]),
     "mg_block_forward": (_i, [_p] + [_i] * 10 + [_f] * 3 + [_p] * 9),
+    "mg_feature_loss_work_bytes": (_i64, [_i, _i]),
+    "mg_feature_consistency_loss": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "mg_feature_consistency_loss_backward": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "mg_tv_loss_work_bytes": (_i64, [_i] * 5),
+    "mg_tv_loss": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
+    "mg_tv_loss_backward": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
 }
 
 _lib = None

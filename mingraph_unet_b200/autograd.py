@@ -170,3 +170,47 @@ def ncut_loss_apply(h: torch.Tensor, S: torch.Tensor, g: Graph) -> torch.Tensor:
     if _wants_grad(h, S):
         return _NcutFn.apply(h.contiguous(), S.contiguous(), g)
     return ops.ncut_loss(h, S, g.rowptr_out, g.col_out, g.nodes_per_graph)
+
+
+class _FeatureLossFn(torch.autograd.Function):
+    """FeatureConsistencyLoss (model/unet/feature_loss.py:103-123); labels are data, not differentiated."""
+
+    @staticmethod
+    def forward(ctx, f_unet, f_graph, y, margin: float):
+        ctx.save_for_backward(f_unet, f_graph, y)
+        ctx.margin = margin
+        return ops.feature_consistency_loss(f_unet, f_graph, y, margin)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        f_unet, f_graph, y = ctx.saved_tensors
+        gu, gg = ops.feature_consistency_loss_backward(f_unet, f_graph, y, ctx.margin, grad_loss,
+                                                       ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return (None if gu is None else gu.to(f_unet.dtype)), (None if gg is None else gg.to(f_graph.dtype)), None, None
+
+
+def feature_loss_apply(f_unet: torch.Tensor, f_graph: torch.Tensor, y: torch.Tensor, margin: float) -> torch.Tensor:
+    if _wants_grad(f_unet, f_graph):
+        return _FeatureLossFn.apply(f_unet, f_graph, y, margin)
+    return ops.feature_consistency_loss(f_unet, f_graph, y, margin)
+
+
+class _TVLossFn(torch.autograd.Function):
+    """TVLoss (scripts/train_end_to_end.py:73-89)."""
+
+    @staticmethod
+    def forward(ctx, x, weight: float):
+        ctx.save_for_backward(x)
+        ctx.weight = weight
+        return ops.tv_loss(x, weight).clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (x,) = ctx.saved_tensors
+        return ops.tv_loss_backward(x, ctx.weight, grad_loss).to(x.dtype), None
+
+
+def tv_loss_apply(x: torch.Tensor, weight: float) -> torch.Tensor:
+    if _wants_grad(x):
+        return _TVLossFn.apply(x, weight)
+    return ops.tv_loss(x, weight)

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .autograd import ncut_loss_apply, segment_mean_apply, softmax_rows_with_labels, unpool_apply
+from .autograd import feature_loss_apply, ncut_loss_apply, segment_mean_apply, softmax_rows_with_labels, unpool_apply
 from .graph import Graph
 from .modules import GATNetwork, MinCutRefinement, PatchGraphConstructor, PatchSegmentPredictor, _layer_forward
 
@@ -33,6 +33,7 @@ class GraphBlockOutput(NamedTuple):
     patch_features: torch.Tensor         # (B, N, D) patch-GAT output h
     region_features: torch.Tensor        # (B, K, D) region-GAT output
     grid: Tuple[int, int]                # (nph, npw)
+    l_feature: Optional[torch.Tensor] = None   # 0-dim: FeatureConsistencyLoss(f_unet_patches, patch_features, y) (:344)
 
 
 class GraphBlock(nn.Module):
@@ -60,10 +61,27 @@ class GraphBlock(nn.Module):
 
     def forward(self, node_features: Optional[torch.Tensor] = None, image_size: Optional[Tuple[int, int]] = None,
                 feature_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, _block_outs=None) -> GraphBlockOutput:
+                out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, _block_outs=None,
+                f_unet_patches: Optional[torch.Tensor] = None, patch_labels_y: Optional[torch.Tensor] = None,
+                feature_loss_margin: float = 1.0) -> GraphBlockOutput:
         """Either ``node_features (B,N,in)`` + ``image_size (H,W)`` or a per-pixel ``feature_map
         (B,in,H,W)`` (patch-mean pooled to node features).  ``out`` may be a channel slice of a fusion
-        buffer ``(B,Ctot,H,W)[:, c0:c0+D]``; the dense map is written there directly."""
+        buffer ``(B,Ctot,H,W)[:, c0:c0+D]``; the dense map is written there directly.
+        ``f_unet_patches (B,N,D)`` + ``patch_labels_y (B,N)``: also return ``l_feature``, the reference's
+        feature-consistency loss between them and the patch-GAT output (train_end_to_end.py:344,
+        batch mean of the per-image sums)."""
+        res = self._forward(node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs)
+        if f_unet_patches is None:
+            return res
+        if patch_labels_y is None:
+            raise ValueError("patch_labels_y is required with f_unet_patches")
+        if tuple(f_unet_patches.shape) != tuple(res.patch_features.shape):
+            raise ValueError(f"f_unet ({f_unet_patches.shape}) and f_graph ({res.patch_features.shape}) must have "
+                             f"same dimensions for this loss version.")
+        return res._replace(l_feature=feature_loss_apply(f_unet_patches, res.patch_features, patch_labels_y,
+                                                         float(feature_loss_margin)))
+
+    def _forward(self, node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs) -> GraphBlockOutput:
         if (node_features is None) == (feature_map is None):
             raise ValueError("pass exactly one of node_features / feature_map")
         if feature_map is not None:

@@ -11,6 +11,8 @@ reference root):
 * ``PatchGraphConstructor`` — preprocessing/graph_construction/patch_graph_construction.py:5-136
 * ``MinCutRefinement``      — model/graph_partition/mincut_refinement.py:5-205
 * ``PatchSegmentPredictor`` — scripts/train_end_to_end.py:40-70
+* ``FeatureConsistencyLoss`` — model/unet/feature_loss.py:5-123   (scope row f4)
+* ``TVLoss``                — scripts/train_end_to_end.py:73-89    (scope row f4)
 
 so a reference checkpoint loads with ``load_state_dict`` unchanged and the classes can replace
 the reference's at its two call sites (scripts/train_end_to_end.py:318-421,
@@ -26,7 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .autograd import gat_layer_apply, ncut_loss_apply, softmax_rows
+from .autograd import feature_loss_apply, gat_layer_apply, ncut_loss_apply, softmax_rows, tv_loss_apply
 from .graph import Graph, register
 
 
@@ -119,7 +121,9 @@ class GATNetwork(nn.Module):
     (``hidden_dim`` unused).  Two or more layers are CONSTRUCTED exactly like the reference (same
     state_dict shapes), which means they inherit its width mismatch (:176-186: the next layer
     expects ``hidden_dim*num_heads`` inputs but the concatenating layer emits ``hidden_dim``) and
-    raise the same RuntimeError at forward."""
+    raise the same RuntimeError at forward.  :class:`StackedGATNetwork` is the working stack."""
+
+    _consistent_widths = False
 
     def __init__(self, node_feature_dim, hidden_dim, output_dim, num_heads, num_gat_layers=1, dropout_rate=0.1,
                  alpha=0.2):
@@ -130,13 +134,14 @@ class GATNetwork(nn.Module):
             self.gat_layers.append(
                 MultiHeadGATLayer(node_feature_dim, output_dim, num_heads, dropout_rate, alpha, concat=False))
         else:
+            mid_in = hidden_dim if self._consistent_widths else hidden_dim * num_heads
             self.gat_layers.append(
                 MultiHeadGATLayer(node_feature_dim, hidden_dim, num_heads, dropout_rate, alpha, concat=True))
             for _ in range(num_gat_layers - 2):
                 self.gat_layers.append(
-                    MultiHeadGATLayer(hidden_dim * num_heads, hidden_dim, num_heads, dropout_rate, alpha, concat=True))
+                    MultiHeadGATLayer(mid_in, hidden_dim, num_heads, dropout_rate, alpha, concat=True))
             self.gat_layers.append(
-                MultiHeadGATLayer(hidden_dim * num_heads, output_dim, num_heads, dropout_rate, alpha, concat=False))
+                MultiHeadGATLayer(mid_in, output_dim, num_heads, dropout_rate, alpha, concat=False))
 
     def forward(self, node_features, edge_index):
         h = node_features
@@ -145,6 +150,18 @@ class GATNetwork(nn.Module):
         for layer in self.gat_layers:
             h = layer(h, edge_index)
         return h
+
+
+class StackedGATNetwork(GATNetwork):
+    """The WORKING multi-layer stack (scope row f4; a deliberate, flagged deviation from
+    graph_attention.py:176-186): same constructor signature as :class:`GATNetwork`, but every layer
+    after the first takes the ``hidden_dim`` columns the concatenating layer actually emits
+    (:137-139,155), i.e. exactly the composition ``MultiHeadGATLayer(in, hidden, H, concat=True) ->
+    ... -> MultiHeadGATLayer(hidden, out, H, concat=False)`` of untouched reference layers.  Its
+    state_dict differs from the reference's (unusable) one only in the ``W.weight`` widths of layers
+    >= 1; with ``num_gat_layers=1`` it is identical to :class:`GATNetwork`."""
+
+    _consistent_widths = True
 
 
 class PatchGraphConstructor:
@@ -261,3 +278,37 @@ class PatchSegmentPredictor(nn.Module):
                 raise ValueError("edge_index must be provided for GNN-based segment predictor.")
             return self.gnn_predictor(x, edge_index)
         return self.mlp_predictor(x)
+
+
+class FeatureConsistencyLoss(nn.Module):
+    """``L_feature`` (model/unet/feature_loss.py:5-123): per patch ``y*d^2 + (1-y)*max(0, margin-d)^2``
+    with ``d = |f_unet - f_graph|``, summed over patches, averaged over the batch.  Same signature,
+    same ``ValueError``s (:95-101); one streaming kernel + a fixed-order reduction, differentiable
+    w.r.t. both feature tensors."""
+
+    def __init__(self, margin=1.0):
+        super().__init__()
+        self.margin = margin
+
+    def forward(self, f_unet, f_graph, correspondence_map_y, regions_unet=None, regions_graph=None):
+        B, N_patches, _ = f_unet.shape
+        _, _, _ = f_graph.shape
+        if f_unet.shape != f_graph.shape:
+            raise ValueError(f"f_unet ({f_unet.shape}) and f_graph ({f_graph.shape}) must have same dimensions "
+                             f"for this loss version.")
+        if correspondence_map_y.shape != (B, N_patches):
+            raise ValueError(f"correspondence_map_y (patch_region_labels_y) shape ({correspondence_map_y.shape}) "
+                             f"is not (Batch, Num_Patches) = ({B}, {N_patches}).")
+        return feature_loss_apply(f_unet, f_graph, correspondence_map_y, float(self.margin))
+
+
+class TVLoss(nn.Module):
+    """Total-variation smoothness loss (scripts/train_end_to_end.py:73-89) over ``(B,C,H,W)``; the map
+    is read once by a strip-walking kernel, differentiable w.r.t. ``x``."""
+
+    def __init__(self, weight=1.0):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, x):
+        return tv_loss_apply(x, float(self.weight))

@@ -438,3 +438,78 @@ def block_forward(x: torch.Tensor, Hp: int, Wp: int, prep: torch.Tensor, D: int,
              float(slopes[0]), float(slopes[1]), float(slopes[2]), prep.data_ptr(), h.data_ptr(), q.data_ptr(),
              S.data_ptr(), labels.data_ptr(), loss.data_ptr(), _ptr(rin), rout.data_ptr(), _stream())
     return h, S, labels, loss, rin, rout
+
+
+# ---------------------------------------------------------------------------------------------
+# losses on tensors the block already holds (scope row f4)
+# ---------------------------------------------------------------------------------------------
+_YDT = {torch.float32: MG_F32, torch.bfloat16: MG_BF16, torch.int32: _lib.MG_I32, torch.int64: _lib.MG_I64}
+
+
+def _label_tensor(y: torch.Tensor) -> torch.Tensor:
+    """Labels in a dtype the kernels read directly; other dtypes (bool, uint8, fp16, ...) take the
+    reference's own ``.float()`` (feature_loss.py:106)."""
+    return y.contiguous() if y.dtype in _YDT else y.float().contiguous()
+
+
+def feature_consistency_loss(f_unet: torch.Tensor, f_graph: torch.Tensor, y: torch.Tensor, margin: float = 1.0,
+                             with_per_image: bool = False):
+    """``mean_b sum_n [y*d^2 + (1-y)*max(0, margin-d)^2]``, ``d = |f_unet - f_graph|`` per patch
+    (model/unet/feature_loss.py:103-123).  ``f_* (B,N,D)`` f32|bf16, ``y (B,N)``.  Returns a 0-dim
+    float32 tensor (and the ``(B,)`` per-image sums)."""
+    dev = _need_cuda(f_unet, f_graph, y)
+    f_unet, f_graph, y = f_unet.contiguous(), f_graph.contiguous(), _label_tensor(y)
+    B, N, D = f_unet.shape
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    per = torch.empty(B, dtype=torch.float32, device=dev) if with_per_image else None
+    work = torch.empty(int(_lib.load().mg_feature_loss_work_bytes(B, N)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        call("mg_feature_consistency_loss", f_unet.data_ptr(), _dtype_code(f_unet.dtype), f_graph.data_ptr(),
+             _dtype_code(f_graph.dtype), y.data_ptr(), _YDT[y.dtype], B, N, D, float(margin), work.data_ptr(), _ptr(per),
+             loss.data_ptr(), _stream())
+    return (loss, per) if with_per_image else loss
+
+
+def feature_consistency_loss_backward(f_unet, f_graph, y, margin: float, grad_loss: torch.Tensor, need_unet: bool = True,
+                                      need_graph: bool = True):
+    """float32 gradients w.r.t. ``f_unet`` and ``f_graph`` (``None`` where not needed)."""
+    dev = _need_cuda(f_unet, f_graph, y, grad_loss)
+    f_unet, f_graph, y = f_unet.contiguous(), f_graph.contiguous(), _label_tensor(y)
+    B, N, D = f_unet.shape
+    gu = torch.empty((B, N, D), dtype=torch.float32, device=dev) if need_unet else None
+    gg = torch.empty((B, N, D), dtype=torch.float32, device=dev) if need_graph else None
+    grad_loss = grad_loss.contiguous().float()
+    with torch.cuda.device(dev):
+        call("mg_feature_consistency_loss_backward", f_unet.data_ptr(), _dtype_code(f_unet.dtype), f_graph.data_ptr(),
+             _dtype_code(f_graph.dtype), y.data_ptr(), _YDT[y.dtype], B, N, D, float(margin), grad_loss.data_ptr(),
+             _ptr(gu), _ptr(gg), _stream())
+    return gu, gg
+
+
+def tv_loss(x: torch.Tensor, weight: float = 1.0, with_terms: bool = False):
+    """``weight * (h_tv/((H-1)W) + w_tv/(H(W-1))) / B`` over ``x (B,C,H,W)`` f32|bf16
+    (scripts/train_end_to_end.py:73-89).  Returns a 0-dim float32 tensor (view of a 3-float result
+    ``[loss, h_tv, w_tv]`` when ``with_terms``)."""
+    dev = _need_cuda(x)
+    if x.dim() != 4:
+        raise RuntimeError("tv_loss expects (B, C, H, W)")
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    code = _dtype_code(x.dtype)
+    out3 = torch.empty(3, dtype=torch.float32, device=dev)
+    work = torch.empty(int(_lib.load().mg_tv_loss_work_bytes(code, B, C, H, W)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        call("mg_tv_loss", x.data_ptr(), code, B, C, H, W, float(weight), work.data_ptr(), out3.data_ptr(), _stream())
+    return out3 if with_terms else out3[0]
+
+
+def tv_loss_backward(x: torch.Tensor, weight: float, grad_loss: torch.Tensor) -> torch.Tensor:
+    dev = _need_cuda(x, grad_loss)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    gx = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+    grad_loss = grad_loss.contiguous().float()
+    with torch.cuda.device(dev):
+        call("mg_tv_loss_backward", x.data_ptr(), _dtype_code(x.dtype), B, C, H, W, float(weight), grad_loss.data_ptr(),
+             gx.data_ptr(), _stream())
+    return gx

@@ -129,6 +129,18 @@ def gat_network(x, ei, Ws, As, alpha: float = 0.2):
     return gat_layer(x, ei, Ws, As, alpha, concat=False)
 
 
+def gat_network_multilayer(x, ei, layers, alpha: float = 0.2):
+    """Working multi-layer stack (scope row f4): ``layers`` = list of ``(Ws, As)``; every layer but
+    the last concatenates its heads (graph_attention.py:137-139,155,176,181), the last averages
+    (:141,158,185); eval mode, so the inter-layer ``nn.Dropout`` (:160) is the identity.  This is
+    the composition of reference ``MultiHeadGATLayer``s with the widths the concatenating layer
+    really emits (the reference's own ``GATNetwork`` wires ``hidden*heads`` there and crashes)."""
+    h = x
+    for i, (Ws, As) in enumerate(layers):
+        h = gat_layer(h, ei, Ws, As, alpha, concat=i + 1 < len(layers))
+    return h
+
+
 # ----------------------------------------------------------------------------
 # normalized cut
 # ----------------------------------------------------------------------------
@@ -298,3 +310,31 @@ def stack_from_state_dict(sd, prefix: str = "gat_layers.0.heads."):
     Ws = torch.stack([sd[f"{prefix}{h}.W.weight"] for h in hs], 0).float()
     As = torch.stack([sd[f"{prefix}{h}.a.weight"].reshape(-1) for h in hs], 0).float()
     return Ws, As
+
+
+# ----------------------------------------------------------------------------
+# losses on block tensors (scope row f4)
+# ----------------------------------------------------------------------------
+def feature_consistency_loss(f_unet, f_graph, y, margin: float = 1.0):
+    """model/unet/feature_loss.py:103-123 with the revised-argument reading the code implements:
+    ``f_* (B,N,D)``, ``y (B,N)``; positive term ``y*dist_sq`` (:110), ``dist = sqrt(dist_sq + 1e-8)``
+    (:116), hinge ``relu(margin - dist)`` (:118), negative term ``(1-y)*hinge**2`` (:119), sum over
+    patches then mean over the batch (:124)."""
+    y_p = y.float().unsqueeze(-1)
+    dist_sq = torch.sum((f_unet - f_graph) ** 2, dim=2)
+    loss_positive = y_p.squeeze(-1) * dist_sq
+    dist = torch.sqrt(dist_sq + 1e-8)
+    hinge_term = F.relu(margin - dist)
+    loss_negative = (1 - y_p.squeeze(-1)) * (hinge_term ** 2)
+    return torch.sum(loss_positive + loss_negative, dim=1).mean()
+
+
+def tv_loss(x, weight: float = 1.0):
+    """scripts/train_end_to_end.py:79-89 — squared forward differences along H and W, each normalised
+    by its element count, scaled by ``weight`` and divided by the batch size."""
+    batch_size, h_x, w_x = x.size(0), x.size(2), x.size(3)
+    count_h = (h_x - 1) * w_x
+    count_w = h_x * (w_x - 1)
+    h_tv = torch.pow(x[:, :, 1:, :] - x[:, :, :-1, :], 2).sum()
+    w_tv = torch.pow(x[:, :, :, 1:] - x[:, :, :, :-1], 2).sum()
+    return weight * (h_tv / count_h + w_tv / count_w) / batch_size

@@ -91,6 +91,10 @@ def test_interface_matches_live_reference(mg):
              (R.PatchGraphConstructor, mg.PatchGraphConstructor)]
     if R.PatchSegmentPredictor is not None:
         pairs.append((R.PatchSegmentPredictor, mg.PatchSegmentPredictor))
+        import importlib
+        pairs.append((importlib.import_module("scripts.train_end_to_end").TVLoss, mg.TVLoss))
+        pairs.append((importlib.import_module("model.unet.feature_loss").FeatureConsistencyLoss, mg.FeatureConsistencyLoss))
+    pairs.append((R.GATNetwork, mg.StackedGATNetwork))
     for ref_cls, our_cls in pairs:
         assert str(inspect.signature(ref_cls.__init__)) == str(inspect.signature(our_cls.__init__)), ref_cls.__name__
         if hasattr(ref_cls, "forward"):

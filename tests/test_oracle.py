@@ -156,3 +156,56 @@ def test_knn_oracle_matches_pure_python_definition():
         assert [int(v) for v in ei[0, j * k:(j + 1) * k]] == [i for _, i in want]
         assert all(int(t) == j for t in ei[1, j * k:(j + 1) * k])
         assert [float(v) for v in dist[j]] == [float(d) for d, _ in want]
+
+
+# ---- scope row f4: losses and the multi-layer stack ------------------------------------------------
+FL_CASES = ["b3_n37_d64", "b1_n256_d64", "b2_n50_d7"]
+TV_CASES = ["b2_c1_64x64", "b3_c2_37x53", "b1_c3_5x200", "b2_c2_19x8"]
+
+
+@pytest.mark.parametrize("tag", FL_CASES)
+def test_feature_consistency_loss_restatement(golden, tag):
+    g = golden("losses.npz")
+    fu = T(g[f"fl_{tag}_fu"]).requires_grad_(True)
+    fg = T(g[f"fl_{tag}_fg"]).requires_grad_(True)
+    loss = O.feature_consistency_loss(fu, fg, T(g[f"fl_{tag}_y"]), float(g[f"fl_{tag}_margin"]))
+    loss.backward()
+    assert float(loss) == pytest.approx(float(g[f"fl_{tag}_loss"]), rel=1e-6)
+    assert same(fu.grad, T(g[f"fl_{tag}_gfu"]), 1e-6) and same(fg.grad, T(g[f"fl_{tag}_gfg"]), 1e-6)
+
+
+@pytest.mark.parametrize("tag", TV_CASES)
+def test_tv_loss_restatement(golden, tag):
+    g = golden("losses.npz")
+    x = T(g[f"tv_{tag}_x"]).requires_grad_(True)
+    loss = O.tv_loss(x, float(g[f"tv_{tag}_weight"]))
+    loss.backward()
+    assert float(loss) == pytest.approx(float(g[f"tv_{tag}_loss"]), rel=1e-6)
+    assert same(x.grad, T(g[f"tv_{tag}_gx"]), 1e-7)
+
+
+@pytest.mark.parametrize("tag", ["2layer", "3layer"])
+def test_multilayer_stack_restatement(golden, tag):
+    g = golden("multilayer_gat.npz")
+    hp, wp, fin, hidden, fout, heads, nl = (int(v) for v in g[f"{tag}_meta"])
+    layers = [(T(g[f"{tag}_W{i}"]), T(g[f"{tag}_a{i}"])) for i in range(nl)]
+    y = O.gat_network_multilayer(T(g[f"{tag}_x"]), T(O.grid_edge_index(hp, wp)), layers)
+    assert same(y, T(g[f"{tag}_y"]))
+    assert "cannot be multiplied" in str(g[f"{tag}_ref_network_error"])    # the reference's own stack crashes
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_losses_against_live_reference():
+    import importlib
+    import warnings
+    ref_loader.load()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fl = importlib.import_module("model.unet.feature_loss")
+        te = importlib.import_module("scripts.train_end_to_end")
+    gen = torch.Generator().manual_seed(9)
+    fu, fg = 0.1 * torch.randn(2, 33, 16, generator=gen), 0.1 * torch.randn(2, 33, 16, generator=gen)
+    y = torch.randint(0, 2, (2, 33), generator=gen)
+    assert torch.equal(O.feature_consistency_loss(fu, fg, y, 0.7), fl.FeatureConsistencyLoss(0.7)(fu, fg, y))
+    x = torch.rand(2, 3, 17, 9, generator=gen)
+    assert torch.equal(O.tv_loss(x, 1.5), te.TVLoss(1.5)(x))
