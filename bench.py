@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--shards", type=int, default=2, help="parallel sub-batches inside the captured graph (ours arm)")
+    ap.add_argument("--shards", type=int, default=1, help="parallel sub-batches inside the captured graph (ours arm)")
+    ap.add_argument("--pipeline-depth", type=int, default=2,
+                    help="independent steps in flight (PipelinedGraphBlock slots; 1 = one replay at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
@@ -220,36 +222,46 @@ def run_ours(args):
     gen = torch.Generator().manual_seed(1000 + rank)
     fm_host = torch.randn(B, IN_DIM, H, W, generator=gen).to(dtype).pin_memory()
     fm_dev = fm_host.to(dev)
-    fusion = torch.zeros(B, C_UNET + D_OUT, H, W, dtype=dtype, device=dev)     # [0:32] decoder features, [32:96] F_g
-    f_g_slice = fusion[:, C_UNET:]
-    host_loss = torch.empty(B, dtype=torch.float32).pin_memory()
-    host_region = torch.empty(B, K_SEG, D_OUT, dtype=torch.float32).pin_memory()
-    host_labels = torch.empty(B, N, dtype=torch.int32).pin_memory()
+    depth = max(1, args.pipeline_depth)
+    # one fusion buffer per pipeline slot: [0:32] decoder features, [32:96] F_g
+    fusions = [torch.zeros(B, C_UNET + D_OUT, H, W, dtype=dtype, device=dev) for _ in range(depth)]
+    f_g_slices = [f[:, C_UNET:] for f in fusions]
+    f_g_slice = f_g_slices[0]
+    host_loss = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(depth)]
+    host_region = [torch.empty(B, K_SEG, D_OUT, dtype=torch.float32).pin_memory() for _ in range(depth)]
+    host_labels = [torch.empty(B, N, dtype=torch.int32).pin_memory() for _ in range(depth)]
 
     # public API: the block recorded once into a CUDA graph (pool -> fused block kernel -> un-pool), replayed per step
     # two independent half batches on parallel branches of the graph: the latency-bound cluster kernel of one half
     # overlaps the HBM-bound pool / un-pool of the other
+    # consecutive steps are independent batches: `depth` recorded graphs (own buffers, own stream) are used round-robin
+    # so the HBM-bound un-pool of step i overlaps the pool + latency-bound cluster kernel of step i+1
     lc0 = _lib.launch_count()
-    runner = mg.CapturedGraphBlock(blk, fm_dev, image_size=(H, W), out=f_g_slice, shards=args.shards, warmup=2)
-    per_step_kernels = (_lib.launch_count() - lc0 - 1) // 3        # 2 warm-up passes + the recorded one (+1 weight prepare)
+    pipe = mg.PipelinedGraphBlock(blk, fm_dev, image_size=(H, W), outs=f_g_slices, shards=args.shards, depth=depth, warmup=2)
+    runner = pipe.runners[0]
+    per_step_kernels = (_lib.launch_count() - lc0 - 1) // (3 * depth)   # per slot: 2 warm-up passes + the recorded one (+1 weight prepare)
 
     from mingraph_unet_b200.distributed import OverlappedGather
     gather = OverlappedGather(B, N, K_SEG, D_OUT, dev) if world > 1 else None
 
-    def exchange(out):
-        """N>1: one NCCL all-gather per step of the small per-image outputs (never the dense map), issued on a
-        side stream so it overlaps the next step's kernels; all of them complete inside the timed region."""
+    def exchange(slot, out):
+        """N>1: one NCCL all-gather per step of the small per-image outputs (never the dense map): packed on the
+        step's own stream, gathered on a side stream so it overlaps the next steps' kernels; all of them complete
+        inside the timed region."""
         if gather is not None:
-            gather.push(out.l_partition, out.region_features, out.hard_labels)
+            with torch.cuda.stream(pipe.stream(slot)):
+                gather.push(out.l_partition, out.region_features, out.hard_labels)
+            pipe.mark(slot)
 
     def step():
-        out = runner()                  # static input already resident in HBM
-        exchange(out)
+        slot, out = pipe.submit()       # static input already resident in HBM
+        exchange(slot, out)
         return out
 
     def barrier():
+        pipe.join()                     # every outstanding step belongs to the region being closed
         if gather is not None:
-            gather.drain()              # the side-stream gathers belong to the region being closed
+            gather.drain()              # and so do the side-stream gathers
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -265,9 +277,21 @@ def run_ours(args):
     t_start.record()
     for _ in range(args.steps):
         step()
+    pipe.join()
+    if gather is not None:
+        gather.drain()
     t_end.record()
     barrier()
     sampler.stop()
+    # latency of ONE step (a single replay at a time on the current stream), reported next to the pipelined throughput
+    lat_steps = max(10, min(args.steps, 100))
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for _ in range(lat_steps):
+        runner()
+    l1.record()
+    torch.cuda.synchronize()
+    latency_ms = l0.elapsed_time(l1) / lat_steps
     # kernels recorded in the graph launch once per replay (pool, block, un-pool per shard)
     launches = (_lib.launch_count() - launches0) + per_step_kernels * args.steps
     ms_total = t_start.elapsed_time(t_end)
@@ -277,7 +301,7 @@ def run_ours(args):
         t_until = time.time() + 1.0
         while time.time() < t_until:            # rank-local, time-based loop: NO collectives in here
             for _ in range(20):
-                runner()
+                pipe.submit()
             torch.cuda.synchronize()
         sampler.stop()
         note = "timed region shorter than the NVML sampling period; sampled under the same load right after it"
@@ -315,12 +339,16 @@ def run_ours(args):
 
     # ---- end-to-end through the public API with host buffers (e2e) ---------------------------
     def e2e_step():
-        out = runner(fm_host)                                   # H2D of this step's input from pinned memory
-        exchange(out)
-        host_loss.copy_(out.l_partition, non_blocking=True)     # D2H of the step's results
-        host_region.copy_(out.region_features, non_blocking=True)
-        host_labels.copy_(out.hard_labels, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        slot, out = pipe.submit(fm_host)                        # H2D of this step's input from pinned memory
+        exchange(slot, out)
+        with torch.cuda.stream(pipe.stream(slot)):              # D2H of the step's results, on the step's stream
+            host_loss[slot].copy_(out.l_partition, non_blocking=True)
+            host_region[slot].copy_(out.region_features, non_blocking=True)
+            host_labels[slot].copy_(out.hard_labels, non_blocking=True)
+        pipe.mark(slot)
+        # the host takes delivery of the OLDEST step in flight (the slot the next submit reuses): at most `depth`
+        # steps are outstanding and every step's results are in host memory before the timed region closes
+        pipe.host_wait((slot + 1) % depth)
 
     for _ in range(3):
         e2e_step()
@@ -330,6 +358,9 @@ def run_ours(args):
     e0.record()
     for _ in range(e2e_steps):
         e2e_step()
+    pipe.join()
+    if gather is not None:
+        gather.drain()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -361,7 +392,9 @@ def run_ours(args):
             "dtype": "f32" if dtype == torch.float32 else "bf16 storage / f32 math", "data": "synthetic", "config": cfg,
             "edges_per_s": B * world * E * args.steps / (ms_total * 1e-3),
             "step_hbm_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
-            "gpu_launches": int(launches), "launch_mode": "CUDA graph replay (%d kernels of libmingraph_b200.so per step, %d parallel shard branches)" % (per_step_kernels, runner.shards),
+            "gpu_launches": int(launches), "launch_mode": "CUDA graph replay (%d kernels of libmingraph_b200.so per step, %d parallel shard branches per "
+                                                       "step, %d independent steps in flight on round-robin streams)" % (per_step_kernels, runner.shards, depth),
+            "pipeline_depth": depth, "step_latency_ms": latency_ms,
             "roofline": {"kernel": "unpool_vec_kernel (K7 nearest un-pool)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": unpool_bytes,
@@ -370,17 +403,17 @@ def run_ours(args):
                          "timing": "CUDA events around eager launches of the same kernels with the graph's launch shape "
                                    "(one shard of %d images; graph replays cannot carry timing events)" % Bs,
                          "other_kernels": {
-                             "pool_patches_vec_kernel": {"ms": kern_ms["pool"], "algorithmic_bytes": pool_bytes,
+                             "pool_patches_tma_kernel": {"ms": kern_ms["pool"], "algorithmic_bytes": pool_bytes,
                                                          "achieved_gbs": pool_bytes / (kern_ms["pool"] * 1e-3) / 1e9,
                                                          "frac": pool_bytes / (kern_ms["pool"] * 1e-3) / 1e9 / peak},
                              "block_forward_kernel": {"ms": kern_ms["block"], "note": "latency-bound cluster kernel; "
                                                       "moves ~%.1f MB" % (B * N * (IN_DIM * b + 4 * (D_OUT + 12)) / 1e6)}}},
             "e2e": {"value": B * world * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": fm_host.numel() * fm_host.element_size(),
-                    "d2h_bytes_per_step": 4 * (host_loss.numel() + host_region.numel() + host_labels.numel()),
+                    "d2h_bytes_per_step": 4 * (host_loss[0].numel() + host_region[0].numel() + host_labels[0].numel()),
                     "steps": e2e_steps,
-                    "api": "CapturedGraphBlock(GraphBlock)(pinned host feature map): H2D + graph replay + D2H of "
-                           "loss / region features / labels"},
+                    "api": "PipelinedGraphBlock(GraphBlock).submit(pinned host feature map): H2D + graph replay + D2H of "
+                           "loss / region features / labels per step, %d steps in flight" % depth},
             "clocks": sampler.summary(note),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -12,10 +12,10 @@ _lib.load()          # fail loudly when the CUDA library is missing
 from . import ops  # noqa: E402
 from .block import GraphBlock, GraphBlockOutput  # noqa: E402
 from .graph import Graph  # noqa: E402
-from .runner import CapturedGraphBlock, CapturedTrainStep  # noqa: E402
+from .runner import CapturedGraphBlock, CapturedTrainStep, PipelinedGraphBlock  # noqa: E402
 from .modules import (FeatureConsistencyLoss, GATNetwork, GraphAttentionLayer, MinCutRefinement,  # noqa: E402
                       MultiHeadGATLayer, PatchGraphConstructor, PatchSegmentPredictor, StackedGATNetwork, TVLoss)
 
-__all__ = ["ops", "Graph", "GraphBlock", "CapturedGraphBlock", "CapturedTrainStep", "GraphBlockOutput", "GATNetwork", "GraphAttentionLayer", "MinCutRefinement",
+__all__ = ["ops", "Graph", "GraphBlock", "CapturedGraphBlock", "CapturedTrainStep", "PipelinedGraphBlock", "GraphBlockOutput", "GATNetwork", "GraphAttentionLayer", "MinCutRefinement",
            "MultiHeadGATLayer", "PatchGraphConstructor", "PatchSegmentPredictor", "FeatureConsistencyLoss", "TVLoss", "StackedGATNetwork"]
 __version__ = "0.1.0"

@@ -16,6 +16,8 @@
 // vectors u = W^T a) and staged into shared memory with one TMA bulk copy (cp.async.bulk).
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -886,6 +888,14 @@ static int max_active_clusters(int c, size_t smem) {
 }
 
 static int plan_cluster(BlockShape* s) {
+  // experiment / tuning override: MG_BLOCK_CLUSTER = 1, 2, 4 or 8 CTAs per image (fewer CTAs leave SMs to the HBM-bound
+  // kernels of the neighbouring pipeline step)
+  static const int forced = getenv("MG_BLOCK_CLUSTER") ? atoi(getenv("MG_BLOCK_CLUSTER")) : 0;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
+    s->cluster = forced;
+    s->npc = ceil_div(s->N, forced);
+    return forced;
+  }
   // smallest cluster (power of two <= 8) with <= 256 nodes per CTA, else 8
   int c = 1;
   while (c < kMaxCluster && ceil_div(s->N, c) > 256) c <<= 1;

@@ -3,6 +3,8 @@
 // K7 writes the dense (B,D,H,W) map once with 16-byte streaming stores.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mg {
@@ -144,6 +146,204 @@ __global__ void __launch_bounds__(256) pool_patches_strip_kernel(const TX* __res
   for (int idx = threadIdx.x; idx < Wp * ncc; idx += blockDim.x) {
     const int px = idx / ncc, cc = idx - px * ncc;
     out[((size_t)b * Hp * Wp + (size_t)py * Wp + px) * C + c0 + cc] = from_f32<TO>(tile[px * (nw + 1) + cc]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA path (default when it applies): a (image, channel, patch-row) strip is ph FULL rows of the map = one contiguous
+// run of ph*Wf elements, so the feature map is a stream of contiguous strips.  Persistent CTAs (one per SM) take strips
+// round-robin; inside a CTA warp w owns strips w, w + kPtWarps, ... and runs its OWN ring of `stages` shared-memory
+// buffers: lane 0 moves whole rows global -> shared with cp.async.bulk (chunks of <= stage_bytes) completing on the
+// ring's mbarriers (expect_tx / complete_tx), always `stages` chunks ahead of the chunk being summed, so ~200 KB per SM
+// are in flight with no global load instructions or address arithmetic in the summing code.  The warp reads a landed
+// chunk with conflict-free 16-byte shared loads (kPtUnroll rows per batch), keeps fp32 column sums in registers, folds
+// lanes into patch columns by shuffle and stores one (N,C) element per patch.  A ring is private to its warp, so the
+// buffer hand-back needs no second barrier: after __syncwarp() lane 0 re-arms the buffer it has just drained.  Strips
+// are ordered channel-fastest so that concurrently processed strips fill the same output sectors.
+// ------------------------------------------------------------------------------------------
+constexpr int kPtWarps = 8;
+constexpr int kPtUnroll = 8;        // rows whose 16-byte shared loads are issued together
+constexpr int kPtMaxPasses = 8;
+constexpr int kPtSmemBytes = 208 * 1024;
+
+__device__ __forceinline__ uint32_t pt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pt_mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pt_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pt_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PT_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PT_WAIT_DONE;\n"
+      "bra PT_WAIT_LOOP;\n"
+      "PT_WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// read-once stream: L2 evict-first policy so the map does not displace the block's working set
+__device__ __forceinline__ void pt_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+// sum of 16 bytes as fp32
+template <typename T>
+__device__ __forceinline__ float pt_sum16(const uint4& u);
+template <>
+__device__ __forceinline__ float pt_sum16<float>(const uint4& u) {
+  return (__uint_as_float(u.x) + __uint_as_float(u.y)) + (__uint_as_float(u.z) + __uint_as_float(u.w));
+}
+template <>
+__device__ __forceinline__ float pt_sum16<__nv_bfloat16>(const uint4& u) {
+  const unsigned w[4] = {u.x, u.y, u.z, u.w};
+  float lo = 0.f, hi = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    lo += __uint_as_float(w[i] << 16);
+    hi += __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return lo + hi;
+}
+
+struct PoolTmaArgs {
+  const void* x;
+  void* out;
+  int C, Hf, Wf, ph, pw, Hp, Wp;
+  int rpc;          // rows per chunk (rpc * Wf * esz <= stage_bytes)
+  int nstrips;      // B * Hp * C, strip s = (b * Hp + py) * C + c
+  int stages;       // ring depth per warp
+  int stage_bytes;  // multiple of 128
+};
+
+// walks the chunks of one warp's strips in order
+template <typename TX>
+struct PtCursor {
+  int s, step, r0, rows, c;
+  size_t orow;
+  const TX* base;
+  __device__ __forceinline__ void load(const PoolTmaArgs& A) {
+    if (s >= A.nstrips) return;
+    c = s % A.C;
+    const int bp = s / A.C;
+    const int py = bp % A.Hp, b = bp / A.Hp;
+    const int y0 = py * A.ph;
+    rows = min(A.Hf, y0 + A.ph) - y0;
+    r0 = 0;
+    orow = ((size_t)b * A.Hp + py) * A.Wp;
+    base = reinterpret_cast<const TX*>(A.x) + (((size_t)b * A.C + c) * A.Hf + y0) * A.Wf;
+  }
+  __device__ __forceinline__ bool valid(const PoolTmaArgs& A) const { return s < A.nstrips; }
+  __device__ __forceinline__ void next_chunk(const PoolTmaArgs& A) {
+    r0 += A.rpc;
+    if (r0 >= rows) {
+      s += step;
+      load(A);
+    }
+  }
+};
+
+template <typename TX, typename TO>
+__global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(const PoolTmaArgs A) {
+  constexpr int VEC = Vec16<TX>::N;
+  extern __shared__ __align__(128) unsigned char pt_smem[];
+  const int q = A.stages;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* ring = pt_smem + (size_t)warp * q * A.stage_bytes;
+  const uint32_t ring0 = pt_smem_u32(ring);
+  const uint32_t full0 = pt_smem_u32(pt_smem) + (uint32_t)(kPtWarps * q) * (uint32_t)A.stage_bytes + 8u * (uint32_t)(warp * q);
+  if (lane == 0) {
+    for (int i = 0; i < q; ++i) pt_mbar_init(full0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  const int row_bytes = A.Wf * (int)sizeof(TX);
+  const int rv = row_bytes >> 4;                              // 16-byte vectors per row
+  const int nvec = A.Wf / VEC;
+  const int passes = ceil_div(nvec, 32);
+  const int lpp = A.pw / VEC;
+  const float inv = 1.f / (float)(A.ph * A.pw);
+  TO* out = reinterpret_cast<TO*>(A.out);
+
+  PtCursor<TX> ic, cc;                                        // issue cursor (q chunks ahead), consume cursor
+  ic.s = cc.s = blockIdx.x + warp * gridDim.x;
+  ic.step = cc.step = kPtWarps * gridDim.x;
+  ic.load(A);
+  cc.load(A);
+  int issued = 0;
+  auto issue = [&]() {
+    if (!ic.valid(A)) return;
+    if (lane == 0) {
+      const int st = issued % q;
+      const uint32_t bytes = (uint32_t)(min(A.rpc, ic.rows - ic.r0) * row_bytes);
+      pt_mbar_expect_tx(full0 + 8 * st, bytes);
+      pt_bulk_g2s(ring0 + (uint32_t)st * (uint32_t)A.stage_bytes, ic.base + (size_t)ic.r0 * A.Wf, bytes, full0 + 8 * st, policy);
+    }
+    ++issued;
+    ic.next_chunk(A);
+  };
+  for (int t = 0; t < q; ++t) issue();
+
+  int consumed = 0;
+  float acc[kPtMaxPasses];
+  while (cc.valid(A)) {
+    if (cc.r0 == 0) {
+#pragma unroll
+      for (int p = 0; p < kPtMaxPasses; ++p) acc[p] = 0.f;
+    }
+    const int st = consumed % q;
+    pt_mbar_wait(full0 + 8 * st, (uint32_t)((consumed / q) & 1));
+    const int nr = min(A.rpc, cc.rows - cc.r0);
+    const uint4* sp = reinterpret_cast<const uint4*>(ring + (size_t)st * A.stage_bytes) + lane;
+#pragma unroll
+    for (int p = 0; p < kPtMaxPasses; ++p) {
+      if (p < passes && p * 32 + lane < nvec) {
+        const uint4* a0 = sp + p * 32;
+        float part = 0.f;
+        int r = 0;
+        for (; r + kPtUnroll <= nr; r += kPtUnroll) {
+          uint4 u[kPtUnroll];
+#pragma unroll
+          for (int j = 0; j < kPtUnroll; ++j) u[j] = a0[(r + j) * rv];
+          float t[kPtUnroll];
+#pragma unroll
+          for (int j = 0; j < kPtUnroll; ++j) t[j] = pt_sum16<TX>(u[j]);
+#pragma unroll
+          for (int h = kPtUnroll / 2; h > 0; h >>= 1)
+#pragma unroll
+            for (int j = 0; j < h; ++j) t[j] += t[j + h];
+          part += t[0];
+        }
+        for (; r < nr; ++r) part += pt_sum16<TX>(a0[r * rv]);
+        acc[p] += part;
+      }
+    }
+    __syncwarp();                                             // every lane has read the buffer: lane 0 may re-arm it
+    issue();
+    ++consumed;
+    const bool last = cc.r0 + A.rpc >= cc.rows;
+    if (last) {
+#pragma unroll
+      for (int p = 0; p < kPtMaxPasses; ++p) {
+        if (p < passes) {
+          float v = acc[p];
+          for (int o = 1; o < lpp; o <<= 1) v += __shfl_xor_sync(kFull, v, o);
+          const int px = (p * 32 + lane) / lpp;
+          if ((lane & (lpp - 1)) == 0 && p * 32 + lane < nvec && px < A.Wp)
+            out[(cc.orow + px) * A.C + cc.c] = from_f32<TO>(v * inv);
+        }
+      }
+    }
+    cc.next_chunk(A);
   }
 }
 
@@ -379,6 +579,33 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
   const bool fast = (pw % VEC == 0) && (Wf % VEC == 0) && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 &&
                     ((uintptr_t)x % 16 == 0);
   static const int variant = getenv("MG_POOL_VARIANT") ? atoi(getenv("MG_POOL_VARIANT")) : 0;
+  // default: TMA-staged persistent kernel (at least one whole row per ring buffer, <= 8 column passes per warp)
+  const int row_bytes = Wf * (int)sizeof(TX);
+  static const int stages_env = getenv("MG_POOL_STAGES") ? atoi(getenv("MG_POOL_STAGES")) : 3;
+  static const int chunk_env = getenv("MG_POOL_CHUNK") ? atoi(getenv("MG_POOL_CHUNK")) : 8192;
+  {
+    int stages = std::max(2, std::min(8, stages_env));
+    int stage_bytes = std::max(row_bytes, std::max(1024, chunk_env)) / 128 * 128;
+    stage_bytes = std::max(stage_bytes, (row_bytes + 127) / 128 * 128);
+    while (stages > 2 && (size_t)kPtWarps * stages * (stage_bytes + 8) > (size_t)kPtSmemBytes) --stages;
+    const size_t smem = (size_t)kPtWarps * stages * (stage_bytes + 8);
+    if (fast && variant == 0 && smem <= (size_t)kPtSmemBytes && ceil_div(Wf / VEC, 32) <= kPtMaxPasses && lpp <= 32) {
+      PoolTmaArgs A;
+      A.x = x; A.out = out; A.C = C; A.Hf = Hf; A.Wf = Wf; A.ph = ph; A.pw = pw; A.Hp = Hp; A.Wp = Wp;
+      A.rpc = std::max(1, std::min(ph, stage_bytes / row_bytes));
+      A.nstrips = B * Hp * C;
+      A.stages = stages;
+      A.stage_bytes = stage_bytes;
+      auto kern = pool_patches_tma_kernel<TX, TO>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes) != cudaSuccess) {
+        set_error("mg_pool_patches: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+        return MG_ERR_CUDA;
+      }
+      const int grid = std::min(num_sms(), ceil_div(A.nstrips, kPtWarps));
+      kern<<<grid, kPtWarps * 32, smem, st>>>(A);
+      return check_launch("pool_patches_tma_kernel");
+    }
+  }
   if (fast && variant >= 1 && (size_t)Wp * 9 * 4 <= 48 * 1024) {
     const int nw = variant >= 2 ? variant : 4;             // warps (= channels) per block
     dim3 grid(ceil_div(C, nw), Hp, B);

@@ -139,6 +139,69 @@ class CapturedGraphBlock:
         return self.outputs
 
 
+class PipelinedGraphBlock:
+    """``depth`` :class:`CapturedGraphBlock` slots (own static input, own outputs, own stream each), used round-robin so
+    that CONSECUTIVE steps overlap: while step ``i`` streams its dense map out (HBM-bound un-pool), step ``i+1`` already
+    runs its pool and its latency-bound cluster kernel.  Within a step the stage order is a dependency chain
+    (pool -> block -> un-pool), so a single replay leaves the HBM pipe idle during the block kernel and the SMs idle
+    during the tail of the un-pool; across independent batches nothing has to wait.  Throughput per step approaches the
+    step's HBM time; the latency of one step is unchanged.
+
+    ``submit(x)`` enqueues one step on the next slot's stream (after everything the caller has enqueued on the current
+    stream so far, so an ``x`` produced there is visible) and returns ``(slot, outputs)``; the outputs are that slot's
+    static tensors, valid on ``stream(slot)`` and overwritten ``depth`` submits later.  Consumers either enqueue on
+    ``stream(slot)`` or call ``join()`` (current stream waits for every outstanding slot) / ``host_wait(slot)``.
+    Weight updates are picked up by the next submit; call ``join()`` before changing parameters."""
+
+    def __init__(self, block: GraphBlock, example: torch.Tensor, image_size: Optional[Tuple[int, int]] = None,
+                 outs=None, out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, depth: int = 2,
+                 shards: int = 1, warmup: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        if outs is not None and len(outs) != depth:
+            raise ValueError("outs must hold one dense output (slice) per slot")
+        dev = example.device
+        self.depth = depth
+        self.runners = [CapturedGraphBlock(block, example, image_size, out=None if outs is None else outs[i],
+                                           out_dtype=out_dtype, want_dense=want_dense, warmup=warmup, shards=shards)
+                        for i in range(depth)]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self.done = [None] * depth
+        self.shards = self.runners[0].shards
+        self._turn = 0
+
+    def stream(self, slot: int) -> torch.cuda.Stream:
+        return self.streams[slot]
+
+    def submit(self, x: Optional[torch.Tensor] = None):
+        i = self._turn
+        self._turn = (i + 1) % self.depth
+        st = self.streams[i]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(st.device))
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
+            out = self.runners[i](x)
+        self.mark(i)
+        return i, out
+
+    def mark(self, slot: int) -> None:
+        """(Re-)record the slot's completion after the caller enqueued consumer work on ``stream(slot)``."""
+        ev = torch.cuda.Event()
+        ev.record(self.streams[slot])
+        self.done[slot] = ev
+
+    def join(self) -> None:
+        cur = torch.cuda.current_stream(self.streams[0].device)
+        for ev in self.done:
+            if ev is not None:
+                cur.wait_event(ev)
+
+    def host_wait(self, slot: int) -> None:
+        if self.done[slot] is not None:
+            self.done[slot].synchronize()
+
+
 class CapturedTrainStep:
     """One training step of a :class:`GraphBlock` recorded into CUDA graphs and replayed with one or two driver calls.
 

@@ -257,7 +257,11 @@ def test_patch_pool_golden(mg, golden):
 
 
 @pytest.mark.parametrize("B,C,H,W,p", [(2, 20, 64, 64, 16), (1, 33, 70, 75, 16), (3, 512, 32, 32, 1), (2, 32, 128, 96, 8),
-                                       (1, 5, 37, 53, 7), (2, 20, 512, 512, 16)])
+                                       (1, 5, 37, 53, 7), (2, 20, 512, 512, 16),
+                                       # TMA-staged path: ragged bottom strip, rows wider than a chunk row budget
+                                       # (several chunks per strip), fewer vectors than lanes, more strips than warps
+                                       (2, 5, 70, 64, 16), (1, 3, 64, 1024, 16), (1, 2, 40, 2048, 16), (1, 2, 33, 96, 8),
+                                       (3, 7, 100, 256, 32), (1, 1, 16, 16, 16), (2, 20, 1024, 1024, 16)])
 def test_patch_pool_vs_oracle(mg, B, C, H, W, p):
     gen = torch.Generator().manual_seed(C)
     x = torch.randn(B, C, H, W, generator=gen)
@@ -620,3 +624,33 @@ def test_captured_graph_block_shards_match_single(mg):
         assert torch.equal(a.patch_features, b.patch_features) and torch.equal(a.region_features, b.region_features)
         assert torch.equal(a.soft_assignments, b.soft_assignments)
         assert torch.equal(buf1, buf2) and float(buf1[:, :32].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("depth,shards", [(2, 1), (3, 2)])
+def test_pipelined_graph_block_matches_eager(mg, depth, shards):
+    """PipelinedGraphBlock: consecutive steps overlap on round-robin slots, every step still returns exactly what the
+    eager block returns for ITS input (7 different inputs through `depth` slots; host and device inputs)."""
+    B, C, H, W, D = 4, 20, 128, 96, 64
+    gen = torch.Generator().manual_seed(21)
+    blk = mg.GraphBlock(node_feature_dim=C, num_segments=2).cuda().eval()
+    xs = [torch.randn(B, C, H, W, generator=gen) for _ in range(7)]
+    bufs = [torch.zeros(B, 32 + D, H, W, device="cuda") for _ in range(depth)]
+    pipe = mg.PipelinedGraphBlock(blk, xs[0].cuda(), image_size=(H, W), outs=[b[:, 32:] for b in bufs], depth=depth, shards=shards)
+    assert pipe.depth == depth and pipe.shards == shards
+    got = []
+    for i, x in enumerate(xs):
+        src = x.pin_memory() if i % 2 else x.cuda()            # pinned host input (H2D on the slot's stream) or device input
+        slot, out = pipe.submit(src)
+        assert slot == i % depth
+        with torch.cuda.stream(pipe.stream(slot)):             # consumer work rides the slot's stream
+            got.append((out.f_g.clone(), out.l_partition.clone(), out.hard_labels.clone(), out.region_features.clone()))
+        pipe.mark(slot)
+    pipe.join()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for x, (fg, loss, lab, reg) in zip(xs, got):
+            ref = blk(feature_map=x.cuda(), image_size=(H, W))
+            assert torch.equal(ref.f_g, fg) and torch.equal(ref.l_partition, loss)
+            assert torch.equal(ref.hard_labels, lab) and torch.equal(ref.region_features, reg)
+    assert all(float(b[:, :32].abs().max()) == 0.0 for b in bufs)
+    pipe.host_wait(0)
