@@ -236,22 +236,19 @@ def run_ours(args):
     # overlaps the HBM-bound pool / un-pool of the other
     # consecutive steps are independent batches: `depth` recorded graphs (own buffers, own stream) are used round-robin
     # so the HBM-bound un-pool of step i overlaps the pool + latency-bound cluster kernel of step i+1
+    # N>1: one NCCL all-gather per step of the small per-image outputs (never the dense map), recorded INSIDE each
+    # slot's graph on the slot's own communicator: the block kernel writes the payload in place, a step is one driver call
+    from mingraph_unet_b200.distributed import CapturedGather
+    gather = CapturedGather(B, N, K_SEG, D_OUT, dev, depth) if world > 1 else None
     lc0 = _lib.launch_count()
-    pipe = mg.PipelinedGraphBlock(blk, fm_dev, image_size=(H, W), outs=f_g_slices, shards=args.shards, depth=depth, warmup=2)
+    pipe = mg.PipelinedGraphBlock(blk, fm_dev, image_size=(H, W), outs=f_g_slices, shards=args.shards, depth=depth, warmup=2,
+                                  packed_small=None if gather is None else gather.packed,
+                                  epilogues=None if gather is None else gather.epilogues())
     runner = pipe.runners[0]
     per_step_kernels = (_lib.launch_count() - lc0 - 1) // (3 * depth)   # per slot: 2 warm-up passes + the recorded one (+1 weight prepare)
 
-    from mingraph_unet_b200.distributed import OverlappedGather
-    gather = OverlappedGather(B, N, K_SEG, D_OUT, dev) if world > 1 else None
-
     def exchange(slot, out):
-        """N>1: one NCCL all-gather per step of the small per-image outputs (never the dense map): packed on the
-        step's own stream, gathered on a side stream so it overlaps the next steps' kernels; all of them complete
-        inside the timed region."""
-        if gather is not None:
-            with torch.cuda.stream(pipe.stream(slot)):
-                gather.push(out.l_partition, out.region_features, out.hard_labels)
-            pipe.mark(slot)
+        pass                            # the gather is part of the replayed graph
 
     def step():
         slot, out = pipe.submit()       # static input already resident in HBM
@@ -259,9 +256,7 @@ def run_ours(args):
         return out
 
     def barrier():
-        pipe.join()                     # every outstanding step belongs to the region being closed
-        if gather is not None:
-            gather.drain()              # and so do the side-stream gathers
+        pipe.join()                     # every outstanding step (and its in-graph gather) belongs to the region being closed
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -278,8 +273,6 @@ def run_ours(args):
     for _ in range(args.steps):
         step()
     pipe.join()
-    if gather is not None:
-        gather.drain()
     t_end.record()
     barrier()
     sampler.stop()
@@ -359,8 +352,6 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()
     pipe.join()
-    if gather is not None:
-        gather.drain()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -428,7 +419,14 @@ def run_ours(args):
                                                               f"{secs:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The slots' CUDA graphs hold NCCL kernels of the per-slot communicators; tearing a communicator down while a
+        # graph that references it is alive blocks.  Everything is measured and printed: leave together, without
+        # running destructors.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------

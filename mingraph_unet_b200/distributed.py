@@ -142,3 +142,40 @@ class OverlappedGather:
         for ev in self.done:
             if ev is not None:
                 torch.cuda.current_stream().wait_event(ev)
+
+
+class CapturedGather:
+    """The per-step all-gather of the small per-image outputs recorded INSIDE each pipeline slot's CUDA graph.
+
+    ``OverlappedGather`` costs the host a pack kernel launch, two event operations and one NCCL enqueue per step; at
+    cfg 2 a pipelined step is ~130 us of GPU time, so that host work (not the 74 KB transfer) set the multi-GPU step
+    time.  Here the block kernel writes ``l_partition | region_features | hard_labels`` straight into the slot's
+    packed buffer (``CapturedGraphBlock(packed_small=...)``: the outputs are views of it, no pack kernel) and the graph
+    ends with ONE ``all_gather_into_tensor`` of that buffer, so a step stays a single ``cudaGraphLaunch`` on every
+    rank.  Each slot has its own communicator: graphs of different slots replay concurrently on different streams, and
+    collectives of ONE communicator must not be issued concurrently."""
+
+    def __init__(self, B: int, N: int, K: int, D: int, device, depth: int):
+        self.B, self.N, self.K, self.D, self.depth = B, N, K, D, depth
+        self.world = dist.get_world_size()
+        self.n_small = B * (1 + K * D + N)
+        self.packed = [torch.zeros(self.n_small, dtype=torch.float32, device=device) for _ in range(depth)]
+        self.gathered = [torch.zeros(self.world * self.n_small, dtype=torch.float32, device=device) for _ in range(depth)]
+        self.groups = [dist.new_group(backend="nccl") for _ in range(depth)]        # collective: same order on all ranks
+
+    def epilogue(self, slot: int):
+        def run(_outputs) -> None:
+            dist.all_gather_into_tensor(self.gathered[slot], self.packed[slot], group=self.groups[slot])
+        return run
+
+    def epilogues(self):
+        return [self.epilogue(i) for i in range(self.depth)]
+
+    def views(self, slot: int) -> GatheredOutputs:
+        """The slot's gathered result (valid on the slot's stream after its replay)."""
+        B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
+        g = self.gathered[slot].view(W, self.n_small)
+        loss = g[:, :B].reshape(W * B)
+        reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
+        lab = g[:, B + B * K * D:].reshape(W * B, N).view(torch.int32)
+        return GatheredOutputs(loss, reg, lab)

@@ -30,7 +30,11 @@ class CapturedGraphBlock:
 
     def __init__(self, block: GraphBlock, example: torch.Tensor, image_size: Optional[Tuple[int, int]] = None,
                  out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, want_dense: bool = True,
-                 warmup: int = 2, shards: int = 1):
+                 warmup: int = 2, shards: int = 1, packed_small: Optional[torch.Tensor] = None, epilogue=None):
+        """``packed_small``: flat fp32 buffer of ``B*(1 + K*D + N)`` elements; the small per-image outputs
+        (``l_partition | region_features | hard_labels``) are then VIEWS of it, i.e. the block kernel writes the
+        multi-GPU exchange payload in place (``distributed.CapturedGather``).  ``epilogue(outputs)``: recorded at the
+        end of the graph (e.g. the all-gather of ``packed_small``), so a step stays ONE driver call."""
         if not example.is_cuda:
             raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
         if block.training and torch.is_grad_enabled():
@@ -42,18 +46,23 @@ class CapturedGraphBlock:
         dev = example.device
         B = example.shape[0]
         self.shards = max(1, min(int(shards), B))
+        self._packed, self._epilogue = packed_small, epilogue
         if self.shards > 1 and not self._shardable(example, image_size, want_dense, out):
             self.shards = 1
+        if packed_small is not None and not self._shardable(example, image_size, want_dense, out):
+            raise RuntimeError("packed_small needs the one-launch block kernel (shape not supported by mg_block_forward)")
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        if self.shards == 1:
+        if self.shards == 1 and packed_small is None:
             with torch.cuda.stream(side), torch.no_grad():
                 for _ in range(max(warmup, 1)):
-                    self._forward()
+                    self._warm()
             torch.cuda.current_stream(dev).wait_stream(side)
             self.graph = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(self.graph):
                 self.outputs: GraphBlockOutput = self._forward()
+                if epilogue is not None:
+                    epilogue(self.outputs)
             return
         self._alloc_shared_outputs(example, image_size, out, out_dtype, want_dense)
         self._branches = [torch.cuda.Stream(device=dev) for _ in range(self.shards)]
@@ -68,6 +77,11 @@ class CapturedGraphBlock:
     # -- single branch ------------------------------------------------------------------------------
     def _forward(self) -> GraphBlockOutput:
         return self.block(**{self.kind: self.static_in}, **self._kw)
+
+    def _warm(self) -> None:
+        out = self._forward()
+        if self._epilogue is not None:
+            self._epilogue(out)
 
     # -- parallel shards ----------------------------------------------------------------------------
     def _shardable(self, example, image_size, want_dense, out) -> bool:
@@ -99,9 +113,17 @@ class CapturedGraphBlock:
         f32 = dict(dtype=torch.float32, device=dev)
         self._h = torch.empty((B, N, D), **f32)
         self._S = torch.empty((B, N, K), **f32)
-        self._labels = torch.empty((B, N), dtype=torch.int32, device=dev)
-        self._loss = torch.empty(B, **f32)
-        self._rout = torch.empty((B, K, D), **f32)
+        if self._packed is not None:
+            pk = self._packed
+            if pk.dtype != torch.float32 or pk.numel() != B * (1 + K * D + N) or not pk.is_contiguous() or pk.device != dev:
+                raise ValueError(f"packed_small must be a contiguous float32 buffer of {B * (1 + K * D + N)} elements on {dev}")
+            self._loss = pk[:B]
+            self._rout = pk[B:B + B * K * D].view(B, K, D)
+            self._labels = pk[B + B * K * D:].view(torch.int32).view(B, N)
+        else:
+            self._labels = torch.empty((B, N), dtype=torch.int32, device=dev)
+            self._loss = torch.empty(B, **f32)
+            self._rout = torch.empty((B, K, D), **f32)
         dense_dtype = out_dtype if out_dtype is not None else example.dtype
         self._dense = out if (out is not None or not want_dense) else torch.empty((B, D, H, W), dtype=dense_dtype, device=dev)
         self.outputs = GraphBlockOutput(self._dense if want_dense else None, self._loss, self._S, self._labels, self._h,
@@ -129,6 +151,9 @@ class CapturedGraphBlock:
                 joins.append(ev)
         for ev in joins:
             main.wait_event(ev)
+        if self._epilogue is not None:
+            with torch.cuda.stream(main):
+                self._epilogue(self.outputs)
 
     def __call__(self, x: Optional[torch.Tensor] = None) -> GraphBlockOutput:
         if x is not None and x.data_ptr() != self.static_in.data_ptr():
@@ -155,7 +180,7 @@ class PipelinedGraphBlock:
 
     def __init__(self, block: GraphBlock, example: torch.Tensor, image_size: Optional[Tuple[int, int]] = None,
                  outs=None, out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, depth: int = 2,
-                 shards: int = 1, warmup: int = 2):
+                 shards: int = 1, warmup: int = 2, packed_small=None, epilogues=None):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         if outs is not None and len(outs) != depth:
@@ -163,7 +188,9 @@ class PipelinedGraphBlock:
         dev = example.device
         self.depth = depth
         self.runners = [CapturedGraphBlock(block, example, image_size, out=None if outs is None else outs[i],
-                                           out_dtype=out_dtype, want_dense=want_dense, warmup=warmup, shards=shards)
+                                           out_dtype=out_dtype, want_dense=want_dense, warmup=warmup, shards=shards,
+                                           packed_small=None if packed_small is None else packed_small[i],
+                                           epilogue=None if epilogues is None else epilogues[i])
                         for i in range(depth)]
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
         self.done = [None] * depth

@@ -654,3 +654,15 @@ def test_pipelined_graph_block_matches_eager(mg, depth, shards):
             assert torch.equal(ref.hard_labels, lab) and torch.equal(ref.region_features, reg)
     assert all(float(b[:, :32].abs().max()) == 0.0 for b in bufs)
     pipe.host_wait(0)
+
+
+def test_captured_gather_single_rank_group():
+    """The in-graph exchange (block kernel writes the packed payload in place, NCCL all-gather recorded in the step's
+    graph) on a 1-rank NCCL group, in a subprocess; the same script checks any world size under torchrun."""
+    import os, subprocess, sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["MASTER_PORT"] = "29541"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_captured_gather.py")], env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
