@@ -304,11 +304,12 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
     pt_mbar_wait(full0 + 8 * st, (uint32_t)((consumed / q) & 1));
     const int nr = min(A.rpc, cc.rows - cc.r0);
     const uint4* sp = reinterpret_cast<const uint4*>(ring + (size_t)st * A.stage_bytes) + lane;
-#pragma unroll
-    for (int p = 0; p < kPtMaxPasses; ++p) {
-      if (p < passes && p * 32 + lane < nvec) {
+    // runtime loop over the 512-byte column passes (ONE copy of the summing code: fully unrolling it per pass made the
+    // kernel instruction-cache bound); the pass's register accumulator is selected by predicated adds
+    for (int p = 0; p < passes; ++p) {
+      float part = 0.f;
+      if (p * 32 + lane < nvec) {
         const uint4* a0 = sp + p * 32;
-        float part = 0.f;
         int r = 0;
         for (; r + kPtUnroll <= nr; r += kPtUnroll) {
           uint4 u[kPtUnroll];
@@ -324,8 +325,10 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
           part += t[0];
         }
         for (; r < nr; ++r) part += pt_sum16<TX>(a0[r * rv]);
-        acc[p] += part;
       }
+#pragma unroll
+      for (int pp = 0; pp < kPtMaxPasses; ++pp)
+        if (pp == p) acc[pp] += part;
     }
     __syncwarp();                                             // every lane has read the buffer: lane 0 may re-arm it
     issue();
