@@ -47,8 +47,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--shards", type=int, default=1, help="parallel sub-batches inside the captured graph (ours arm)")
-    ap.add_argument("--pipeline-depth", type=int, default=2,
-                    help="independent steps in flight (PipelinedGraphBlock slots; 1 = one replay at a time)")
+    ap.add_argument("--pipeline-depth", type=int, default=0,
+                    help="independent steps in flight (PipelinedGraphBlock slots; 1 = one replay at a time; "
+                         "0 = default: 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
@@ -222,7 +223,10 @@ def run_ours(args):
     gen = torch.Generator().manual_seed(1000 + rank)
     fm_host = torch.randn(B, IN_DIM, H, W, generator=gen).to(dtype).pin_memory()
     fm_dev = fm_host.to(dev)
-    depth = max(1, args.pipeline_depth)
+    # three slots: with two, a slot's next step queues behind its own un-pool; with more than one rank the third slot
+    # also gives the per-step collective (ranks wait for the slowest one) a step of slack.  N=1: 131.1 / 124.9 / 125.1 us
+    # per step at depth 2 / 3 / 4.
+    depth = args.pipeline_depth if args.pipeline_depth > 0 else 3
     # one fusion buffer per pipeline slot: [0:32] decoder features, [32:96] F_g
     fusions = [torch.zeros(B, C_UNET + D_OUT, H, W, dtype=dtype, device=dev) for _ in range(depth)]
     f_g_slices = [f[:, C_UNET:] for f in fusions]
@@ -240,9 +244,12 @@ def run_ours(args):
     # slot's graph on the slot's own communicator: the block kernel writes the payload in place, a step is one driver call
     from mingraph_unet_b200.distributed import CapturedGather
     gather = CapturedGather(B, N, K_SEG, D_OUT, dev, depth) if world > 1 else None
+    # same output layout at every N: the small per-image outputs of a slot live in one packed buffer (the exchange payload)
+    packed_small = gather.packed if gather is not None else [
+        torch.zeros(B * (1 + K_SEG * D_OUT + N), dtype=torch.float32, device=dev) for _ in range(depth)]
     lc0 = _lib.launch_count()
     pipe = mg.PipelinedGraphBlock(blk, fm_dev, image_size=(H, W), outs=f_g_slices, shards=args.shards, depth=depth, warmup=2,
-                                  packed_small=None if gather is None else gather.packed,
+                                  packed_small=packed_small,
                                   epilogues=None if gather is None else gather.epilogues())
     runner = pipe.runners[0]
     per_step_kernels = (_lib.launch_count() - lc0 - 1) // (3 * depth)   # per slot: 2 warm-up passes + the recorded one (+1 weight prepare)

@@ -63,14 +63,14 @@ class GraphBlock(nn.Module):
                 feature_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, _block_outs=None,
                 f_unet_patches: Optional[torch.Tensor] = None, patch_labels_y: Optional[torch.Tensor] = None,
-                feature_loss_margin: float = 1.0) -> GraphBlockOutput:
+                feature_loss_margin: float = 1.0, _after_block=None) -> GraphBlockOutput:
         """Either ``node_features (B,N,in)`` + ``image_size (H,W)`` or a per-pixel ``feature_map
         (B,in,H,W)`` (patch-mean pooled to node features).  ``out`` may be a channel slice of a fusion
         buffer ``(B,Ctot,H,W)[:, c0:c0+D]``; the dense map is written there directly.
         ``f_unet_patches (B,N,D)`` + ``patch_labels_y (B,N)``: also return ``l_feature``, the reference's
         feature-consistency loss between them and the patch-GAT output (train_end_to_end.py:344,
         batch mean of the per-image sums)."""
-        res = self._forward(node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs)
+        res = self._forward(node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs, _after_block)
         if f_unet_patches is None:
             return res
         if patch_labels_y is None:
@@ -81,7 +81,8 @@ class GraphBlock(nn.Module):
         return res._replace(l_feature=feature_loss_apply(f_unet_patches, res.patch_features, patch_labels_y,
                                                          float(feature_loss_margin)))
 
-    def _forward(self, node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs) -> GraphBlockOutput:
+    def _forward(self, node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs,
+                 _after_block=None) -> GraphBlockOutput:
         if (node_features is None) == (feature_map is None):
             raise ValueError("pass exactly one of node_features / feature_map")
         if feature_map is not None:
@@ -125,6 +126,8 @@ class GraphBlock(nn.Module):
             h, S, labels, loss, _, G = ops.block_forward(
                 node_features, nph, npw, self._prepared(), D, layers[0].num_heads, layers[1].num_heads,
                 layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers), outs=_block_outs)
+            if _after_block is not None:
+                _after_block()          # the small outputs are final here; the un-pool below only reads them
         elif needs_autograd or (self.training and any(l.dropout_rate > 0 for l in layers)):
             # training: the same stages as differentiable ops (csrc/gat_backward.cu, ncut.cu, block_backward.cu)
             g = Graph.grid(nph, npw, dev, B)

@@ -46,7 +46,7 @@ class CapturedGraphBlock:
         dev = example.device
         B = example.shape[0]
         self.shards = max(1, min(int(shards), B))
-        self._packed, self._epilogue = packed_small, epilogue
+        self._packed, self._epilogue, self._epi_stream = packed_small, epilogue, None
         if self.shards > 1 and not self._shardable(example, image_size, want_dense, out):
             self.shards = 1
         if packed_small is not None and not self._shardable(example, image_size, want_dense, out):
@@ -138,22 +138,39 @@ class CapturedGraphBlock:
     def _forward_sharded(self, main: torch.cuda.Stream) -> None:
         fork = torch.cuda.Event()
         fork.record(main)
-        joins = []
+        joins, blk_done = [], []
+
+        def after_block():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(main.device))
+            blk_done.append(ev)
+
         for (lo, hi), st in zip(self._ranges, self._branches):
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 kw = dict(self._kw)
                 kw["out"] = self._dense[lo:hi] if self._dense is not None else None
                 self.block(**{self.kind: self.static_in[lo:hi]}, **kw,
-                           _block_outs=(self._h[lo:hi], self._S[lo:hi], self._labels[lo:hi], self._loss[lo:hi], self._rout[lo:hi]))
+                           _block_outs=(self._h[lo:hi], self._S[lo:hi], self._labels[lo:hi], self._loss[lo:hi], self._rout[lo:hi]),
+                           _after_block=after_block if self._epilogue is not None else None)
                 ev = torch.cuda.Event()
                 ev.record(st)
                 joins.append(ev)
+        if self._epilogue is not None:
+            # the epilogue (e.g. the all-gather of the packed small outputs) only needs the block kernels: it runs on its
+            # own branch of the graph, in parallel with the HBM-bound un-pool of the same step
+            if self._epi_stream is None:
+                self._epi_stream = torch.cuda.Stream(device=main.device)
+            es = self._epi_stream
+            for ev in blk_done:
+                es.wait_event(ev)
+            with torch.cuda.stream(es):
+                self._epilogue(self.outputs)
+                ev = torch.cuda.Event()
+                ev.record(es)
+                joins.append(ev)
         for ev in joins:
             main.wait_event(ev)
-        if self._epilogue is not None:
-            with torch.cuda.stream(main):
-                self._epilogue(self.outputs)
 
     def __call__(self, x: Optional[torch.Tensor] = None) -> GraphBlockOutput:
         if x is not None and x.data_ptr() != self.static_in.data_ptr():
