@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--pipeline-depth", type=int, default=0,
                     help="independent steps in flight (PipelinedGraphBlock slots; 1 = one replay at a time; "
                          "0 = default: 3)")
+    ap.add_argument("--exchange", default="stream", choices=["stream", "captured", "captured-parallel"],
+                    help="N>1: how the per-step all-gather of the small outputs is issued (see run_ours)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
@@ -235,38 +237,62 @@ def run_ours(args):
     host_region = [torch.empty(B, K_SEG, D_OUT, dtype=torch.float32).pin_memory() for _ in range(depth)]
     host_labels = [torch.empty(B, N, dtype=torch.int32).pin_memory() for _ in range(depth)]
 
-    # public API: the block recorded once into a CUDA graph (pool -> fused block kernel -> un-pool), replayed per step
-    # two independent half batches on parallel branches of the graph: the latency-bound cluster kernel of one half
-    # overlaps the HBM-bound pool / un-pool of the other
-    # consecutive steps are independent batches: `depth` recorded graphs (own buffers, own stream) are used round-robin
-    # so the HBM-bound un-pool of step i overlaps the pool + latency-bound cluster kernel of step i+1
-    # N>1: one NCCL all-gather per step of the small per-image outputs (never the dense map), recorded INSIDE each
-    # slot's graph on the slot's own communicator: the block kernel writes the payload in place, a step is one driver call
-    from mingraph_unet_b200.distributed import CapturedGather
-    gather = CapturedGather(B, N, K_SEG, D_OUT, dev, depth) if world > 1 else None
-    # same output layout at every N: the small per-image outputs of a slot live in one packed buffer (the exchange payload)
-    packed_small = gather.packed if gather is not None else [
+    # public API: the block recorded once into a CUDA graph (pool -> fused block kernel -> un-pool), replayed per step.
+    # Consecutive steps are independent batches: `depth` recorded graphs (own buffers, own stream) are used round-robin
+    # so the HBM-bound un-pool of step i overlaps the pool + latency-bound cluster kernel of step i+1.
+    # N>1: one NCCL all-gather per step of the small per-image outputs (never the dense map).
+    #   --exchange stream (default): packed on the step's stream, gathered on ONE side stream of ONE communicator, in
+    #       step order (distributed.OverlappedGather) — every collective is stream-ordered against the previous one.
+    #   --exchange captured / captured-parallel: the gather recorded inside each slot's graph on a per-slot communicator
+    #       (distributed.CapturedGather); faster (N=2: 230k / 256k vs 176k images/s) but collectives of different
+    #       communicators then run concurrently, and one 8-GPU run of the parallel variant hung — opt-in until diagnosed.
+    from mingraph_unet_b200.distributed import CapturedGather, OverlappedGather
+    captured = world > 1 and args.exchange.startswith("captured")
+    cgather = CapturedGather(B, N, K_SEG, D_OUT, dev, depth) if captured else None
+    gather = OverlappedGather(B, N, K_SEG, D_OUT, dev) if (world > 1 and not captured) else None
+    # same output layout at every N: the small per-image outputs of a slot live in one packed buffer
+    packed_small = cgather.packed if cgather is not None else [
         torch.zeros(B * (1 + K_SEG * D_OUT + N), dtype=torch.float32, device=dev) for _ in range(depth)]
     lc0 = _lib.launch_count()
     pipe = mg.PipelinedGraphBlock(blk, fm_dev, image_size=(H, W), outs=f_g_slices, shards=args.shards, depth=depth, warmup=2,
                                   packed_small=packed_small,
-                                  epilogues=None if gather is None else gather.epilogues())
+                                  epilogues=None if cgather is None else cgather.epilogues(),
+                                  epilogue_parallel=args.exchange == "captured-parallel")
     runner = pipe.runners[0]
     per_step_kernels = (_lib.launch_count() - lc0 - 1) // (3 * depth)   # per slot: 2 warm-up passes + the recorded one (+1 weight prepare)
 
     def exchange(slot, out):
-        pass                            # the gather is part of the replayed graph
+        if gather is not None:          # (captured modes: the gather is part of the replayed graph)
+            with torch.cuda.stream(pipe.stream(slot)):
+                gather.push(out.l_partition, out.region_features, out.hard_labels)
+            pipe.mark(slot)
 
     def step():
         slot, out = pipe.submit()       # static input already resident in HBM
         exchange(slot, out)
         return out
 
+    def close_region():
+        """Every outstanding step and every gather belongs to the region being closed."""
+        pipe.join()
+        if gather is not None:
+            gather.drain()
+
     def barrier():
-        pipe.join()                     # every outstanding step (and its in-graph gather) belongs to the region being closed
+        close_region()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if world > 1:
+        # fail fast instead of hanging the box if a collective never completes
+        def _abort():
+            sys.stderr.write("bench.py: rank %d made no progress for 240 s (stuck collective?); aborting\n" % rank)
+            sys.stderr.flush()
+            os._exit(3)
+        watchdog = threading.Timer(240.0, _abort)
+        watchdog.daemon = True
+        watchdog.start()
 
     # ---- device-resident timing (value) ------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -279,7 +305,7 @@ def run_ours(args):
     t_start.record()
     for _ in range(args.steps):
         step()
-    pipe.join()
+    close_region()
     t_end.record()
     barrier()
     sampler.stop()
@@ -358,7 +384,7 @@ def run_ours(args):
     e0.record()
     for _ in range(e2e_steps):
         e2e_step()
-    pipe.join()
+    close_region()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -392,7 +418,7 @@ def run_ours(args):
             "step_hbm_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
             "gpu_launches": int(launches), "launch_mode": "CUDA graph replay (%d kernels of libmingraph_b200.so per step, %d parallel shard branches per "
                                                        "step, %d independent steps in flight on round-robin streams)" % (per_step_kernels, runner.shards, depth),
-            "pipeline_depth": depth, "step_latency_ms": latency_ms,
+            "pipeline_depth": depth, "step_latency_ms": latency_ms, "exchange": args.exchange if world > 1 else "none (1 GPU)",
             "roofline": {"kernel": "unpool_vec_kernel (K7 nearest un-pool)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": unpool_bytes,

@@ -30,11 +30,16 @@ class CapturedGraphBlock:
 
     def __init__(self, block: GraphBlock, example: torch.Tensor, image_size: Optional[Tuple[int, int]] = None,
                  out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, want_dense: bool = True,
-                 warmup: int = 2, shards: int = 1, packed_small: Optional[torch.Tensor] = None, epilogue=None):
+                 warmup: int = 2, shards: int = 1, packed_small: Optional[torch.Tensor] = None, epilogue=None,
+                 epilogue_parallel: bool = False):
         """``packed_small``: flat fp32 buffer of ``B*(1 + K*D + N)`` elements; the small per-image outputs
         (``l_partition | region_features | hard_labels``) are then VIEWS of it, i.e. the block kernel writes the
         multi-GPU exchange payload in place (``distributed.CapturedGather``).  ``epilogue(outputs)``: recorded at the
-        end of the graph (e.g. the all-gather of ``packed_small``), so a step stays ONE driver call."""
+        end of the graph (e.g. the all-gather of ``packed_small``), so a step stays ONE driver call.
+        ``epilogue_parallel``: record the epilogue on its own branch right after the block kernel, beside the un-pool
+        (it only needs the small outputs).  Measured with the NCCL all-gather as epilogue: fine at 2 GPUs (256k images/s),
+        but one 8-GPU run HUNG (three slots = three communicators whose collectives then overlap each other and every
+        HBM kernel); undiagnosed, hence off by default."""
         if not example.is_cuda:
             raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
         if block.training and torch.is_grad_enabled():
@@ -47,6 +52,7 @@ class CapturedGraphBlock:
         B = example.shape[0]
         self.shards = max(1, min(int(shards), B))
         self._packed, self._epilogue, self._epi_stream = packed_small, epilogue, None
+        self._epi_parallel = bool(epilogue_parallel)
         if self.shards > 1 and not self._shardable(example, image_size, want_dense, out):
             self.shards = 1
         if packed_small is not None and not self._shardable(example, image_size, want_dense, out):
@@ -152,11 +158,11 @@ class CapturedGraphBlock:
                 kw["out"] = self._dense[lo:hi] if self._dense is not None else None
                 self.block(**{self.kind: self.static_in[lo:hi]}, **kw,
                            _block_outs=(self._h[lo:hi], self._S[lo:hi], self._labels[lo:hi], self._loss[lo:hi], self._rout[lo:hi]),
-                           _after_block=after_block if self._epilogue is not None else None)
+                           _after_block=after_block if (self._epilogue is not None and self._epi_parallel) else None)
                 ev = torch.cuda.Event()
                 ev.record(st)
                 joins.append(ev)
-        if self._epilogue is not None:
+        if self._epilogue is not None and self._epi_parallel:
             # the epilogue (e.g. the all-gather of the packed small outputs) only needs the block kernels: it runs on its
             # own branch of the graph, in parallel with the HBM-bound un-pool of the same step
             if self._epi_stream is None:
@@ -171,6 +177,9 @@ class CapturedGraphBlock:
                 joins.append(ev)
         for ev in joins:
             main.wait_event(ev)
+        if self._epilogue is not None and not self._epi_parallel:
+            with torch.cuda.stream(main):
+                self._epilogue(self.outputs)
 
     def __call__(self, x: Optional[torch.Tensor] = None) -> GraphBlockOutput:
         if x is not None and x.data_ptr() != self.static_in.data_ptr():
@@ -197,7 +206,7 @@ class PipelinedGraphBlock:
 
     def __init__(self, block: GraphBlock, example: torch.Tensor, image_size: Optional[Tuple[int, int]] = None,
                  outs=None, out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, depth: int = 2,
-                 shards: int = 1, warmup: int = 2, packed_small=None, epilogues=None):
+                 shards: int = 1, warmup: int = 2, packed_small=None, epilogues=None, epilogue_parallel: bool = False):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         if outs is not None and len(outs) != depth:
@@ -207,7 +216,8 @@ class PipelinedGraphBlock:
         self.runners = [CapturedGraphBlock(block, example, image_size, out=None if outs is None else outs[i],
                                            out_dtype=out_dtype, want_dense=want_dense, warmup=warmup, shards=shards,
                                            packed_small=None if packed_small is None else packed_small[i],
-                                           epilogue=None if epilogues is None else epilogues[i])
+                                           epilogue=None if epilogues is None else epilogues[i],
+                                           epilogue_parallel=epilogue_parallel)
                         for i in range(depth)]
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
         self.done = [None] * depth
