@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--pipeline-depth", type=int, default=0,
                     help="independent steps in flight (PipelinedGraphBlock slots; 1 = one replay at a time; "
                          "0 = default: 3)")
-    ap.add_argument("--exchange", default="stream", choices=["stream", "captured", "captured-parallel"],
+    ap.add_argument("--exchange", default="inline", choices=["inline", "stream", "captured", "captured-parallel"],
                     help="N>1: how the per-step all-gather of the small outputs is issued (see run_ours)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
@@ -241,17 +241,21 @@ def run_ours(args):
     # Consecutive steps are independent batches: `depth` recorded graphs (own buffers, own stream) are used round-robin
     # so the HBM-bound un-pool of step i overlaps the pool + latency-bound cluster kernel of step i+1.
     # N>1: one NCCL all-gather per step of the small per-image outputs (never the dense map).
-    #   --exchange stream (default): packed on the step's stream, gathered on ONE side stream of ONE communicator, in
-    #       step order (distributed.OverlappedGather) — every collective is stream-ordered against the previous one.
+    #   --exchange inline (default): the block kernel writes the packed payload in place and ONE all-gather per step is
+    #       enqueued from the step's own stream on ONE communicator (distributed.InlineGather): torch.distributed
+    #       serialises a group's collectives on its internal NCCL stream, in step order.
+    #   --exchange stream: packed by a cat kernel on the step's stream, gathered on one side stream of one communicator
+    #       (distributed.OverlappedGather): same ordering, more host work per step (N=2: 176k images/s, host-bound).
     #   --exchange captured / captured-parallel: the gather recorded inside each slot's graph on a per-slot communicator
     #       (distributed.CapturedGather); faster (N=2: 230k / 256k vs 176k images/s) but collectives of different
     #       communicators then run concurrently, and one 8-GPU run of the parallel variant hung — opt-in until diagnosed.
-    from mingraph_unet_b200.distributed import CapturedGather, OverlappedGather
+    from mingraph_unet_b200.distributed import CapturedGather, InlineGather, OverlappedGather
     captured = world > 1 and args.exchange.startswith("captured")
     cgather = CapturedGather(B, N, K_SEG, D_OUT, dev, depth) if captured else None
-    gather = OverlappedGather(B, N, K_SEG, D_OUT, dev) if (world > 1 and not captured) else None
+    igather = InlineGather(B, N, K_SEG, D_OUT, dev, depth) if (world > 1 and args.exchange == "inline") else None
+    gather = OverlappedGather(B, N, K_SEG, D_OUT, dev) if (world > 1 and args.exchange == "stream") else None
     # same output layout at every N: the small per-image outputs of a slot live in one packed buffer
-    packed_small = cgather.packed if cgather is not None else [
+    packed_small = cgather.packed if cgather is not None else igather.packed if igather is not None else [
         torch.zeros(B * (1 + K_SEG * D_OUT + N), dtype=torch.float32, device=dev) for _ in range(depth)]
     lc0 = _lib.launch_count()
     pipe = mg.PipelinedGraphBlock(blk, fm_dev, image_size=(H, W), outs=f_g_slices, shards=args.shards, depth=depth, warmup=2,
@@ -262,7 +266,10 @@ def run_ours(args):
     per_step_kernels = (_lib.launch_count() - lc0 - 1) // (3 * depth)   # per slot: 2 warm-up passes + the recorded one (+1 weight prepare)
 
     def exchange(slot, out):
-        if gather is not None:          # (captured modes: the gather is part of the replayed graph)
+        if igather is not None:         # one collective enqueue from the step's own stream, no pack kernel
+            igather.gather(slot, pipe.stream(slot))
+            pipe.mark(slot)
+        elif gather is not None:        # (captured modes: the gather is part of the replayed graph)
             with torch.cuda.stream(pipe.stream(slot)):
                 gather.push(out.l_partition, out.region_features, out.hard_labels)
             pipe.mark(slot)

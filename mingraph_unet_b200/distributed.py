@@ -179,3 +179,39 @@ class CapturedGather:
         reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
         lab = g[:, B + B * K * D:].reshape(W * B, N).view(torch.int32)
         return GatheredOutputs(loss, reg, lab)
+
+
+class InlineGather:
+    """The per-step all-gather issued straight from the step's own stream, on ONE communicator, with no pack kernel:
+    ``gather(slot, stream)`` all-gathers the slot's packed small-output buffer (the block kernel wrote
+    ``l_partition | region_features | hard_labels`` into it in place, ``CapturedGraphBlock(packed_small=...)``).
+
+    ``torch.distributed`` runs every collective of a process group on the group's internal NCCL stream, in issue order:
+    that stream waits for the caller's stream (the step's replay), and the caller's stream — whose next work is the
+    slot's replay ``depth`` steps later — waits for the collective.  So the gathers of all slots are serialised on one
+    communicator in step order (no concurrent collectives, unlike :class:`CapturedGather`), nothing blocks the other
+    slots, and the host pays one collective enqueue per step (``OverlappedGather`` additionally launches a pack kernel
+    and four event operations)."""
+
+    def __init__(self, B: int, N: int, K: int, D: int, device, depth: int, group: Optional[dist.ProcessGroup] = None):
+        self.B, self.N, self.K, self.D, self.depth, self.group = B, N, K, D, depth, group
+        self.world = dist.get_world_size(group)
+        self.n_small = B * (1 + K * D + N)
+        self.packed = [torch.zeros(self.n_small, dtype=torch.float32, device=device) for _ in range(depth)]
+        self.gathered = [torch.zeros(self.world * self.n_small, dtype=torch.float32, device=device) for _ in range(depth)]
+
+    def gather(self, slot: int, stream=None) -> None:
+        if stream is None:
+            dist.all_gather_into_tensor(self.gathered[slot], self.packed[slot], group=self.group)
+            return
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(self.gathered[slot], self.packed[slot], group=self.group)
+
+    def views(self, slot: int) -> GatheredOutputs:
+        """The slot's gathered result (valid on the stream ``gather`` was issued from)."""
+        B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
+        g = self.gathered[slot].view(W, self.n_small)
+        loss = g[:, :B].reshape(W * B)
+        reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
+        lab = g[:, B + B * K * D:].reshape(W * B, N).view(torch.int32)
+        return GatheredOutputs(loss, reg, lab)

@@ -160,6 +160,21 @@ for p in m.parameters():
     p.grad = torch.full_like(p, float(rank + 1))
 n = allreduce_graph_grads(m)
 assert n == 8 and all(torch.allclose(p.grad, torch.full_like(p, (world + 1) / 2)) for p in m.parameters())
+# InlineGather: the packed per-slot payload (what the block kernel writes in place) gathered in step order
+from mingraph_unet_b200.distributed import InlineGather
+if Bg % world == 0:
+    B = Bg // world
+    ig = InlineGather(B, N, K, D, "cpu", depth=3)
+    for step in range(5):
+        slot = step % 3
+        sl = slice(rank * B, (rank + 1) * B)
+        pk = ig.packed[slot]
+        pk[:B] = loss[sl] + step
+        pk[B:B + B * K * D] = reg[sl].reshape(-1)
+        pk[B + B * K * D:].view(torch.int32).copy_(lab[sl].reshape(-1))
+        ig.gather(slot)
+        v = ig.views(slot)
+        assert torch.equal(v.l_partition, loss + step) and torch.equal(v.region_features, reg) and torch.equal(v.hard_labels, lab)
 dist.destroy_process_group()
 print("OK", rank)
 """
