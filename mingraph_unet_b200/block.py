@@ -163,13 +163,40 @@ class GraphBlock(nn.Module):
             f_g = ops.unpool_nearest(G, labels, nph, npw, H, W, out=out, out_dtype=dense_dtype)
         return GraphBlockOutput(f_g, loss, S, labels, h, G, (nph, npw))
 
+    def __setattr__(self, name, value):
+        if isinstance(value, (nn.Module, nn.Parameter)):
+            self.__dict__["_weight_mods"] = None          # a sub-network was replaced: re-walk the module tree
+        super().__setattr__(name, value)
+
+    def _weight_linears(self):
+        """The 2 x heads ``nn.Linear`` modules of the three 1-layer networks, in blob order.  Walking the module tree
+        (``net.parameters()``) costs ~130 us of host time per call — as much as a whole pipelined step — so the walk is
+        cached; the parameters themselves are read from the modules' dicts on every call, so in-place updates,
+        ``load_state_dict`` (also ``assign=True``) and ``.to()`` are all seen.  Replacing a head module inside a
+        network (structural surgery) needs ``block._weight_mods = None``."""
+        mods = self.__dict__.get("_weight_mods")
+        if mods is None:
+            mods = []
+            for net in (self.patch_gat_model, self.segment_predictor.gnn_predictor, self.region_gat_model):
+                for hd in net.gat_layers[0].heads:
+                    mods.append(hd.W)
+                    mods.append(hd.a)
+            self.__dict__["_weight_mods"] = mods
+        return mods
+
+    def _weight_key(self):
+        key = []
+        for m in self._weight_linears():
+            p = m._parameters["weight"]
+            key.append((p.data_ptr(), p._version))
+        return tuple(key)
+
     def _prepared(self) -> torch.Tensor:
         """Weights re-arranged for the fused kernel, cached per weight version (one tiny launch when
         any parameter changed, e.g. after an optimizer step or ``load_state_dict``)."""
-        nets = (self.patch_gat_model, self.segment_predictor.gnn_predictor, self.region_gat_model)
-        ps = [p for net in nets for p in net.parameters()]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = self._weight_key()
         if self._prep_cache is None or self._prep_cache[0] != key:
+            nets = (self.patch_gat_model, self.segment_predictor.gnn_predictor, self.region_gat_model)
             stacks = []
             for net in nets:
                 heads = list(net.gat_layers[0].heads)

@@ -199,3 +199,33 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_prepared_weight_cache_tracks_every_kind_of_update(mg, monkeypatch):
+    """GraphBlock._prepared() re-arranges the weights only when a parameter changed.  The module-tree walk is cached (it
+    costs as much host time as a pipelined step), so every way weights can change must still be noticed."""
+    import time
+    calls = []
+    monkeypatch.setattr(mg.ops, "block_prepare", lambda *stacks, out=None: calls.append(1) or torch.zeros(1))
+    blk = mg.GraphBlock()
+    blk._prepared(); blk._prepared()
+    assert len(calls) == 1
+    with torch.no_grad():                                                    # optimizer-style in-place update
+        blk.region_gat_model.gat_layers[0].heads[3].a.weight.add_(1.0)
+    blk._prepared(); blk._prepared()
+    assert len(calls) == 2
+    blk.patch_gat_model.load_state_dict(mg.GATNetwork(20, 128, 64, 4).state_dict())           # copy into the same tensors
+    blk._prepared()
+    assert len(calls) == 3
+    blk.segment_predictor.gnn_predictor.load_state_dict(mg.GATNetwork(64, 32, 2, 2).state_dict(), assign=True)   # new tensors
+    blk._prepared()
+    assert len(calls) == 4
+    blk.region_gat_model = mg.GATNetwork(64, 128, 64, 4)                     # a sub-network replaced
+    blk._prepared(); blk._prepared()
+    assert len(calls) == 5
+    blk.double(); blk._prepared()                                            # .to()/.double() re-allocate the data
+    assert len(calls) == 6
+    t0 = time.perf_counter()
+    for _ in range(200):
+        blk._prepared()
+    assert len(calls) == 6 and (time.perf_counter() - t0) / 200 < 60e-6      # the per-step host cost stays small
