@@ -13,4 +13,9 @@ reference classes* run in the build container: ``tests/golden/make_golden.py``
 imports them from ``/root/reference`` and writes ``tests/golden/*.npz``; the
 CPU test-suite checks the restatement against those fixtures (and against the
 live reference whenever ``/root/reference`` is mounted).
+
+Two independently written restatements: ``restate.py`` (numpy / torch CPU ops, everything) and
+``restate_int.c`` (plain C, the integer / index arithmetic: grid and region edge lists, stable CSR,
+argmax labels, nearest un-pool indices; loaded through ``cint.py``); ``tests/test_oracle_c.py``
+checks them against each other and against the fixtures.
 """
