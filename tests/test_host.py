@@ -237,3 +237,33 @@ def test_prepared_weight_cache_tracks_every_kind_of_update(mg, monkeypatch):
     walk = best_of(lambda: tuple((p.data_ptr(), p._version) for net in nets for p in net.parameters()))
     cached = best_of(blk._prepared)
     assert len(calls) == 6 and cached < walk / 3, (cached, walk)            # the per-step host cost stays small
+
+
+def test_loss_modules_error_behaviour_on_cpu(mg):
+    """Argument checks of the f4 loss modules run before any device work, so they are testable here: same exceptions as
+    the reference (model/unet/feature_loss.py:91-101), and no CPU fallback."""
+    fl = mg.FeatureConsistencyLoss(margin=1.0)
+    x2 = torch.randn(6, 8)
+    # the reference's own call site (scripts/train_end_to_end.py:344) passes 2-D (N, D) tensors and dies in the shape
+    # unpacking at feature_loss.py:91 with a ValueError; the mirror keeps that contract
+    with pytest.raises(ValueError):
+        fl(x2, x2, torch.zeros(6))
+    x3 = torch.randn(2, 6, 8)
+    with pytest.raises(ValueError, match="must have same dimensions"):
+        fl(x3, torch.randn(2, 6, 9), torch.zeros(2, 6))
+    with pytest.raises(ValueError, match="is not \\(Batch, Num_Patches\\)"):
+        fl(x3, x3, torch.zeros(2, 7))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        fl(x3, x3, torch.zeros(2, 6))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        mg.TVLoss()(torch.rand(1, 1, 8, 8))
+    if ref_loader.available():
+        import importlib
+        ref_loader.load()
+        ref_fl = importlib.import_module("model.unet.feature_loss").FeatureConsistencyLoss(1.0)
+        with pytest.raises(ValueError):
+            ref_fl(x2, x2, torch.zeros(6))
+        with pytest.raises(ValueError, match="must have same dimensions"):
+            ref_fl(x3, torch.randn(2, 6, 9), torch.zeros(2, 6))
+        with pytest.raises(ValueError, match="is not \\(Batch, Num_Patches\\)"):
+            ref_fl(x3, x3, torch.zeros(2, 7))
