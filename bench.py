@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--pipeline-depth", type=int, default=0,
                     help="independent steps in flight (PipelinedGraphBlock slots; 1 = one replay at a time; "
                          "0 = default: 3)")
-    ap.add_argument("--exchange", default="inline", choices=["inline", "stream", "captured", "captured-parallel"],
+    ap.add_argument("--exchange", default="inline", choices=["inline", "stream", "captured", "captured-parallel", "p2p"],
                     help="N>1: how the per-step all-gather of the small outputs is issued (see run_ours)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
@@ -249,9 +249,13 @@ def run_ours(args):
     #   --exchange captured / captured-parallel: the gather recorded inside each slot's graph on a per-slot communicator
     #       (distributed.CapturedGather); faster (N=2: 230k / 256k vs 176k images/s) but collectives of different
     #       communicators then run concurrently, and one 8-GPU run of the parallel variant hung — opt-in until diagnosed.
-    from mingraph_unet_b200.distributed import CapturedGather, InlineGather, OverlappedGather
+    #   --exchange p2p: EXPERIMENTAL, not yet run on hardware — plain NVLink stores into every peer's symmetric buffer
+    #       by one kernel at the end of the step's graph (distributed.PeerGather, csrc/peer_push.cu); no collective.
+    from mingraph_unet_b200.distributed import CapturedGather, InlineGather, OverlappedGather, PeerGather
     captured = world > 1 and args.exchange.startswith("captured")
     cgather = CapturedGather(B, N, K_SEG, D_OUT, dev, depth) if captured else None
+    if world > 1 and args.exchange == "p2p":
+        cgather = PeerGather(B, N, K_SEG, D_OUT, dev, depth)       # same interface: .packed, .epilogues()
     igather = InlineGather(B, N, K_SEG, D_OUT, dev, depth) if (world > 1 and args.exchange == "inline") else None
     gather = OverlappedGather(B, N, K_SEG, D_OUT, dev) if (world > 1 and args.exchange == "stream") else None
     # same output layout at every N: the small per-image outputs of a slot live in one packed buffer
@@ -261,7 +265,7 @@ def run_ours(args):
     pipe = mg.PipelinedGraphBlock(blk, fm_dev, image_size=(H, W), outs=f_g_slices, shards=args.shards, depth=depth, warmup=2,
                                   packed_small=packed_small,
                                   epilogues=None if cgather is None else cgather.epilogues(),
-                                  epilogue_parallel=args.exchange == "captured-parallel")
+                                  epilogue_parallel=args.exchange in ("captured-parallel", "p2p"))
     runner = pipe.runners[0]
     per_step_kernels = (_lib.launch_count() - lc0 - 1) // (3 * depth)   # per slot: 2 warm-up passes + the recorded one (+1 weight prepare)
 

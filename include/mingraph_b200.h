@@ -239,6 +239,25 @@ MG_API int mg_tv_loss(const void* x, int dtype, int B, int C, int H, int W, floa
 MG_API int mg_tv_loss_backward(const void* x, int dtype, int B, int C, int H, int W, float weight, const float* grad_loss,
                                float* grad_x, mg_stream_t stream);
 
+/* ---- peer-memory exchange of the small per-image outputs (multi-GPU, scope row (e)) ----------------
+ * The batch shards by image (scripts/train_end_to_end.py:300-425 builds one graph per image), so the only
+ * per-step exchange is an all-gather of l_partition | region_features | hard_labels.  These two entry points do it
+ * over NVLink peer mappings instead of a collective call: every rank owns a symmetric "gathered" buffer and a
+ * signal pad, both mapped into every peer (peer_bufs_dev / peer_signals_dev: DEVICE arrays of `world` pointers,
+ * entry p = rank p's buffer / signal pad as seen from this GPU).
+ * mg_peer_push: copy nbytes from src into [dst_offset_bytes, +nbytes) of EVERY peer's buffer, then publish a
+ *   sequence number (seq[p] is incremented on the device, so the call is graph-replayable) at
+ *   peer_signals[p][flag_index] with a system-scope release.  seq: `world` uint32 owned by the caller, zeroed once.
+ *   Waits for nothing.
+ * mg_peer_wait: block the stream until my_signals[first_flag + r] has reached this consumer's own count for every
+ *   source rank r (wseq: `world` uint32, zeroed once); bounded spin (~2 s), on expiry status[0] = 1 (nullable).
+ * STATUS: compiled but not yet run on hardware (round-1 GPU budget was spent); opt-in. */
+MG_API int mg_peer_push(const void* src, int64_t nbytes, const void* const* peer_bufs_dev, int world,
+                        int64_t dst_offset_bytes, const void* const* peer_signals_dev, int64_t flag_index, uint32_t* seq,
+                        mg_stream_t stream);
+MG_API int mg_peer_wait(const uint32_t* my_signals, int64_t first_flag, int world, uint32_t* wseq, int32_t* status,
+                        mg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,3 +215,64 @@ class InlineGather:
         reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
         lab = g[:, B + B * K * D:].reshape(W * B, N).view(torch.int32)
         return GatheredOutputs(loss, reg, lab)
+
+
+class PeerGather:
+    """EXPERIMENTAL — compiled and wired, not yet run on hardware (the round-1 GPU budget was spent); opt-in via
+    ``bench.py --exchange p2p`` / ``tools/check_captured_gather.py --mode p2p``.
+
+    The per-step exchange of the small outputs as plain NVLink stores (``csrc/peer_push.cu``) instead of a collective:
+    every rank owns a symmetric gathered buffer (``depth`` slots x ``world`` slices) mapped into all peers through
+    ``torch.distributed._symmetric_memory``; the epilogue of a step's graph is ONE kernel that stores the slot's packed
+    payload into slice ``rank`` of every peer's buffer and publishes a sequence number.  No kernel of this scheme waits
+    for another GPU, so a slow rank never makes a fast rank hold SMs (the failure mode of concurrent NCCL kernels).
+    Consumers call ``wait(slot)`` exactly once per step before reading ``views(slot)``.  Flow control is the caller's:
+    a producer may overwrite slot ``s`` of a peer ``depth`` steps later, so a consumer that reads the gathered data must
+    keep ranks within ``depth`` steps of each other (the bench does not read it; its end-of-region barrier closes it)."""
+
+    def __init__(self, B: int, N: int, K: int, D: int, device, depth: int, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm
+        from . import ops
+        self._ops = ops
+        group = group if group is not None else dist.group.WORLD
+        self.B, self.N, self.K, self.D, self.depth = B, N, K, D, depth
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_small = B * (1 + K * D + N)
+        self.n_pad = (self.n_small + 3) // 4 * 4                      # 16-byte payloads
+        self._packed = [torch.zeros(self.n_pad, dtype=torch.float32, device=device) for _ in range(depth)]
+        self.packed = [p[:self.n_small] for p in self._packed]       # what the block kernel writes (views)
+        self._gathered = symm.empty(depth * self.world * self.n_pad, dtype=torch.float32, device=device)
+        self._flags = symm.empty(depth * self.world, dtype=torch.int32, device=device)
+        self._gathered.zero_()
+        self._flags.zero_()
+        self._h_buf = symm.rendezvous(self._gathered, group)
+        self._h_flag = symm.rendezvous(self._flags, group)
+        self._seq = torch.zeros(depth, self.world, dtype=torch.int32, device=device)
+        self._wseq = torch.zeros(depth, self.world, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                            # nobody pushes before every flag is zeroed
+
+    def epilogue(self, slot: int):
+        off = (slot * self.world + self.rank) * self.n_pad * 4
+        flag = slot * self.world + self.rank
+
+        def run(_outputs) -> None:
+            self._ops.peer_push(self._packed[slot], self._h_buf.buffer_ptrs_dev, self.world, off,
+                                self._h_flag.buffer_ptrs_dev, flag, self._seq[slot])
+        return run
+
+    def epilogues(self):
+        return [self.epilogue(i) for i in range(self.depth)]
+
+    def wait(self, slot: int) -> None:
+        """Current stream waits for every rank's payload of this slot's next step (call once per step)."""
+        self._ops.peer_wait(self._flags, slot * self.world, self.world, self._wseq[slot], self.status)
+
+    def views(self, slot: int) -> GatheredOutputs:
+        B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
+        g = self._gathered[slot * W * self.n_pad:(slot + 1) * W * self.n_pad].view(W, self.n_pad)
+        loss = g[:, :B].reshape(W * B)
+        reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
+        lab = g[:, B + B * K * D:self.n_small].reshape(W * B, N).view(torch.int32)
+        return GatheredOutputs(loss, reg, lab)

@@ -513,3 +513,28 @@ def tv_loss_backward(x: torch.Tensor, weight: float, grad_loss: torch.Tensor) ->
         call("mg_tv_loss_backward", x.data_ptr(), _dtype_code(x.dtype), B, C, H, W, float(weight), grad_loss.data_ptr(),
              gx.data_ptr(), _stream())
     return gx
+
+
+# ---------------------------------------------------------------------------------------------
+# peer-memory exchange (multi-GPU; csrc/peer_push.cu) — compiled, not yet run on hardware (opt-in)
+# ---------------------------------------------------------------------------------------------
+def peer_push(src: torch.Tensor, peer_bufs_dev: int, world: int, dst_offset_bytes: int, peer_signals_dev: int,
+              flag_index: int, seq: torch.Tensor) -> None:
+    """Store ``src`` (contiguous, a multiple of 16 bytes) into ``[dst_offset_bytes, +nbytes)`` of every peer's symmetric
+    buffer and publish the next sequence number at ``flag_index`` of every peer's flag buffer.  ``peer_bufs_dev`` /
+    ``peer_signals_dev``: device addresses of the per-rank pointer arrays (``_SymmetricMemory.buffer_ptrs_dev``);
+    ``seq``: ``world`` int32 on this device, zeroed once, advanced by the kernel."""
+    dev = _need_cuda(src, seq)
+    if not src.is_contiguous() or seq.numel() != world or seq.dtype != torch.int32:
+        raise ValueError("peer_push: src must be contiguous, seq must be `world` int32")
+    with torch.cuda.device(dev):
+        call("mg_peer_push", src.data_ptr(), src.numel() * src.element_size(), int(peer_bufs_dev), int(world),
+             int(dst_offset_bytes), int(peer_signals_dev), int(flag_index), seq.data_ptr(), _stream())
+
+
+def peer_wait(flags: torch.Tensor, first_flag: int, world: int, wseq: torch.Tensor, status: Optional[torch.Tensor] = None) -> None:
+    """Make the current stream wait until ``flags[first_flag + r]`` has reached this consumer's own count for every source
+    rank ``r`` (``wseq``: ``world`` int32, zeroed once, advanced by the kernel).  Bounded spin; ``status[0] = 1`` on expiry."""
+    dev = _need_cuda(flags, wseq, status)
+    with torch.cuda.device(dev):
+        call("mg_peer_wait", flags.data_ptr(), int(first_flag), int(world), wseq.data_ptr(), _ptr(status), _stream())

@@ -17,7 +17,9 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 import mingraph_unet_b200 as mg
-from mingraph_unet_b200.distributed import CapturedGather
+from mingraph_unet_b200.distributed import CapturedGather, PeerGather
+
+MODE = "p2p" if "--mode=p2p" in sys.argv or ("--mode" in sys.argv and sys.argv[sys.argv.index("--mode") + 1] == "p2p") else "captured"
 
 B, C, H, W, D, K, depth, steps = 4, 20, 128, 96, 64, 2, 2, 5
 N = (H // 16) * (W // 16)
@@ -29,16 +31,22 @@ def make_input(step, r):
     return torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(1000 * step + r)).to(dev)
 
 
-gather = CapturedGather(B, N, K, D, dev, depth)
+gather = CapturedGather(B, N, K, D, dev, depth) if MODE == "captured" else PeerGather(B, N, K, D, dev, depth)
 pipe = mg.PipelinedGraphBlock(blk, make_input(0, rank), image_size=(H, W), depth=depth, packed_small=gather.packed,
                               epilogues=gather.epilogues())
 got = []
 for s in range(steps):
     slot, out = pipe.submit(make_input(s, rank))
     with torch.cuda.stream(pipe.stream(slot)):
+        if MODE == "p2p":
+            gather.wait(slot)                 # every rank's payload of this step has landed
         g = gather.views(slot)
         got.append((g.l_partition.clone(), g.region_features.clone(), g.hard_labels.clone(), out.l_partition.clone()))
     pipe.mark(slot)
+    if MODE == "p2p" and (s + 1) % depth == 0:
+        pipe.join()
+        torch.cuda.synchronize()
+        dist.barrier()                        # flow control: no rank overwrites a slot a peer has not read yet
 pipe.join()
 torch.cuda.synchronize()
 ok = True
@@ -53,7 +61,7 @@ with torch.no_grad():
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("captured gather world=%d: %s" % (world, "OK" if int(flag) else "MISMATCH"), flush=True)
+    print("%s gather world=%d: %s" % (MODE, world, "OK" if int(flag) else "MISMATCH"), flush=True)
 # the slots' graphs hold NCCL kernels: leave without tearing the communicators down under them
 code = 0 if int(flag) else 1
 dist.barrier()
