@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -213,6 +214,22 @@ __device__ __forceinline__ float pt_sum16<__nv_bfloat16>(const uint4& u) {
   return lo + hi;
 }
 
+// Dynamic strip scheduling (MG_POOL_DYNAMIC=1; off by default: written after the round-1 GPU budget was spent, not yet
+// measured).  Counter pairs live in a small device array; a launch takes the next pair round-robin (a recorded graph
+// node keeps the pair it was recorded with; its replays are serialised), the kernel's last CTA re-arms the pair.
+__device__ int g_pool_counters[64][2];
+static int* pool_counters() {
+  static const int enabled = getenv("MG_POOL_DYNAMIC") ? atoi(getenv("MG_POOL_DYNAMIC")) : 0;
+  if (!enabled) return nullptr;
+  static int* base = nullptr;
+  static std::atomic<unsigned> next{0};
+  if (!base && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_pool_counters) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return base + 2 * (next.fetch_add(1) % 64);
+}
+
 struct PoolTmaArgs {
   const void* x;
   void* out;
@@ -221,7 +238,10 @@ struct PoolTmaArgs {
   int nstrips;      // B * Hp * C, strip s = (b * Hp + py) * C + c
   int stages;       // ring depth per warp
   int stage_bytes;  // multiple of 128
+  int* counters;    // null: static round-robin strips.  else {next strip, finished CTAs}: dynamic strip scheduling
 };
+
+constexpr int kPtFifo = 16;         // per-warp FIFO of fetched strip ids (dynamic scheduling), > stages + 1
 
 // walks the chunks of one warp's strips in order
 template <typename TX>
@@ -241,12 +261,10 @@ struct PtCursor {
     base = reinterpret_cast<const TX*>(A.x) + (((size_t)b * A.C + c) * A.Hf + y0) * A.Wf;
   }
   __device__ __forceinline__ bool valid(const PoolTmaArgs& A) const { return s < A.nstrips; }
-  __device__ __forceinline__ void next_chunk(const PoolTmaArgs& A) {
+  // advance by one chunk; returns true when the strip is exhausted (the caller then sets s and calls load)
+  __device__ __forceinline__ bool advance(const PoolTmaArgs& A) {
     r0 += A.rpc;
-    if (r0 >= rows) {
-      s += step;
-      load(A);
-    }
+    return r0 >= rows;
   }
 };
 
@@ -274,9 +292,36 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
   const float inv = 1.f / (float)(A.ph * A.pw);
   TO* out = reinterpret_cast<TO*>(A.out);
 
+  // Strip order.  Static: warp w of CTA b takes strips b + (w + 8 i) * grid.  Dynamic (A.counters): every warp draws
+  // its next strip from one global counter, so CTAs that become resident late (SMs held by a neighbouring step's
+  // cluster kernel) simply draw fewer strips; the issue cursor draws, the consume cursor follows through a small
+  // per-warp FIFO in shared memory (an id >= nstrips terminates both).
+  const bool dynamic = A.counters != nullptr;
+  int* fifo = reinterpret_cast<int*>(pt_smem + (size_t)kPtWarps * q * (A.stage_bytes + 8)) + warp * kPtFifo;
+  int tail = 0, head = 0;
+  auto draw = [&]() -> int {                                    // issue side: next strip id
+    int s = 0;
+    if (lane == 0) {
+      s = atomicAdd(A.counters, 1);
+      fifo[tail & (kPtFifo - 1)] = s;
+    }
+    ++tail;
+    __syncwarp();
+    return __shfl_sync(kFull, s, 0);
+  };
+  auto follow = [&]() -> int {                                  // consume side: same sequence, later
+    const int s = fifo[head & (kPtFifo - 1)];
+    ++head;
+    return s;
+  };
   PtCursor<TX> ic, cc;                                        // issue cursor (q chunks ahead), consume cursor
-  ic.s = cc.s = blockIdx.x + warp * gridDim.x;
   ic.step = cc.step = kPtWarps * gridDim.x;
+  if (dynamic) {
+    ic.s = draw();
+    cc.s = follow();
+  } else {
+    ic.s = cc.s = blockIdx.x + warp * gridDim.x;
+  }
   ic.load(A);
   cc.load(A);
   int issued = 0;
@@ -289,7 +334,10 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
       pt_bulk_g2s(ring0 + (uint32_t)st * (uint32_t)A.stage_bytes, ic.base + (size_t)ic.r0 * A.Wf, bytes, full0 + 8 * st, policy);
     }
     ++issued;
-    ic.next_chunk(A);
+    if (ic.advance(A)) {
+      ic.s = dynamic ? draw() : ic.s + ic.step;
+      ic.load(A);
+    }
   };
   for (int t = 0; t < q; ++t) issue();
 
@@ -346,7 +394,21 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
         }
       }
     }
-    cc.next_chunk(A);
+    if (cc.advance(A)) {
+      cc.s = dynamic ? follow() : cc.s + cc.step;
+      cc.load(A);
+    }
+  }
+  if (dynamic) {                                              // the last CTA to finish re-arms the counters
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(A.counters + 1, 1) == (int)gridDim.x - 1) {
+        A.counters[0] = 0;
+        A.counters[1] = 0;
+        __threadfence();
+      }
+    }
   }
 }
 
@@ -590,8 +652,8 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
     int stages = std::max(2, std::min(8, stages_env));
     int stage_bytes = std::max(row_bytes, std::max(1024, chunk_env)) / 128 * 128;
     stage_bytes = std::max(stage_bytes, (row_bytes + 127) / 128 * 128);
-    while (stages > 2 && (size_t)kPtWarps * stages * (stage_bytes + 8) > (size_t)kPtSmemBytes) --stages;
-    const size_t smem = (size_t)kPtWarps * stages * (stage_bytes + 8);
+    while (stages > 2 && (size_t)kPtWarps * stages * (stage_bytes + 8) + kPtWarps * kPtFifo * 4 > (size_t)kPtSmemBytes) --stages;
+    const size_t smem = (size_t)kPtWarps * stages * (stage_bytes + 8) + kPtWarps * kPtFifo * 4;
     if (fast && variant == 0 && smem <= (size_t)kPtSmemBytes && ceil_div(Wf / VEC, 32) <= kPtMaxPasses && lpp <= 32) {
       PoolTmaArgs A;
       A.x = x; A.out = out; A.C = C; A.Hf = Hf; A.Wf = Wf; A.ph = ph; A.pw = pw; A.Hp = Hp; A.Wp = Wp;
@@ -599,6 +661,7 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
       A.nstrips = B * Hp * C;
       A.stages = stages;
       A.stage_bytes = stage_bytes;
+      A.counters = pool_counters();
       auto kern = pool_patches_tma_kernel<TX, TO>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes) != cudaSuccess) {
         set_error("mg_pool_patches: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
