@@ -268,7 +268,7 @@ struct PtCursor {
   }
 };
 
-template <typename TX, typename TO>
+template <typename TX, typename TO, bool DYN>
 __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(const PoolTmaArgs A) {
   constexpr int VEC = Vec16<TX>::N;
   extern __shared__ __align__(128) unsigned char pt_smem[];
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
   // its next strip from one global counter, so CTAs that become resident late (SMs held by a neighbouring step's
   // cluster kernel) simply draw fewer strips; the issue cursor draws, the consume cursor follows through a small
   // per-warp FIFO in shared memory (an id >= nstrips terminates both).
-  const bool dynamic = A.counters != nullptr;
+  constexpr bool dynamic = DYN;                              // the static instantiation carries none of the dynamic code
   int* fifo = reinterpret_cast<int*>(pt_smem + (size_t)kPtWarps * q * (A.stage_bytes + 8)) + warp * kPtFifo;
   int tail = 0, head = 0;
   auto draw = [&]() -> int {                                    // issue side: next strip id
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
   };
   PtCursor<TX> ic, cc;                                        // issue cursor (q chunks ahead), consume cursor
   ic.step = cc.step = kPtWarps * gridDim.x;
-  if (dynamic) {
+  if constexpr (dynamic) {
     ic.s = draw();
     cc.s = follow();
   } else {
@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
     }
     ++issued;
     if (ic.advance(A)) {
-      ic.s = dynamic ? draw() : ic.s + ic.step;
+      if constexpr (dynamic) ic.s = draw();
+      else ic.s += ic.step;
       ic.load(A);
     }
   };
@@ -395,11 +396,12 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
       }
     }
     if (cc.advance(A)) {
-      cc.s = dynamic ? follow() : cc.s + cc.step;
+      if constexpr (dynamic) cc.s = follow();
+      else cc.s += cc.step;
       cc.load(A);
     }
   }
-  if (dynamic) {                                              // the last CTA to finish re-arms the counters
+  if constexpr (dynamic) {                                    // the last CTA to finish re-arms the counters
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -662,7 +664,7 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
       A.stages = stages;
       A.stage_bytes = stage_bytes;
       A.counters = pool_counters();
-      auto kern = pool_patches_tma_kernel<TX, TO>;
+      auto kern = A.counters ? pool_patches_tma_kernel<TX, TO, true> : pool_patches_tma_kernel<TX, TO, false>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes) != cudaSuccess) {
         set_error("mg_pool_patches: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
         return MG_ERR_CUDA;
