@@ -92,64 +92,6 @@ __global__ void __launch_bounds__(256) pool_patches_vec_kernel(const TX* __restr
   }
 }
 
-// strip path: warp task = one (image, channel, patch-row) strip = ph full rows, contiguous in memory
-// (ph * Wf elements).  The warp streams the strip with 16-byte loads, 2*kStripRows loads in flight per
-// lane, and folds each vector into its patch column; conditions as for the fast path plus Wf <= 64*VEC*?:
-// handled generally by looping over 32-vector chunks.  Block = NW warps = NW channels of one (b, py).
-constexpr int kStripRows = 8;
-template <typename TX, typename TO>
-__global__ void __launch_bounds__(256) pool_patches_strip_kernel(const TX* __restrict__ x, int C, int Hf, int Wf, int ph,
-                                                                 int pw, int Hp, int Wp, TO* __restrict__ out) {
-  constexpr int VEC = Vec16<TX>::N;
-  extern __shared__ float tile[];   // [Wp][nw + 1]
-  const int b = blockIdx.z, py = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int c = blockIdx.x * nw + warp;
-  const int lpp = pw / VEC, pp = 32 / lpp;
-  const int y0 = py * ph, rows = min(Hf, y0 + ph) - y0;
-  const float inv = 1.f / (float)(ph * pw);
-  const int nvec = Wf / VEC;
-  if (c < C) {
-    const TX* base = x + (((size_t)b * C + c) * Hf + y0) * Wf;
-    for (int xc0 = 0; xc0 < nvec; xc0 += 64) {               // two 32-vector chunks per pass
-      const int xa = xc0 + lane, xb = xc0 + 32 + lane;
-      const bool ina = xa < nvec, inb = xb < nvec;
-      float acca = 0.f, accb = 0.f;
-      for (int r0 = 0; r0 < rows; r0 += kStripRows) {
-        float pa[kStripRows], pb[kStripRows];
-#pragma unroll
-        for (int r = 0; r < kStripRows; ++r) {
-          const bool rk = r0 + r < rows;
-          const TX* rowp = base + (size_t)(r0 + r) * Wf;
-          pa[r] = (ina && rk) ? Vec16<TX>::sum(rowp + (size_t)xa * VEC) : 0.f;
-          pb[r] = (inb && rk) ? Vec16<TX>::sum(rowp + (size_t)xb * VEC) : 0.f;
-        }
-#pragma unroll
-        for (int st = kStripRows / 2; st > 0; st >>= 1)
-#pragma unroll
-          for (int r = 0; r < st; ++r) { pa[r] += pa[r + st]; pb[r] += pb[r + st]; }
-        acca += pa[0];
-        accb += pb[0];
-      }
-      for (int o = 1; o < lpp; o <<= 1) {
-        acca += __shfl_xor_sync(kFull, acca, o);
-        accb += __shfl_xor_sync(kFull, accb, o);
-      }
-      if ((lane & (lpp - 1)) == 0) {
-        const int pa_ = (xc0 / 32) * pp + lane / lpp, pb_ = pa_ + pp;
-        if (pa_ < Wp) tile[pa_ * (nw + 1) + warp] = acca * inv;
-        if (pb_ < Wp) tile[pb_ * (nw + 1) + warp] = accb * inv;
-      }
-    }
-  }
-  __syncthreads();
-  const int c0 = blockIdx.x * nw, ncc = min(nw, C - c0);
-  for (int idx = threadIdx.x; idx < Wp * ncc; idx += blockDim.x) {
-    const int px = idx / ncc, cc = idx - px * ncc;
-    out[((size_t)b * Hp * Wp + (size_t)py * Wp + px) * C + c0 + cc] = from_f32<TO>(tile[px * (nw + 1) + cc]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // TMA path (default when it applies): a (image, channel, patch-row) strip is ph FULL rows of the map = one contiguous
 // run of ph*Wf elements, so the feature map is a stream of contiguous strips.  Persistent CTAs (one per SM) take strips
@@ -645,6 +587,7 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
   const int lpp = pw / VEC;
   const bool fast = (pw % VEC == 0) && (Wf % VEC == 0) && lpp >= 1 && lpp <= 32 && (lpp & (lpp - 1)) == 0 &&
                     ((uintptr_t)x % 16 == 0);
+  // MG_POOL_VARIANT=-1 forces the LDG kernel below (A/B runs); default 0 = bulk-copy staged kernel where it applies
   static const int variant = getenv("MG_POOL_VARIANT") ? atoi(getenv("MG_POOL_VARIANT")) : 0;
   // default: TMA-staged persistent kernel (at least one whole row per ring buffer, <= 8 column passes per warp)
   const int row_bytes = Wf * (int)sizeof(TX);
@@ -673,13 +616,6 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
       kern<<<grid, kPtWarps * 32, smem, st>>>(A);
       return check_launch("pool_patches_tma_kernel");
     }
-  }
-  if (fast && variant >= 1 && (size_t)Wp * 9 * 4 <= 48 * 1024) {
-    const int nw = variant >= 2 ? variant : 4;             // warps (= channels) per block
-    dim3 grid(ceil_div(C, nw), Hp, B);
-    pool_patches_strip_kernel<TX, TO><<<grid, nw * 32, (size_t)Wp * (nw + 1) * 4, st>>>(
-        reinterpret_cast<const TX*>(x), C, Hf, Wf, ph, pw, Hp, Wp, reinterpret_cast<TO*>(out));
-    return check_launch("pool_patches_strip_kernel");
   }
   if (fast) {
     const int cg = std::min(C, pool_cc());
