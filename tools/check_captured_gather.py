@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Check of the in-graph multi-GPU exchange (distributed.CapturedGather + PipelinedGraphBlock) at any world size:
+"""Check of the multi-GPU exchange variants (distributed.CapturedGather / InlineGather / PeerGather + PipelinedGraphBlock;
+--mode captured | inline | p2p) at any world size:
 every rank pipelines several steps, then verifies that each step's GATHERED per-image outputs (loss, region features,
 labels of ALL ranks) equal what the eager block computes for every rank's input of that step (inputs are seeded by
 (step, rank), so each rank can recompute the others').  Launch: torchrun --nproc-per-node N tools/check_captured_gather.py,
@@ -17,9 +18,15 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 import mingraph_unet_b200 as mg
-from mingraph_unet_b200.distributed import CapturedGather, PeerGather
+from mingraph_unet_b200.distributed import CapturedGather, InlineGather, PeerGather
 
-MODE = "p2p" if "--mode=p2p" in sys.argv or ("--mode" in sys.argv and sys.argv[sys.argv.index("--mode") + 1] == "p2p") else "captured"
+MODE = "captured"                       # --mode captured | inline | p2p
+for i, a in enumerate(sys.argv):
+    if a.startswith("--mode="):
+        MODE = a.split("=", 1)[1]
+    elif a == "--mode" and i + 1 < len(sys.argv):
+        MODE = sys.argv[i + 1]
+assert MODE in ("captured", "inline", "p2p"), MODE
 
 B, C, H, W, D, K, depth, steps = 4, 20, 128, 96, 64, 2, 2, 5
 N = (H // 16) * (W // 16)
@@ -31,12 +38,15 @@ def make_input(step, r):
     return torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(1000 * step + r)).to(dev)
 
 
-gather = CapturedGather(B, N, K, D, dev, depth) if MODE == "captured" else PeerGather(B, N, K, D, dev, depth)
+gather = {"captured": CapturedGather, "inline": InlineGather, "p2p": PeerGather}[MODE](B, N, K, D, dev, depth)
 pipe = mg.PipelinedGraphBlock(blk, make_input(0, rank), image_size=(H, W), depth=depth, packed_small=gather.packed,
-                              epilogues=gather.epilogues())
+                              epilogues=None if MODE == "inline" else gather.epilogues(),
+                              epilogue_parallel=MODE == "p2p")
 got = []
 for s in range(steps):
     slot, out = pipe.submit(make_input(s, rank))
+    if MODE == "inline":
+        gather.gather(slot, pipe.stream(slot))        # one collective enqueue from the step's own stream
     with torch.cuda.stream(pipe.stream(slot)):
         if MODE == "p2p":
             gather.wait(slot)                 # every rank's payload of this step has landed
