@@ -250,7 +250,7 @@ MG_API int mg_tv_loss_backward(const void* x, int dtype, int B, int C, int H, in
  *   peer_signals[p][flag_index] with a system-scope release.  seq: `world` uint32 owned by the caller, zeroed once.
  *   Waits for nothing.
  * mg_peer_wait: block the stream until my_signals[first_flag + r] has reached this consumer's own count for every
- *   source rank r (wseq: `world` uint32, zeroed once); bounded spin (~2 s), on expiry status[0] = 1 (nullable).
+ *   source rank r (wseq: `world` uint32, zeroed once); bounded spin (a few seconds), on expiry status[0] = 1 (nullable).
  * STATUS: compiled but not yet run on hardware (round-1 GPU budget was spent); opt-in. */
 MG_API int mg_peer_push(const void* src, int64_t nbytes, const void* const* peer_bufs_dev, int world,
                         int64_t dst_offset_bytes, const void* const* peer_signals_dev, int64_t flag_index, uint32_t* seq,

@@ -72,8 +72,9 @@ int mg_peer_push(const void* src, int64_t nbytes, const void* const* peer_bufs_d
 
 int mg_peer_wait(const uint32_t* my_signals, int64_t first_flag, int world, uint32_t* wseq, int32_t* status, mg_stream_t stream) {
   MG_REQUIRE(my_signals && wseq && world > 0 && world <= 64, MG_ERR_INVALID, "mg_peer_wait: bad arguments");
-  // ~2 s at 64 ns per poll plus the load round trip: a missing peer shows up in status[0], not as a hung GPU
-  peer_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(my_signals, first_flag, world, wseq, status, 8ull * 1000 * 1000);
+  // 2 M polls of (64 ns sleep + one system-scope load, ~1 us) = a few seconds: a missing peer shows up in status[0],
+  // not as a hung GPU
+  peer_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(my_signals, first_flag, world, wseq, status, 2ull * 1000 * 1000);
   return check_launch("peer_wait_kernel");
 }
 
