@@ -279,6 +279,7 @@ def run_ours(args):
             pipe.mark(slot)
 
     def step():
+        beat[0] = time.monotonic()
         slot, out = pipe.submit()       # static input already resident in HBM
         exchange(slot, out)
         return out
@@ -295,15 +296,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # fail fast instead of hanging the box if a collective never completes: a heartbeat the step functions advance; the
+    # watchdog thread aborts the rank when it has not moved for 240 s (progress-based, so long --steps runs are fine)
+    beat = [time.monotonic()]
     if world > 1:
-        # fail fast instead of hanging the box if a collective never completes
-        def _abort():
-            sys.stderr.write("bench.py: rank %d made no progress for 240 s (stuck collective?); aborting\n" % rank)
-            sys.stderr.flush()
-            os._exit(3)
-        watchdog = threading.Timer(240.0, _abort)
-        watchdog.daemon = True
-        watchdog.start()
+        def _watch():
+            while True:
+                time.sleep(5.0)
+                if time.monotonic() - beat[0] > 240.0:
+                    sys.stderr.write("bench.py: rank %d made no progress for 240 s (stuck collective?); aborting\n" % rank)
+                    sys.stderr.flush()
+                    os._exit(3)
+        threading.Thread(target=_watch, daemon=True).start()
 
     # ---- device-resident timing (value) ------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -335,11 +339,18 @@ def run_ours(args):
     note = "sampled during the timed region"
     if len(sampler.samples) < 5:        # very short timed region: keep the same load running while sampling
         sampler.start()
-        t_until = time.time() + 1.0
-        while time.time() < t_until:            # rank-local, time-based loop: NO collectives in here
-            for _ in range(20):
-                pipe.submit()
-            torch.cuda.synchronize()
+        if cgather is None:
+            t_until = time.time() + 1.0
+            while time.time() < t_until:        # rank-local, time-based loop: no collective is part of a submit here
+                for _ in range(20):
+                    pipe.submit()
+                torch.cuda.synchronize()
+        else:                                   # the slots' graphs contain the exchange: same count on every rank
+            for _ in range(200):
+                beat[0] = time.monotonic()
+                for _ in range(20):
+                    pipe.submit()
+                torch.cuda.synchronize()
         sampler.stop()
         note = "timed region shorter than the NVML sampling period; sampled under the same load right after it"
 
@@ -359,6 +370,7 @@ def run_ours(args):
     with torch.no_grad():
         prep = blk._prepared()
         for i in range(args.steps + 3):
+            beat[0] = time.monotonic()
             torch.cuda._sleep(400_000)      # ~0.2 ms spin so the host runs ahead and the three launches queue back to back
             e0 = ev()
             x = mg.ops.pool_patches(fm_shard, PATCH, PATCH)
@@ -376,6 +388,7 @@ def run_ours(args):
 
     # ---- end-to-end through the public API with host buffers (e2e) ---------------------------
     def e2e_step():
+        beat[0] = time.monotonic()
         slot, out = pipe.submit(fm_host)                        # H2D of this step's input from pinned memory
         exchange(slot, out)
         with torch.cuda.stream(pipe.stream(slot)):              # D2H of the step's results, on the step's stream
