@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--pipeline-depth", type=int, default=0,
                     help="independent steps in flight (PipelinedGraphBlock slots; 1 = one replay at a time; "
                          "0 = default: 3)")
-    ap.add_argument("--exchange", default="inline", choices=["inline", "stream", "captured", "captured-parallel", "p2p"],
+    ap.add_argument("--exchange", default="inline", choices=["inline", "stream", "captured", "captured-parallel", "p2p", "bucketed"],
                     help="N>1: how the per-step all-gather of the small outputs is issued (see run_ours)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
@@ -228,7 +228,7 @@ def run_ours(args):
     # three slots: with two, a slot's next step queues behind its own un-pool; with more than one rank the third slot
     # also gives the per-step collective (ranks wait for the slowest one) a step of slack.  N=1: 131.1 / 124.9 / 125.1 us
     # per step at depth 2 / 3 / 4.
-    depth = args.pipeline_depth if args.pipeline_depth > 0 else 3
+    depth = args.pipeline_depth if args.pipeline_depth > 0 else (4 if (world > 1 and args.exchange == "bucketed") else 3)
     # one fusion buffer per pipeline slot: [0:32] decoder features, [32:96] F_g
     fusions = [torch.zeros(B, C_UNET + D_OUT, H, W, dtype=dtype, device=dev) for _ in range(depth)]
     f_g_slices = [f[:, C_UNET:] for f in fusions]
@@ -249,17 +249,22 @@ def run_ours(args):
     #   --exchange captured / captured-parallel: the gather recorded inside each slot's graph on a per-slot communicator
     #       (distributed.CapturedGather); faster (N=2: 230k / 256k vs 176k images/s) but collectives of different
     #       communicators then run concurrently, and one 8-GPU run of the parallel variant hung — opt-in until diagnosed.
+    #   --exchange bucketed: NOT YET TIMED ON HARDWARE — the slots' payloads are views of one ring and a bucket of
+    #       consecutive steps is gathered by ONE collective on a side stream (distributed.BucketedGather; depth 4, buckets
+    #       of 2 by default): half the collective enqueues and rendezvous per step, results up to one step late.
     #   --exchange p2p: EXPERIMENTAL, not yet run on hardware — plain NVLink stores into every peer's symmetric buffer
     #       by one kernel at the end of the step's graph (distributed.PeerGather, csrc/peer_push.cu); no collective.
-    from mingraph_unet_b200.distributed import CapturedGather, InlineGather, OverlappedGather, PeerGather
+    from mingraph_unet_b200.distributed import BucketedGather, CapturedGather, InlineGather, OverlappedGather, PeerGather
     captured = world > 1 and args.exchange.startswith("captured")
     cgather = CapturedGather(B, N, K_SEG, D_OUT, dev, depth) if captured else None
     if world > 1 and args.exchange == "p2p":
         cgather = PeerGather(B, N, K_SEG, D_OUT, dev, depth)       # same interface: .packed, .epilogues()
     igather = InlineGather(B, N, K_SEG, D_OUT, dev, depth) if (world > 1 and args.exchange == "inline") else None
     gather = OverlappedGather(B, N, K_SEG, D_OUT, dev) if (world > 1 and args.exchange == "stream") else None
+    bgather = BucketedGather(B, N, K_SEG, D_OUT, dev, depth) if (world > 1 and args.exchange == "bucketed") else None
     # same output layout at every N: the small per-image outputs of a slot live in one packed buffer
-    packed_small = cgather.packed if cgather is not None else igather.packed if igather is not None else [
+    packed_small = cgather.packed if cgather is not None else igather.packed if igather is not None else \
+        bgather.packed if bgather is not None else [
         torch.zeros(B * (1 + K_SEG * D_OUT + N), dtype=torch.float32, device=dev) for _ in range(depth)]
     lc0 = _lib.launch_count()
     pipe = mg.PipelinedGraphBlock(blk, fm_dev, image_size=(H, W), outs=f_g_slices, shards=args.shards, depth=depth, warmup=2,
@@ -273,6 +278,8 @@ def run_ours(args):
         if igather is not None:         # one collective enqueue from the step's own stream, no pack kernel
             igather.gather(slot, pipe.stream(slot))
             pipe.mark(slot)
+        elif bgather is not None:       # one collective per bucket of steps, on a side stream
+            bgather.after(slot, pipe.stream(slot))
         elif gather is not None:        # (captured modes: the gather is part of the replayed graph)
             with torch.cuda.stream(pipe.stream(slot)):
                 gather.push(out.l_partition, out.region_features, out.hard_labels)
@@ -280,6 +287,8 @@ def run_ours(args):
 
     def step():
         beat[0] = time.monotonic()
+        if bgather is not None:
+            bgather.before(pipe.next_slot, pipe.stream(pipe.next_slot))
         slot, out = pipe.submit()       # static input already resident in HBM
         exchange(slot, out)
         return out
@@ -289,6 +298,9 @@ def run_ours(args):
         pipe.join()
         if gather is not None:
             gather.drain()
+        if bgather is not None:         # same step count on every rank: a partly filled bucket is gathered here
+            bgather.flush()
+            bgather.drain()
 
     def barrier():
         close_region()
@@ -389,6 +401,8 @@ def run_ours(args):
     # ---- end-to-end through the public API with host buffers (e2e) ---------------------------
     def e2e_step():
         beat[0] = time.monotonic()
+        if bgather is not None:
+            bgather.before(pipe.next_slot, pipe.stream(pipe.next_slot))
         slot, out = pipe.submit(fm_host)                        # H2D of this step's input from pinned memory
         exchange(slot, out)
         with torch.cuda.stream(pipe.stream(slot)):              # D2H of the step's results, on the step's stream

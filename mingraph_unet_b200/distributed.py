@@ -217,6 +217,96 @@ class InlineGather:
         return GatheredOutputs(loss, reg, lab)
 
 
+class BucketedGather:
+    """The exchange of several consecutive steps in ONE collective (opt-in, ``bench.py --exchange bucketed``; written
+    after the round-1 GPU budget was spent — host logic covered by the gloo world-2 test, not yet timed on hardware).
+
+    The per-step payload is 74 KB at cfg 2 while a pipelined step is ~125 us of GPU time: a per-step collective costs
+    the host one NCCL enqueue and every rank one rendezvous per step.  Here the ``depth`` pipeline slots' packed
+    buffers are consecutive views of ONE ring; the ring is cut into buckets of ``bucket`` consecutive slots and a
+    bucket is gathered with one ``all_gather_into_tensor`` on a side stream after its LAST slot's step was enqueued
+    (the side stream waits for the events of exactly the bucket's steps).  A slot's next replay (``depth`` steps later)
+    waits for the gather that read its buffer, so with ``depth >= 2 * bucket`` that gather has the other buckets' steps
+    as slack.  One communicator, collectives in step order (same liveness argument as :class:`InlineGather`); results
+    of a step become visible up to ``bucket - 1`` steps late — a throughput, not a latency, optimisation.
+
+    Use: ``before(slot, stream)`` ahead of the slot's submit, ``after(slot, stream)`` behind it; ``flush()`` gathers a
+    partly filled bucket (end of a run); ``views(slot)`` as for the other variants."""
+
+    def __init__(self, B: int, N: int, K: int, D: int, device, depth: int, bucket: Optional[int] = None,
+                 group: Optional[dist.ProcessGroup] = None):
+        if bucket is None:
+            bucket = max(1, depth // 2)
+        if bucket < 1 or depth % bucket != 0:
+            raise ValueError("depth must be a multiple of bucket")
+        self.B, self.N, self.K, self.D, self.depth, self.bucket, self.group = B, N, K, D, depth, bucket, group
+        self.world = dist.get_world_size(group)
+        self.n_small = B * (1 + K * D + N)
+        self._cuda = torch.device(device).type == "cuda"
+        self._ring = torch.zeros(depth * self.n_small, dtype=torch.float32, device=device)
+        self.packed = [self._ring[i * self.n_small:(i + 1) * self.n_small] for i in range(depth)]
+        nb = depth // bucket
+        self.gathered = [torch.zeros(self.world * bucket * self.n_small, dtype=torch.float32, device=device)
+                         for _ in range(nb)]
+        self.side = torch.cuda.Stream(device=device) if self._cuda else None
+        self._ready = [torch.cuda.Event() for _ in range(depth)] if self._cuda else None
+        self._done = [torch.cuda.Event() for _ in range(nb)] if self._cuda else None
+        self._done_valid = [False] * nb
+        self._pending: List[int] = []            # slots stepped since the last gather, in step order
+
+    def before(self, slot: int, stream=None) -> None:
+        """The slot's stream waits for the gather that last read the slot's packed buffer."""
+        b = slot // self.bucket
+        if self._cuda and self._done_valid[b]:
+            stream.wait_event(self._done[b])
+
+    def after(self, slot: int, stream=None) -> None:
+        """Call after the slot's step was enqueued on ``stream``; gathers the bucket when this was its last slot."""
+        if self._pending and (slot != self._pending[-1] + 1 or slot // self.bucket != self._pending[0] // self.bucket):
+            raise RuntimeError("BucketedGather: slots must be stepped round-robin (0, 1, ..., depth-1, 0, ...)")
+        if self._cuda:
+            self._ready[slot].record(stream)
+        self._pending.append(slot)
+        if (slot + 1) % self.bucket == 0:
+            self._gather()
+
+    def flush(self) -> None:
+        """Gather a partly filled bucket (collective: every rank must call it at the same step)."""
+        if self._pending:
+            self._gather()
+
+    def _gather(self) -> None:
+        b = self._pending[0] // self.bucket
+        src = self._ring[b * self.bucket * self.n_small:(b + 1) * self.bucket * self.n_small]
+        if self._cuda:
+            for s in self._pending:
+                self.side.wait_event(self._ready[s])
+            with torch.cuda.stream(self.side):
+                dist.all_gather_into_tensor(self.gathered[b], src, group=self.group)
+                self._done[b].record(self.side)
+            self._done_valid[b] = True
+        else:
+            dist.all_gather_into_tensor(self.gathered[b], src, group=self.group)
+        self._pending = []
+
+    def drain(self) -> None:
+        """Current stream waits for every gather issued so far."""
+        if self._cuda:
+            cur = torch.cuda.current_stream()
+            for ok, ev in zip(self._done_valid, self._done):
+                if ok:
+                    cur.wait_event(ev)
+
+    def views(self, slot: int) -> GatheredOutputs:
+        """The gathered result of the slot's most recent GATHERED step (valid after ``drain()`` / on the side stream)."""
+        B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
+        g = self.gathered[slot // self.bucket].view(W, self.bucket, self.n_small)[:, slot % self.bucket]
+        loss = g[:, :B].reshape(W * B)
+        reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
+        lab = g[:, B + B * K * D:].view(torch.int32).reshape(W * B, N)
+        return GatheredOutputs(loss, reg, lab)
+
+
 class PeerGather:
     """EXPERIMENTAL — compiled and wired, not yet run on hardware (the round-1 GPU budget was spent); opt-in via
     ``bench.py --exchange p2p`` / ``tools/check_captured_gather.py --mode p2p``.

@@ -230,6 +230,11 @@ class PipelinedGraphBlock:
     def stream(self, slot: int) -> torch.cuda.Stream:
         return self.streams[slot]
 
+    @property
+    def next_slot(self) -> int:
+        """The slot the next ``submit`` will use."""
+        return self._turn
+
     def submit(self, x: Optional[torch.Tensor] = None):
         i = self._turn
         self._turn = (i + 1) % self.depth

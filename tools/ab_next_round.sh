@@ -2,7 +2,7 @@
 # A/B matrix for the variants written after the round-1 GPU budget was spent.  Every command is wrapped in `timeout`;
 # results land in gpurun_out/ab_*.log.  Usage (from the repo root):
 #   gpurun --timeout 600 -- 'bash tools/ab_next_round.sh 1'            # one GPU: dynamic strip scheduling of the pool kernel
-#   gpurun --gpus 2 --timeout 600 -- 'bash tools/ab_next_round.sh 2'   # two GPUs: exchange variants (inline / captured / p2p)
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/ab_next_round.sh 2'   # two GPUs: exchange variants (inline / captured / bucketed / p2p)
 #   gpurun --gpus 8 --timeout 400 -- 'bash tools/ab_next_round.sh 8 inline'   # one variant at a time at 8 GPUs
 N=${1:-1}
 mkdir -p gpurun_out
@@ -25,7 +25,7 @@ if [ "$N" = "1" ]; then
     summ gpurun_out/ab_dyn$dyn.log
   done
 else
-  modes=${2:-"inline captured p2p"}
+  modes=${2:-"inline captured bucketed p2p"}
   port=29600
   for m in $modes; do
     if [ "$m" != "captured" ] || [ "$N" = "2" ]; then

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Check of the multi-GPU exchange variants (distributed.CapturedGather / InlineGather / PeerGather + PipelinedGraphBlock;
---mode captured | inline | p2p) at any world size:
+"""Check of the multi-GPU exchange variants (distributed.CapturedGather / InlineGather / PeerGather / BucketedGather +
+PipelinedGraphBlock; --mode captured | inline | p2p | bucketed) at any world size:
 every rank pipelines several steps, then verifies that each step's GATHERED per-image outputs (loss, region features,
 labels of ALL ranks) equal what the eager block computes for every rank's input of that step (inputs are seeded by
 (step, rank), so each rank can recompute the others').  Launch: torchrun --nproc-per-node N tools/check_captured_gather.py,
@@ -18,17 +18,19 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 import mingraph_unet_b200 as mg
-from mingraph_unet_b200.distributed import CapturedGather, InlineGather, PeerGather
+from mingraph_unet_b200.distributed import BucketedGather, CapturedGather, InlineGather, PeerGather
 
-MODE = "captured"                       # --mode captured | inline | p2p
+MODE = "captured"                       # --mode captured | inline | p2p | bucketed
 for i, a in enumerate(sys.argv):
     if a.startswith("--mode="):
         MODE = a.split("=", 1)[1]
     elif a == "--mode" and i + 1 < len(sys.argv):
         MODE = sys.argv[i + 1]
-assert MODE in ("captured", "inline", "p2p"), MODE
+assert MODE in ("captured", "inline", "p2p", "bucketed"), MODE
 
 B, C, H, W, D, K, depth, steps = 4, 20, 128, 96, 64, 2, 2, 5
+if MODE == "bucketed":
+    depth, steps = 4, 11                # buckets of two slots; the last step leaves a partly filled bucket
 N = (H // 16) * (W // 16)
 torch.manual_seed(1234)
 blk = mg.GraphBlock(node_feature_dim=C, num_segments=K).to(dev).eval()
@@ -38,12 +40,41 @@ def make_input(step, r):
     return torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(1000 * step + r)).to(dev)
 
 
-gather = {"captured": CapturedGather, "inline": InlineGather, "p2p": PeerGather}[MODE](B, N, K, D, dev, depth)
+gather = {"captured": CapturedGather, "inline": InlineGather, "p2p": PeerGather,
+          "bucketed": BucketedGather}[MODE](B, N, K, D, dev, depth)
 pipe = mg.PipelinedGraphBlock(blk, make_input(0, rank), image_size=(H, W), depth=depth, packed_small=gather.packed,
-                              epilogues=None if MODE == "inline" else gather.epilogues(),
+                              epilogues=None if MODE in ("inline", "bucketed") else gather.epilogues(),
                               epilogue_parallel=MODE == "p2p")
 got = []
+
+
+def collect_bucket(step_slots, own):
+    """bucketed: the gathers issued so far are complete on the current stream; copy the results of these steps out."""
+    gather.drain()
+    for slot_, own_loss in zip(step_slots, own):
+        g = gather.views(slot_)
+        got.append((g.l_partition.clone(), g.region_features.clone(), g.hard_labels.clone(), own_loss))
+    gather.side.wait_stream(torch.cuda.current_stream())      # the next gather into this buffer comes after the copies
+
+
+open_slots, open_own = [], []
 for s in range(steps):
+    if MODE == "bucketed":
+        nxt = pipe.next_slot
+        gather.before(nxt, pipe.stream(nxt))
+        slot, out = pipe.submit(make_input(s, rank))
+        with torch.cuda.stream(pipe.stream(slot)):
+            open_own.append(out.l_partition.clone())
+        pipe.mark(slot)
+        open_slots.append(slot)
+        gather.after(slot, pipe.stream(slot))
+        last = s == steps - 1
+        if last:
+            gather.flush()
+        if (slot + 1) % gather.bucket == 0 or last:
+            collect_bucket(open_slots, open_own)
+            open_slots, open_own = [], []
+        continue
     slot, out = pipe.submit(make_input(s, rank))
     if MODE == "inline":
         gather.gather(slot, pipe.stream(slot))        # one collective enqueue from the step's own stream
