@@ -191,8 +191,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import mingraph_unet_b200 as mg
-    from mingraph_unet_b200 import _lib
-    from oracle import restate as O          # only for the reference weight init + the cpu_baseline leg
+    from mingraph_unet_b200 import _lib      # (oracle/ is imported by the cpu_baseline leg only: cpu_block_images)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,16 +209,10 @@ def run_ours(args):
     N, E = cfg["nodes_per_image"], cfg["edges_per_image"]
     nph, npw = -(-H // PATCH), -(-W // PATCH)
 
-    # model: reference init (xavier_uniform gain 1.414) under seed 1234, loaded through state_dict
-    params = O.init_block_params(IN_DIM, D_OUT, HEADS, K_SEG, seed=1234)
-    blk = mg.GraphBlock(node_feature_dim=IN_DIM, num_segments=K_SEG)
-    for name, net in (("patch", blk.patch_gat_model), ("pred", blk.segment_predictor.gnn_predictor),
-                      ("region", blk.region_gat_model)):
-        sd = {}
-        for h in range(params[f"{name}_W"].shape[0]):
-            sd[f"gat_layers.0.heads.{h}.W.weight"] = params[f"{name}_W"][h].clone()
-            sd[f"gat_layers.0.heads.{h}.a.weight"] = params[f"{name}_a"][h].reshape(1, -1).clone()
-        net.load_state_dict(sd)
+    # model: the modules' own construction = the reference's init (xavier_uniform gain 1.414, graph_attention.py:36-37,
+    # same RNG consumption) under seed 1234
+    torch.manual_seed(1234)
+    blk = mg.GraphBlock(node_feature_dim=IN_DIM, gat_output_dim=D_OUT, num_heads=HEADS, num_segments=K_SEG)
     blk = blk.to(dev).eval()
 
     gen = torch.Generator().manual_seed(1000 + rank)
@@ -509,7 +502,6 @@ def run_train(args):
 
     import mingraph_unet_b200 as mg
     from mingraph_unet_b200 import _lib
-    from oracle import restate as O          # reference weight init only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -525,15 +517,8 @@ def run_train(args):
     cfg = workload_config(args.workload, world)
     cfg["workload"] = cfg["workload"].replace("graph block (", "graph block TRAINING step (fwd + bwd + grad all-reduce + Adam; ")
     N, E = cfg["nodes_per_image"], cfg["edges_per_image"]
-    params = O.init_block_params(IN_DIM, D_OUT, HEADS, K_SEG, seed=1234)
-    blk = mg.GraphBlock(node_feature_dim=IN_DIM, num_segments=K_SEG)
-    for name, net in (("patch", blk.patch_gat_model), ("pred", blk.segment_predictor.gnn_predictor),
-                      ("region", blk.region_gat_model)):
-        sd = {}
-        for h in range(params[f"{name}_W"].shape[0]):
-            sd[f"gat_layers.0.heads.{h}.W.weight"] = params[f"{name}_W"][h].clone()
-            sd[f"gat_layers.0.heads.{h}.a.weight"] = params[f"{name}_a"][h].reshape(1, -1).clone()
-        net.load_state_dict(sd)
+    torch.manual_seed(1234)                   # reference init = the modules' own construction (graph_attention.py:36-37)
+    blk = mg.GraphBlock(node_feature_dim=IN_DIM, gat_output_dim=D_OUT, num_heads=HEADS, num_segments=K_SEG)
     blk = blk.to(dev).train()                 # dropout 0.1 on, as the reference trains (configs/model.yaml)
     opt = torch.optim.Adam(blk.parameters(), lr=1e-4, capturable=True)
     gen = torch.Generator().manual_seed(1000 + rank)

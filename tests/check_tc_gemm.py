@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Error and time of the GAT layer through the 3xTF32 tensor-pipe transform (csrc/gat_tc_gemm.cu) against the FP32-pipe
 kernels, both against the CPU oracle.  Runs each path in a fresh process (the switch is read once per process):
-    python tools/tc_gemm_check.py            # parent: prints a table
+    python tests/check_tc_gemm.py            # parent: prints a table
 """
 import os
 import subprocess
