@@ -239,6 +239,16 @@ MG_API int mg_tv_loss(const void* x, int dtype, int B, int C, int H, int W, floa
 MG_API int mg_tv_loss_backward(const void* x, int dtype, int B, int C, int H, int W, float weight, const float* grad_loss,
                                float* grad_x, mg_stream_t stream);
 
+/* ---- fusion: per-region embeddings -> dense per-pixel map (next caller after the block, scope row f1) ----
+ * FeatureFusion.forward, per-region branch — model/fusion_detection/feature_fusion.py:81-140:
+ *   out[b, d, y, x] = table[map[b,y,x], d] if 0 <= map[b,y,x] < R, else 0   (valid_mask :119; zeros :85)
+ * table (R, D) f32 = f_g; map (B,H,W) MG_I32 | MG_I64 = region_to_pixel_map (the reference calls .long() on it);
+ * out: image b at out + b*out_batch_stride elements, (D,H,W) contiguous planes f32|bf16 — i.e. the channel slice
+ * [C_u : C_u + D] of the fused (B, C_u + D, H, W) buffer, so Concat(F_u, F_g) (:143) needs no extra pass.
+ * STATUS: compiled, not yet run on hardware (written after the round-1 GPU budget was spent). */
+MG_API int mg_region_map_gather(const float* table, int R, int D, const void* map, int map_dtype, int B, int H, int W,
+                                void* out, int out_dtype, int64_t out_batch_stride, mg_stream_t stream);
+
 /* ---- peer-memory exchange of the small per-image outputs (multi-GPU, scope row (e)) ----------------
  * The batch shards by image (scripts/train_end_to_end.py:300-425 builds one graph per image), so the only
  * per-step exchange is an all-gather of l_partition | region_features | hard_labels.  These two entry points do it

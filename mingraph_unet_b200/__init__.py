@@ -13,9 +13,9 @@ from . import ops  # noqa: E402
 from .block import GraphBlock, GraphBlockOutput  # noqa: E402
 from .graph import Graph  # noqa: E402
 from .runner import CapturedGraphBlock, CapturedTrainStep, PipelinedGraphBlock  # noqa: E402
-from .modules import (FeatureConsistencyLoss, GATNetwork, GraphAttentionLayer, MinCutRefinement,  # noqa: E402
+from .modules import (FeatureConsistencyLoss, FeatureFusion, GATNetwork, GraphAttentionLayer, MinCutRefinement,  # noqa: E402
                       MultiHeadGATLayer, PatchGraphConstructor, PatchSegmentPredictor, StackedGATNetwork, TVLoss)
 
 __all__ = ["ops", "Graph", "GraphBlock", "CapturedGraphBlock", "CapturedTrainStep", "PipelinedGraphBlock", "GraphBlockOutput", "GATNetwork", "GraphAttentionLayer", "MinCutRefinement",
-           "MultiHeadGATLayer", "PatchGraphConstructor", "PatchSegmentPredictor", "FeatureConsistencyLoss", "TVLoss", "StackedGATNetwork"]
+           "MultiHeadGATLayer", "PatchGraphConstructor", "PatchSegmentPredictor", "FeatureConsistencyLoss", "TVLoss", "StackedGATNetwork", "FeatureFusion"]
 __version__ = "0.1.0"

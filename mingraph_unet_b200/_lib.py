@@ -72,6 +72,7 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_tv_loss_work_bytes": (_i64, [_i] * 5),
     "mg_tv_loss": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
     "mg_tv_loss_backward": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
+    "mg_region_map_gather": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i64, _p]),
     "mg_peer_push": (_i, [_p, _i64, _p, _i, _i64, _p, _i64, _p, _p]),
     "mg_peer_wait": (_i, [_p, _i64, _i, _p, _p, _p]),
 }

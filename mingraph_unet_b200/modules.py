@@ -312,3 +312,99 @@ class TVLoss(nn.Module):
 
     def forward(self, x):
         return tv_loss_apply(x, float(self.weight))
+
+
+class FeatureFusion(nn.Module):
+    """``F_f = Concat(F_u, F_g)`` (model/fusion_detection/feature_fusion.py:5-153) — the consumer of the graph block's
+    output, same constructor and ``forward`` signature (``out`` is an addition).
+
+    * ``f_u_list``: U-Net feature maps; scales whose size differs from ``target_spatial_size`` are resized with
+      stock ``F.interpolate(mode='bilinear', align_corners=False)`` (:67-73; the conv side stays in PyTorch).
+    * ``f_g`` 4-D ``(B, D, H, W)`` (:134-138, what train_end_to_end.py:439-443 passes): resized the same way if needed.
+    * ``f_g`` 2-D ``(R, D)`` + ``region_to_pixel_map (B, H, W)`` (:81-132): every pixel takes the embedding of its region,
+      pixels whose index is outside ``[0, R)`` stay zero — one gather kernel (``mg_region_map_gather``) instead of the
+      reference's per-image mask / index / scatter sequence.
+
+    The fused tensor is allocated once and every input is written straight into its channel slice (the reference
+    materialises ``f_u_combined``, ``f_g_pixel`` and then ``cat`` re-copies both).  An input that already IS the matching
+    slice of ``out`` (e.g. the block's un-pool wrote ``F_g`` into ``out[:, C_u:]``, scope row f1) is not copied at all.
+    The per-region branch is inference-only for now (no gradient to ``f_g``); the 4-D branch is differentiable through
+    torch's slice copies.  CUDA tensors only."""
+
+    def __init__(self, unet_feature_dims, gat_feature_dim, fusion_method="concat"):
+        super().__init__()
+        self.unet_feature_dims = unet_feature_dims
+        self.gat_feature_dim = gat_feature_dim
+        self.fusion_method = fusion_method.lower()
+
+    @staticmethod
+    def _place(dst: torch.Tensor, src: torch.Tensor, size) -> None:
+        if (src.size(2), src.size(3)) != tuple(size):
+            src = F.interpolate(src, size=tuple(size), mode="bilinear", align_corners=False)
+        if src.data_ptr() == dst.data_ptr() and src.shape == dst.shape and src.stride() == dst.stride() and src.dtype == dst.dtype:
+            return                                   # already in place (written there by its producer)
+        dst.copy_(src)
+
+    def forward(self, f_u_list, f_g, target_spatial_size=None, region_to_pixel_map=None, out=None):
+        B = f_u_list[0].size(0)
+        if target_spatial_size is None:
+            target_spatial_size = (f_u_list[0].size(2), f_u_list[0].size(3))
+        Hh, Ww = int(target_spatial_size[0]), int(target_spatial_size[1])
+        per_region = f_g.ndim == 2 and region_to_pixel_map is not None
+        if not per_region and f_g.ndim != 4:
+            raise ValueError(f"f_g has unsupported shape {f_g.shape}. "
+                             "Expected (Num_regions, D_gat) with region_map or (B, D_gat, H, W).")
+        if self.fusion_method not in ("concat", "add"):
+            raise NotImplementedError(f"Fusion method '{self.fusion_method}' not implemented.")
+        c_u = sum(int(t.size(1)) for t in f_u_list)
+        d_g = int(self.gat_feature_dim) if per_region else int(f_g.size(1))
+        if self.fusion_method == "add" and c_u != d_g:
+            raise ValueError("Channel dimensions must match for 'add' fusion or implement adaptation.")
+        for t in list(f_u_list) + [f_g] + ([region_to_pixel_map] if per_region else []):
+            if not t.is_cuda:
+                raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        dev = f_u_list[0].device
+        dt = f_u_list[0].dtype
+        for t in f_u_list[1:]:
+            dt = torch.promote_types(dt, t.dtype)
+        dt = torch.promote_types(dt, torch.float32 if per_region else f_g.dtype)     # f_g_pixel is float32 zeros (:85)
+        if per_region:
+            if f_g.requires_grad and torch.is_grad_enabled():
+                raise NotImplementedError("FeatureFusion: the per-region branch is inference-only (pass the 4-D f_g, as "
+                                          "scripts/train_end_to_end.py does, to train through the fusion)")
+            if f_g.size(1) != d_g:
+                raise RuntimeError(f"shape mismatch: f_g has {f_g.size(1)} columns, gat_feature_dim is {d_g}")
+            rmap = region_to_pixel_map
+            if rmap.dim() != 3 or rmap.size(0) != B or (rmap.size(1), rmap.size(2)) != (Hh, Ww):
+                raise IndexError(f"region_to_pixel_map {tuple(rmap.shape)} does not match (B, H_out, W_out) = "
+                                 f"({B}, {Hh}, {Ww})")
+            if rmap.dtype not in (torch.int32, torch.int64):
+                rmap = rmap.long()                                                   # (:115)
+            table = f_g.float()
+        if self.fusion_method == "add":
+            f_u = f_u_list[0] if len(f_u_list) == 1 and (f_u_list[0].size(2), f_u_list[0].size(3)) == (Hh, Ww) else None
+            if f_u is None:
+                f_u = torch.empty((B, c_u, Hh, Ww), dtype=dt, device=dev)
+                c = 0
+                for t in f_u_list:
+                    self._place(f_u[:, c:c + t.size(1)], t, (Hh, Ww))
+                    c += t.size(1)
+            if per_region:
+                g = ops.region_map_gather(table, rmap, out_dtype=torch.float32)
+            else:
+                g = f_g if (f_g.size(2), f_g.size(3)) == (Hh, Ww) else \
+                    F.interpolate(f_g, size=(Hh, Ww), mode="bilinear", align_corners=False)
+            return f_u + g
+        if out is None:
+            out = torch.empty((B, c_u + d_g, Hh, Ww), dtype=dt, device=dev)
+        elif tuple(out.shape) != (B, c_u + d_g, Hh, Ww) or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous ({B}, {c_u + d_g}, {Hh}, {Ww}) tensor")
+        c = 0
+        for t in f_u_list:
+            self._place(out[:, c:c + t.size(1)], t, (Hh, Ww))
+            c += t.size(1)
+        if per_region:
+            ops.region_map_gather(table, rmap, out=out[:, c_u:])
+        else:
+            self._place(out[:, c_u:], f_g, (Hh, Ww))
+        return out

@@ -516,6 +516,38 @@ def tv_loss_backward(x: torch.Tensor, weight: float, grad_loss: torch.Tensor) ->
 
 
 # ---------------------------------------------------------------------------------------------
+# fusion: per-region embeddings -> dense per-pixel map (csrc/fusion.cu) — compiled, not yet run on hardware
+# ---------------------------------------------------------------------------------------------
+def region_map_gather(table: torch.Tensor, region_map: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """``out[b,d,y,x] = table[region_map[b,y,x], d]`` where the index is in ``[0, R)``, else 0
+    (FeatureFusion.forward per-region branch, model/fusion_detection/feature_fusion.py:81-140).
+    ``table (R,D)`` float32, ``region_map (B,H,W)`` int32 | int64; ``out`` may be a channel slice
+    ``buf[:, c0:c0+D]`` of a contiguous ``(B,Ctot,H,W)`` buffer."""
+    _need_cuda(table, region_map, out)
+    if table.dim() != 2 or region_map.dim() != 3:
+        raise ValueError("region_map_gather expects table (R,D) and region_map (B,H,W)")
+    if table.dtype != torch.float32:
+        raise RuntimeError("region_map_gather expects a float32 table")
+    if region_map.dtype not in (torch.int32, torch.int64):
+        raise RuntimeError("region_map must be int32 or int64")
+    table, region_map = table.contiguous(), region_map.contiguous()
+    R, D = table.shape
+    B, H, W = region_map.shape
+    if R == 0 or D == 0 or B * H * W == 0:
+        raise ValueError("region_map_gather: empty table or map")
+    if out is None:
+        out = torch.empty((B, D, H, W), dtype=out_dtype, device=table.device)
+    if tuple(out.shape) != (B, D, H, W) or out.stride()[1:] != (H * W, W, 1):
+        raise ValueError("out must be (B,D,H,W) with contiguous (D,H,W) planes")
+    with torch.cuda.device(table.device):
+        call("mg_region_map_gather", table.data_ptr(), R, D, region_map.data_ptr(),
+             _lib.MG_I32 if region_map.dtype == torch.int32 else _lib.MG_I64, B, H, W, out.data_ptr(),
+             _dtype_code(out.dtype), out.stride(0) if B > 1 else D * H * W, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # peer-memory exchange (multi-GPU; csrc/peer_push.cu) — compiled, not yet run on hardware (opt-in)
 # ---------------------------------------------------------------------------------------------
 def peer_push(src: torch.Tensor, peer_bufs_dev: int, world: int, dst_offset_bytes: int, peer_signals_dev: int,

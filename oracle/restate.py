@@ -338,3 +338,45 @@ def tv_loss(x, weight: float = 1.0):
     h_tv = torch.pow(x[:, :, 1:, :] - x[:, :, :-1, :], 2).sum()
     w_tv = torch.pow(x[:, :, :, 1:] - x[:, :, :, :-1], 2).sum()
     return weight * (h_tv / count_h + w_tv / count_w) / batch_size
+
+
+# ----------------------------------------------------------------------------
+# feature fusion (the consumer of the block's output; scope row f1)
+# ----------------------------------------------------------------------------
+def region_map_gather(f_g: torch.Tensor, region_to_pixel_map: torch.Tensor) -> torch.Tensor:
+    """model/fusion_detection/feature_fusion.py:81-132: ``f_g (R, D)`` + ``region_to_pixel_map (B, H, W)`` ->
+    ``(B, D, H, W)`` float32; pixels whose index is outside ``[0, R)`` (``valid_mask``, :119) stay zero (:85)."""
+    B, H, W = region_to_pixel_map.shape
+    R, D = f_g.shape
+    idx = region_to_pixel_map.reshape(B, H * W).long()                      # (:115)
+    valid = (idx >= 0) & (idx < R)                                          # (:119)
+    rows = f_g.float()[idx.clamp(0, R - 1)]                                 # (B, H*W, D), (:124)
+    rows = torch.where(valid.unsqueeze(-1), rows, torch.zeros((), dtype=torch.float32))
+    return rows.permute(0, 2, 1).reshape(B, D, H, W).contiguous()          # (:131-133)
+
+
+def feature_fusion(f_u_list: Sequence[torch.Tensor], f_g: torch.Tensor, target_spatial_size=None,
+                   region_to_pixel_map: Optional[torch.Tensor] = None, fusion_method: str = "concat") -> torch.Tensor:
+    """``FeatureFusion.forward`` (feature_fusion.py:43-153): bilinear resize of the U-Net scales (:67-73), ``cat``
+    (:75), per-region gather (:81-132) or 4-D pass-through / resize (:134-138), then ``concat`` (:143) or ``add``
+    (:144-148)."""
+    if target_spatial_size is None:
+        target_spatial_size = (f_u_list[0].size(2), f_u_list[0].size(3))
+    size = (int(target_spatial_size[0]), int(target_spatial_size[1]))
+    fu = [t if (t.size(2), t.size(3)) == size else F.interpolate(t, size=size, mode="bilinear", align_corners=False)
+          for t in f_u_list]
+    f_u = torch.cat(fu, dim=1)
+    if f_g.ndim == 2 and region_to_pixel_map is not None:
+        g = region_map_gather(f_g, region_to_pixel_map)
+    elif f_g.ndim == 4:
+        g = f_g if (f_g.size(2), f_g.size(3)) == size else F.interpolate(f_g, size=size, mode="bilinear", align_corners=False)
+    else:
+        raise ValueError(f"f_g has unsupported shape {f_g.shape}. "
+                         "Expected (Num_regions, D_gat) with region_map or (B, D_gat, H, W).")
+    if fusion_method == "concat":
+        return torch.cat([f_u, g], dim=1)
+    if fusion_method == "add":
+        if f_u.shape[1] != g.shape[1]:
+            raise ValueError("Channel dimensions must match for 'add' fusion or implement adaptation.")
+        return f_u + g
+    raise NotImplementedError(f"Fusion method '{fusion_method}' not implemented.")
