@@ -264,6 +264,8 @@ def run_ours(args):
                                   packed_small=packed_small,
                                   epilogues=None if cgather is None else cgather.epilogues(),
                                   epilogue_parallel=args.exchange in ("captured-parallel", "p2p"))
+    if hasattr(cgather, "reset"):
+        cgather.reset()                 # p2p: the graphs' warm-up passes pushed too; restart the sequence numbers together
     runner = pipe.runners[0]
     per_step_kernels = (_lib.launch_count() - lc0 - 1) // (3 * depth)   # per slot: 2 warm-up passes + the recorded one (+1 weight prepare)
 

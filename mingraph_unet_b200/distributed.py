@@ -316,6 +316,7 @@ class PeerGather:
     ``torch.distributed._symmetric_memory``; the epilogue of a step's graph is ONE kernel that stores the slot's packed
     payload into slice ``rank`` of every peer's buffer and publishes a sequence number.  No kernel of this scheme waits
     for another GPU, so a slow rank never makes a fast rank hold SMs (the failure mode of concurrent NCCL kernels).
+    Call ``reset()`` once after the step graphs were built (their warm-up passes push too).
     Consumers call ``wait(slot)`` exactly once per step before reading ``views(slot)``.  Flow control is the caller's:
     a producer may overwrite slot ``s`` of a peer ``depth`` steps later, so a consumer that reads the gathered data must
     keep ranks within ``depth`` steps of each other (the bench does not read it; its end-of-region barrier closes it)."""
@@ -325,6 +326,7 @@ class PeerGather:
         from . import ops
         self._ops = ops
         group = group if group is not None else dist.group.WORLD
+        self._group = group
         self.B, self.N, self.K, self.D, self.depth = B, N, K, D, depth
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.n_small = B * (1 + K * D + N)
@@ -342,6 +344,20 @@ class PeerGather:
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group)                                            # nobody pushes before every flag is zeroed
+
+    def reset(self) -> None:
+        """Collective.  Zero every sequence counter and flag once all ranks are idle.  Must be called after the graphs
+        that contain the push were built: building a ``CapturedGraphBlock`` runs its epilogue eagerly ``warmup`` times,
+        so without this the producers' counters would start ahead of the consumers' and the first ``wait`` of a slot
+        would be satisfied by a warm-up push (stale payload)."""
+        torch.cuda.synchronize(self._flags.device)
+        dist.barrier(self._group)                                      # every rank's warm-up pushes have landed
+        self._flags.zero_()
+        self._seq.zero_()
+        self._wseq.zero_()
+        self.status.zero_()
+        torch.cuda.synchronize(self._flags.device)
+        dist.barrier(self._group)                                      # nobody pushes before every flag is zeroed
 
     def epilogue(self, slot: int):
         off = (slot * self.world + self.rank) * self.n_pad * 4

@@ -45,6 +45,8 @@ gather = {"captured": CapturedGather, "inline": InlineGather, "p2p": PeerGather,
 pipe = mg.PipelinedGraphBlock(blk, make_input(0, rank), image_size=(H, W), depth=depth, packed_small=gather.packed,
                               epilogues=None if MODE in ("inline", "bucketed") else gather.epilogues(),
                               epilogue_parallel=MODE == "p2p")
+if MODE == "p2p":
+    gather.reset()                      # the graphs' warm-up passes pushed too: restart the sequence numbers together
 got = []
 
 
