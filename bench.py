@@ -52,6 +52,8 @@ def parse_args():
                          "0 = default: 3)")
     ap.add_argument("--exchange", default="inline", choices=["inline", "stream", "captured", "captured-parallel", "p2p", "bucketed"],
                     help="N>1: how the per-step all-gather of the small outputs is issued (see run_ours)")
+    ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false",
+                    help="N>1: do not bind each rank to its GPU's NUMA node (A/B of the e2e leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
@@ -200,8 +202,16 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N>1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = "not bound (single rank: the cpu_baseline leg uses every host core)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if args.numa_bind:
+            # one process per GPU: keep this rank's pinned buffers and launch thread on the GPU's own NUMA node (the e2e
+            # leg moves 168 MB per step and rank from host memory)
+            from mingraph_unet_b200.distributed import bind_to_gpu_numa
+            numa = bind_to_gpu_numa(dev)
+        else:
+            numa = "not bound (--no-numa-bind)"
 
     H, W, B, dtname = WORKLOADS[args.workload]
     dtype = getattr(torch, dtname)
@@ -468,7 +478,7 @@ def run_ours(args):
             "e2e": {"value": B * world * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": fm_host.numel() * fm_host.element_size(),
                     "d2h_bytes_per_step": 4 * (host_loss[0].numel() + host_region[0].numel() + host_labels[0].numel()),
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "numa": numa,
                     "api": "PipelinedGraphBlock(GraphBlock).submit(pinned host feature map): H2D + graph replay + D2H of "
                            "loss / region features / labels per step, %d steps in flight" % depth},
             "clocks": sampler.summary(note),

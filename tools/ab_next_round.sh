@@ -41,4 +41,9 @@ else
       bench.py --gpus $N --steps 200 --warmup 10 --exchange $m > gpurun_out/ab_n${N}_$m.log 2> gpurun_out/ab_n${N}_$m.err
     echo "rc=$?"; summ gpurun_out/ab_n${N}_$m.log
   done
+  # NUMA binding of the ranks (on by default at N>1): the same run without it, for the e2e leg
+  port=$((port + 1))
+  timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
+    bench.py --gpus $N --steps 200 --warmup 10 --no-numa-bind > gpurun_out/ab_n${N}_nonuma.log 2> gpurun_out/ab_n${N}_nonuma.err
+  echo "rc=$?"; summ gpurun_out/ab_n${N}_nonuma.log
 fi
