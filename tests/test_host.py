@@ -304,3 +304,14 @@ def test_loss_modules_error_behaviour_on_cpu(mg):
             ref_fl(x3, torch.randn(2, 6, 9), torch.zeros(2, 6))
         with pytest.raises(ValueError, match="is not \\(Batch, Num_Patches\\)"):
             ref_fl(x3, x3, torch.zeros(2, 7))
+
+
+def test_numa_binding_never_raises():
+    """bind_to_gpu_numa is an optimisation of the N>1 bench ranks: without NVML / a GPU it reports why it did nothing."""
+    from mingraph_unet_b200.distributed import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    msg = bind_to_gpu_numa("cuda:0")
+    assert isinstance(msg, str) and (msg.startswith("bound to") or msg.startswith("not bound"))
+    if msg.startswith("not bound"):
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
