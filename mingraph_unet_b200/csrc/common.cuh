@@ -119,9 +119,12 @@ __device__ __forceinline__ float leaky_relu(float v, float slope) { return v > 0
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 
 // Streaming (evict-first) 16-byte store for write-once outputs.
+#ifndef MG_HOST_EMULATION
 __device__ __forceinline__ void st_cs_v4(void* p, uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+#else   // tests/emu: the kernels compiled for the host; the shim header provides an alignment-checking st_cs_v4
+#endif
 
 }  // namespace mg
