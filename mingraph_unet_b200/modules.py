@@ -360,9 +360,7 @@ class FeatureFusion(nn.Module):
         d_g = int(self.gat_feature_dim) if per_region else int(f_g.size(1))
         if self.fusion_method == "add" and c_u != d_g:
             raise ValueError("Channel dimensions must match for 'add' fusion or implement adaptation.")
-        for t in list(f_u_list) + [f_g] + ([region_to_pixel_map] if per_region else []):
-            if not t.is_cuda:
-                raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        ops._need_cuda(*f_u_list, f_g, region_to_pixel_map if per_region else None)     # no CPU fallback
         dev = f_u_list[0].device
         dt = f_u_list[0].dtype
         for t in f_u_list[1:]:

@@ -132,3 +132,86 @@ def test_golden_fixture_through_the_emulated_kernel(emu, golden):
                                        base + cu * H * W * 4, 0, (cu + D) * H * W, base, base + buf.nbytes, 148, 0)
         assert rc >= 0
         assert np.array_equal(buf.reshape(B, cu + D, H, W), ref), tag          # Concat(F_u, F_g) bit for bit
+
+
+# ---------------------------------------------------------------------------------------------
+# the Python side (modules.FeatureFusion -> ops.region_map_gather -> ctypes arguments) driven end to end on CPU tensors,
+# with the C-ABI call routed to the emulated kernel: checks the wrapper's pointer / stride / dtype-code marshalling and
+# the module's channel-slice bookkeeping against the reference fixtures
+# ---------------------------------------------------------------------------------------------
+class _NullCtx:
+    def __init__(self, *a, **k):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+@pytest.fixture
+def routed(emu, monkeypatch):
+    import mingraph_unet_b200 as mg
+    calls = []
+
+    def call(fn, *args):
+        assert fn == "mg_region_map_gather"
+        table, R, D, mp, map_dt, B, H, W, out, out_dt, stride, stream = args
+        esz = 4 if out_dt == mg._lib.MG_F32 else 2
+        hi = out + ((B - 1) * stride + D * H * W) * esz
+        rc = emu.emu_region_map_gather(table, R, D, mp, int(map_dt == mg._lib.MG_I64), B, H, W, out,
+                                       int(out_dt == mg._lib.MG_BF16), stride, out, hi, 148, 0)
+        assert rc >= 0, "misaligned or out-of-range access"
+        calls.append(rc)
+
+    monkeypatch.setattr(mg.ops, "call", call)
+    monkeypatch.setattr(mg.ops, "_need_cuda", lambda *ts: next(t.device for t in ts if t is not None))
+    monkeypatch.setattr(mg.ops, "_stream", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", _NullCtx)
+    return mg, calls
+
+
+def test_module_and_wrapper_end_to_end_on_the_emulated_kernel(routed, golden):
+    mg, calls = routed
+    g = golden("fusion.npz")
+    T = lambda a: torch.from_numpy(np.asarray(a))          # noqa: E731
+    for tag in ["rand_i64", "rand_i32", "invalid", "blocky", "odd", "allbad"]:
+        fu, table, m, ref = T(g[f"rg_{tag}_fu"]), T(g[f"rg_{tag}_table"]), T(g[f"rg_{tag}_map"]), T(g[f"rg_{tag}_out"])
+        mod = mg.FeatureFusion([fu.shape[1]], table.shape[1])
+        out = mod([fu], table, region_to_pixel_map=m)
+        assert out.dtype == torch.float32 and torch.equal(out, ref), tag
+        # bf16 fused buffer supplied by the caller
+        buf = torch.empty(ref.shape, dtype=torch.bfloat16)
+        out16 = mod([fu.bfloat16()], table, region_to_pixel_map=m, out=buf)
+        assert out16.data_ptr() == buf.data_ptr()
+        assert torch.equal(out16[:, fu.shape[1]:], ref[:, fu.shape[1]:].bfloat16()) and torch.equal(out16[:, :fu.shape[1]], fu.bfloat16())
+    assert len(calls) == 12 and calls.count(1) >= 6               # the vector kernel served the aligned cases
+    # uint8 map (the reference calls .long() on it), add fusion, dense branches
+    out = mg.FeatureFusion([16], 16, "add")([T(g["add_fu"])], T(g["add_table"]), region_to_pixel_map=T(g["add_map"]))
+    assert torch.equal(out, T(g["add_out"]))
+    m8 = torch.randint(0, 5, (2, 8, 8), dtype=torch.uint8)
+    out = mg.FeatureFusion([16], 16)([T(g["add_fu"])], T(g["add_table"]), region_to_pixel_map=m8)
+    assert torch.equal(out, O.feature_fusion([T(g["add_fu"])], T(g["add_table"]), region_to_pixel_map=m8))
+    out = mg.FeatureFusion([6], 10)([T(g["d4_same_fu"])], T(g["d4_same_fg"]), target_spatial_size=(16, 16))
+    assert torch.equal(out, T(g["d4_same_out"]))
+    out = mg.FeatureFusion([4, 3], 8)([T(g["d4_resize_fu0"]), T(g["d4_resize_fu1"])], T(g["d4_resize_fg"]))
+    assert torch.allclose(out, T(g["d4_resize_out"]), atol=1e-6, rtol=0)
+    # inputs that already are the channel slices of `out` are not copied (scope row f1)
+    fused = torch.randn(2, 32 + 64, 16, 8)
+    keep = fused.clone()
+    out = mg.FeatureFusion([32], 64)([fused[:, :32]], fused[:, 32:], out=fused)
+    assert out.data_ptr() == fused.data_ptr() and torch.equal(out, keep)
+    # wrapper straight into a channel slice of a wider buffer; neighbours untouched
+    table = torch.randn(9, 64)
+    m = torch.randint(-1, 10, (3, 16, 32))
+    wide = torch.full((3, 32 + 64 + 4, 16, 32), 7.0)
+    mg.ops.region_map_gather(table, m, out=wide[:, 32:96])
+    assert torch.equal(wide[:, 32:96], O.region_map_gather(table, m))
+    assert bool((wide[:, :32] == 7.0).all()) and bool((wide[:, 96:] == 7.0).all())
+    with pytest.raises(ValueError):
+        mg.ops.region_map_gather(table, m, out=torch.empty(3, 64, 16, 33))
+    with pytest.raises(IndexError):
+        mg.FeatureFusion([32], 64)([torch.zeros(3, 32, 16, 32)], table, region_to_pixel_map=m[:, :8])
+    with pytest.raises(NotImplementedError):
+        mg.FeatureFusion([32], 64)([torch.zeros(3, 32, 16, 32)], table.clone().requires_grad_(True), region_to_pixel_map=m)

@@ -4,8 +4,9 @@ values), bf16 output equals the rounded fp32 result, the dense branches equal to
 
 OPT-IN for now: the kernel was written after the round-1 GPU budget was spent and has not run on hardware yet, so
 these tests only run with ``MG_TEST_UNVERIFIED=1`` (first thing to run in the next round:
-``MG_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_zfusion.py -m gpu -q``).  The index arithmetic of the vector
-kernel is covered on the CPU by tests/test_oracle_fusion.py."""
+``MG_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_zfusion.py -m gpu -q``).  On the CPU the kernel SOURCE is compiled for the host
+and executed thread by thread (tests/test_fusion_emulation.py, which also drives the module and the ctypes wrapper end to
+end on the emulated kernel), and tests/test_oracle_fusion.py models its index arithmetic."""
 import os
 
 import numpy as np
