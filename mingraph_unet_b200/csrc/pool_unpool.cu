@@ -157,19 +157,33 @@ __device__ __forceinline__ float pt_sum16<__nv_bfloat16>(const uint4& u) {
 }
 
 // Dynamic strip scheduling (MG_POOL_DYNAMIC=1; off by default: written after the round-1 GPU budget was spent, not yet
-// measured).  Counter pairs live in a small device array; a launch takes the next pair round-robin (a recorded graph
-// node keeps the pair it was recorded with; its replays are serialised), the kernel's last CTA re-arms the pair.
+// measured).  Counter pairs live in a small per-device array; the kernel's last CTA re-arms the pair it used.  A launch
+// recorded into a CUDA graph OWNS its pair for the life of the process (its replays are serialised by the graph's
+// stream; pairs 32..63, static scheduling once they are used up), eager launches take pairs 0..31 round-robin — so an
+// eager launch can never share a pair with a concurrently replaying graph.
 __device__ int g_pool_counters[64][2];
-static int* pool_counters() {
+static int* pool_counters(cudaStream_t st) {
   static const int enabled = getenv("MG_POOL_DYNAMIC") ? atoi(getenv("MG_POOL_DYNAMIC")) : 0;
   if (!enabled) return nullptr;
-  static int* base = nullptr;
-  static std::atomic<unsigned> next{0};
-  if (!base && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_pool_counters) != cudaSuccess) {
+  constexpr int kMaxDev = 64;
+  static int* base[kMaxDev] = {};                            // the symbol has one instance per device
+  static std::atomic<unsigned> next_eager[kMaxDev], next_captured[kMaxDev];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  if (!base[dev] && cudaGetSymbolAddress(reinterpret_cast<void**>(&base[dev]), g_pool_counters) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
-  return base + 2 * (next.fetch_add(1) % 64);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (cs == cudaStreamCaptureStatusActive) {
+    const unsigned i = next_captured[dev].fetch_add(1);
+    return i < 32 ? base[dev] + 2 * (32 + i) : nullptr;
+  }
+  return base[dev] + 2 * (next_eager[dev].fetch_add(1) % 32);
 }
 
 struct PoolTmaArgs {
@@ -606,7 +620,7 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
       A.nstrips = B * Hp * C;
       A.stages = stages;
       A.stage_bytes = stage_bytes;
-      A.counters = pool_counters();
+      A.counters = pool_counters(st);
       auto kern = A.counters ? pool_patches_tma_kernel<TX, TO, true> : pool_patches_tma_kernel<TX, TO, false>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes) != cudaSuccess) {
         set_error("mg_pool_patches: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
