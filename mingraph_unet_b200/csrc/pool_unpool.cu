@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -370,6 +371,123 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core summation (opt-in, MG_POOL_MMA=1; bf16 maps, pw == 16, Wf % 256 == 0).  STATUS: written after the
+// round-1 GPU budget was spent — compiles, NOT yet run on hardware, off by default.
+// Why: the bulk-copy kernel above always finds its data landed (long-scoreboard stalls 2 % of samples) and spends its
+// time ISSUING the sum — ~21 warp instructions per 512 bytes (shift / mask / add per bf16 pair) with two warps per
+// scheduler (profiles/r1_pool_tma.md).  A patch row of 16 bf16 pixels is 32 contiguous bytes, so 512 contiguous bytes
+// of an image row are a 16 x 16 row-major matrix A (row = patch, column = pixel); with B = ones,
+// mma.m16n8k16 (bf16 x bf16 -> fp32) adds that image row's 16 patch-row sums into D, and accumulating D over the ph
+// image rows of the strip gives the 16 patch sums: ONE ldmatrix.x4 + ONE mma per 512 bytes.  Products with 1.0 are
+// exact and the accumulation is fp32, like the scalar code (different summation order).
+// Same persistent per-warp TMA rings and static strip order as pool_patches_tma_kernel; only the consumer differs.
+// ldmatrix lane addresses: matrix m = lane / 8 covers A rows (lane % 8) + 8 (m & 1); the two 16-byte halves of an A row
+// may go to either k half (a sum does not care about k order), so rows 4..7 of every 8-row phase take the other half:
+// the 8 addresses of a phase then fall into 8 different 16-byte bank groups (rows are only 32 bytes apart).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pt_ldmatrix_x4(uint32_t addr, uint32_t (&a)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void pt_mma_ones(float (&d)[4], const uint32_t (&a)[4]) {
+  const uint32_t ones = 0x3F803F80u;                          // bf16 (1.0, 1.0)
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(ones), "r"(ones));
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_mma_kernel(const PoolTmaArgs A) {
+  using TX = __nv_bfloat16;
+  extern __shared__ __align__(128) unsigned char pt_smem[];
+  const int q = A.stages;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* ring = pt_smem + (size_t)warp * q * A.stage_bytes;
+  const uint32_t ring0 = pt_smem_u32(ring);
+  const uint32_t full0 = pt_smem_u32(pt_smem) + (uint32_t)(kPtWarps * q) * (uint32_t)A.stage_bytes + 8u * (uint32_t)(warp * q);
+  if (lane == 0) {
+    for (int i = 0; i < q; ++i) pt_mbar_init(full0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  const int row_bytes = A.Wf * (int)sizeof(TX);
+  const int tiles = A.Wf >> 8;                               // 16 patches x 16 pixels = 512 bytes per tile and image row
+  const float inv = 1.f / (float)(A.ph * A.pw);
+  TO* out = reinterpret_cast<TO*>(A.out);
+  const uint32_t lane_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * 32 + ((((lane >> 4) & 1) ^ ((lane >> 2) & 1)) * 16));
+
+  PtCursor<TX> ic, cc;                                        // issue cursor (q chunks ahead), consume cursor
+  ic.step = cc.step = kPtWarps * gridDim.x;
+  ic.s = cc.s = blockIdx.x + warp * gridDim.x;
+  ic.load(A);
+  cc.load(A);
+  int issued = 0;
+  auto issue = [&]() {
+    if (!ic.valid(A)) return;
+    if (lane == 0) {
+      const int st = issued % q;
+      const uint32_t bytes = (uint32_t)(min(A.rpc, ic.rows - ic.r0) * row_bytes);
+      pt_mbar_expect_tx(full0 + 8 * st, bytes);
+      pt_bulk_g2s(ring0 + (uint32_t)st * (uint32_t)A.stage_bytes, ic.base + (size_t)ic.r0 * A.Wf, bytes, full0 + 8 * st, policy);
+    }
+    ++issued;
+    if (ic.advance(A)) {
+      ic.s += ic.step;
+      ic.load(A);
+    }
+  };
+  for (int t = 0; t < q; ++t) issue();
+
+  int consumed = 0;
+  float d[kPtMaxPasses][4];
+  while (cc.valid(A)) {
+    if (cc.r0 == 0) {
+#pragma unroll
+      for (int p = 0; p < kPtMaxPasses; ++p) d[p][0] = d[p][1] = d[p][2] = d[p][3] = 0.f;
+    }
+    const int st = consumed % q;
+    pt_mbar_wait(full0 + 8 * st, (uint32_t)((consumed / q) & 1));
+    const int nr = min(A.rpc, cc.rows - cc.r0);
+    const uint32_t buf = ring0 + (uint32_t)st * (uint32_t)A.stage_bytes + lane_off;
+    for (int r = 0; r < nr; ++r) {
+#pragma unroll
+      for (int p = 0; p < kPtMaxPasses; ++p) {
+        if (p < tiles) {
+          uint32_t a[4];
+          pt_ldmatrix_x4(buf + (uint32_t)(r * row_bytes + p * 512), a);
+          pt_mma_ones(d[p], a);
+        }
+      }
+    }
+    __syncwarp();                                             // every lane has read the buffer: lane 0 may re-arm it
+    issue();
+    ++consumed;
+    if (cc.r0 + A.rpc >= cc.rows) {                           // strip complete: D rows g and g + 8 of lanes with t == 0
+      if ((lane & 3) == 0) {
+        const int g = lane >> 2;
+#pragma unroll
+        for (int p = 0; p < kPtMaxPasses; ++p) {
+          if (p < tiles) {
+            const int px = p * 16 + g;
+            if (px < A.Wp) out[(cc.orow + px) * A.C + cc.c] = from_f32<TO>(d[p][0] * inv);
+            if (px + 8 < A.Wp) out[(cc.orow + px + 8) * A.C + cc.c] = from_f32<TO>(d[p][2] * inv);
+          }
+        }
+      }
+    }
+    if (cc.advance(A)) {
+      cc.s += cc.step;
+      cc.load(A);
+    }
+  }
+}
+
 // generic path: any window; one thread per output element (px fastest so window reads share lines)
 template <typename TX, typename TO>
 __global__ void pool_patches_generic_kernel(const TX* __restrict__ x, int B, int C, int Hf, int Wf, int ph, int pw,
@@ -620,6 +738,20 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
       A.nstrips = B * Hp * C;
       A.stages = stages;
       A.stage_bytes = stage_bytes;
+      // MG_POOL_MMA=1 (opt-in, not yet run on hardware): tensor-core summation for bf16 maps with 16-pixel-wide patches
+      static const int use_mma = getenv("MG_POOL_MMA") ? atoi(getenv("MG_POOL_MMA")) : 0;
+      if constexpr (std::is_same<TX, __nv_bfloat16>::value) {
+        if (use_mma && pw == 16 && Wf % 256 == 0 && Wf / 256 <= kPtMaxPasses) {
+          A.counters = nullptr;
+          auto mk = pool_patches_mma_kernel<TO>;
+          if (cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes) != cudaSuccess) {
+            set_error("mg_pool_patches: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+            return MG_ERR_CUDA;
+          }
+          mk<<<std::min(num_sms(), ceil_div(A.nstrips, kPtWarps)), kPtWarps * 32, smem, st>>>(A);
+          return check_launch("pool_patches_mma_kernel");
+        }
+      }
       A.counters = pool_counters(st);
       auto kern = A.counters ? pool_patches_tma_kernel<TX, TO, true> : pool_patches_tma_kernel<TX, TO, false>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes) != cudaSuccess) {

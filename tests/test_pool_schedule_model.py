@@ -133,3 +133,36 @@ def test_pool_schedule(B, C, Hf, ph, rpc, q, grid, dynamic):
     assert all(not x.pending and x.issued == x.consumed for x in warps)
     if dynamic:
         assert counter[0] == nstrips + grid * K_WARPS     # each warp draws exactly one terminating id
+
+
+def test_mma_pool_fragment_mapping_sums_every_patch_row_once():
+    """pool_patches_mma_kernel (csrc/pool_unpool.cu, opt-in, not yet run on hardware): model of its ldmatrix lane
+    addresses and of the m16n8k16 fragment layouts.  512 contiguous bytes of an image row = 16 patches x 16 bf16 pixels;
+    with B = ones the MMA must add, into D row i, the 16 pixels of patch i — each exactly once — and the 8 row addresses
+    of every ldmatrix phase must fall into 8 different 16-byte bank groups (rows are 32 bytes apart)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    tile = rng.integers(-8, 9, size=(16, 16)).astype(np.float64)          # [patch][pixel], row-major = the smem bytes
+    flat = tile.reshape(-1)                                                # element index = byte offset / 2
+
+    def lane_off(lane):                                                    # bytes, as in the kernel
+        return ((lane & 7) + ((lane >> 3) & 1) * 8) * 32 + ((((lane >> 4) & 1) ^ ((lane >> 2) & 1)) * 16)
+
+    # ldmatrix.x4: matrix m, row j comes from the address of lane 8 m + j (16 bytes = 8 elements)
+    mats = np.zeros((4, 8, 8))
+    for m in range(4):
+        offs = [lane_off(8 * m + j) for j in range(8)]
+        assert len({(o % 128) // 16 for o in offs}) == 8                   # conflict-free phase
+        for j, o in enumerate(offs):
+            assert o % 16 == 0
+            mats[m, j] = flat[o // 2:o // 2 + 8]
+    # mma A fragment: reg0 = matrix 0 -> A[g][k 0..7], reg1 = matrix 1 -> A[g+8][k 0..7], reg2 -> A[g][8..15], reg3 -> A[g+8][8..15]
+    Am = np.zeros((16, 16))
+    Am[0:8, 0:8], Am[8:16, 0:8], Am[0:8, 8:16], Am[8:16, 8:16] = mats[0], mats[1], mats[2], mats[3]
+    D = Am @ np.ones((16, 8))
+    for i in range(16):
+        assert sorted(Am[i]) == sorted(tile[i])                            # A row i = the 16 pixels of patch i, once each
+    # D fragment: c0 -> D[g][2t], c2 -> D[g+8][2t]; the kernel stores c0 / c2 of the lanes with t == 0 as patches g, g + 8
+    for lane in range(0, 32, 4):
+        g = lane >> 2
+        assert D[g][0] == tile[g].sum() and D[g + 8][0] == tile[g + 8].sum()

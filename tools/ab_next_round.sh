@@ -23,6 +23,9 @@ if [ "$N" = "1" ]; then
   MG_TEST_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_zfusion.py -x -q -m gpu 2>&1 | tail -3
   timeout 200 python tools/fusion_bench.py > gpurun_out/ab_fusion.md 2> gpurun_out/ab_fusion.err; tail -20 gpurun_out/ab_fusion.md
   MG_POOL_DYNAMIC=1 timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "pool or block" 2>&1 | tail -2
+  MG_POOL_MMA=1 timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "pool or block" 2>&1 | tail -2
+  MG_POOL_MMA=1 timeout 150 python bench.py --steps 300 --warmup 10 --no-cpu-baseline > gpurun_out/ab_mma.log 2> gpurun_out/ab_mma.err
+  summ gpurun_out/ab_mma.log
   for dyn in 0 1; do
     MG_POOL_DYNAMIC=$dyn timeout 150 python bench.py --steps 300 --warmup 10 --no-cpu-baseline > gpurun_out/ab_dyn$dyn.log 2> gpurun_out/ab_dyn$dyn.err
     summ gpurun_out/ab_dyn$dyn.log
