@@ -9,34 +9,9 @@
 
 #include "common.cuh"
 
-namespace mg {
+#include "pool_tma_kernels.cuh"
 
-// ------------------------------------------------------------------------------------------
-// K1: (B,C,Hf,Wf) -> (B, Hp*Wp, C), mean over ph x pw windows, zero padded right/bottom
-// oracle: image_to_patches(x).mean((2,3))  (patch_graph_construction.py:27-47)
-// ------------------------------------------------------------------------------------------
-template <typename T>
-struct Vec16;
-template <>
-struct Vec16<float> {
-  static constexpr int N = 4;
-  static __device__ __forceinline__ float sum(const float* p) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    return (v.x + v.y) + (v.z + v.w);
-  }
-};
-template <>
-struct Vec16<__nv_bfloat16> {
-  static constexpr int N = 8;
-  static __device__ __forceinline__ float sum(const __nv_bfloat16* p) {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    float s = 0.f;
-    const unsigned w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s += __uint_as_float(w[i] << 16) + __uint_as_float(w[i] & 0xffff0000u);
-    return s;
-  }
-};
+namespace mg {
 
 // channels per block = warps per block, one channel strip per warp.  Measured at cfg 2 (B200, two shard branches):
 // 32 / 16 / 8 / 4 / 2 channels per block -> 169.2 / 168.5 / 171.2 / 164.4 / 163.9 us per step: many short blocks ramp the
@@ -93,69 +68,6 @@ __global__ void __launch_bounds__(256) pool_patches_vec_kernel(const TX* __restr
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// TMA path (default when it applies): a (image, channel, patch-row) strip is ph FULL rows of the map = one contiguous
-// run of ph*Wf elements, so the feature map is a stream of contiguous strips.  Persistent CTAs (one per SM) take strips
-// round-robin; inside a CTA warp w owns strips w, w + kPtWarps, ... and runs its OWN ring of `stages` shared-memory
-// buffers: lane 0 moves whole rows global -> shared with cp.async.bulk (chunks of <= stage_bytes) completing on the
-// ring's mbarriers (expect_tx / complete_tx), always `stages` chunks ahead of the chunk being summed, so ~200 KB per SM
-// are in flight with no global load instructions or address arithmetic in the summing code.  The warp reads a landed
-// chunk with conflict-free 16-byte shared loads (kPtUnroll rows per batch), keeps fp32 column sums in registers, folds
-// lanes into patch columns by shuffle and stores one (N,C) element per patch.  A ring is private to its warp, so the
-// buffer hand-back needs no second barrier: after __syncwarp() lane 0 re-arms the buffer it has just drained.  Strips
-// are ordered channel-fastest so that concurrently processed strips fill the same output sectors.
-// ------------------------------------------------------------------------------------------
-constexpr int kPtWarps = 8;
-constexpr int kPtUnroll = 8;        // rows whose 16-byte shared loads are issued together
-constexpr int kPtMaxPasses = 8;
-constexpr int kPtSmemBytes = 208 * 1024;
-
-__device__ __forceinline__ uint32_t pt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void pt_mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void pt_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void pt_mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "PT_WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra PT_WAIT_DONE;\n"
-      "bra PT_WAIT_LOOP;\n"
-      "PT_WAIT_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-// read-once stream: L2 evict-first policy so the map does not displace the block's working set
-__device__ __forceinline__ void pt_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-      : "memory");
-}
-
-// sum of 16 bytes as fp32
-template <typename T>
-__device__ __forceinline__ float pt_sum16(const uint4& u);
-template <>
-__device__ __forceinline__ float pt_sum16<float>(const uint4& u) {
-  return (__uint_as_float(u.x) + __uint_as_float(u.y)) + (__uint_as_float(u.z) + __uint_as_float(u.w));
-}
-template <>
-__device__ __forceinline__ float pt_sum16<__nv_bfloat16>(const uint4& u) {
-  const unsigned w[4] = {u.x, u.y, u.z, u.w};
-  float lo = 0.f, hi = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    lo += __uint_as_float(w[i] << 16);
-    hi += __uint_as_float(w[i] & 0xffff0000u);
-  }
-  return lo + hi;
-}
 
 // Dynamic strip scheduling (MG_POOL_DYNAMIC=1; off by default: written after the round-1 GPU budget was spent, not yet
 // measured).  Counter pairs live in a small per-device array; the kernel's last CTA re-arms the pair it used.  A launch
@@ -185,307 +97,6 @@ static int* pool_counters(cudaStream_t st) {
     return i < 32 ? base[dev] + 2 * (32 + i) : nullptr;
   }
   return base[dev] + 2 * (next_eager[dev].fetch_add(1) % 32);
-}
-
-struct PoolTmaArgs {
-  const void* x;
-  void* out;
-  int C, Hf, Wf, ph, pw, Hp, Wp;
-  int rpc;          // rows per chunk (rpc * Wf * esz <= stage_bytes)
-  int nstrips;      // B * Hp * C, strip s = (b * Hp + py) * C + c
-  int stages;       // ring depth per warp
-  int stage_bytes;  // multiple of 128
-  int* counters;    // null: static round-robin strips.  else {next strip, finished CTAs}: dynamic strip scheduling
-};
-
-constexpr int kPtFifo = 16;         // per-warp FIFO of fetched strip ids (dynamic scheduling), > stages + 1
-
-// walks the chunks of one warp's strips in order
-template <typename TX>
-struct PtCursor {
-  int s, step, r0, rows, c;
-  size_t orow;
-  const TX* base;
-  __device__ __forceinline__ void load(const PoolTmaArgs& A) {
-    if (s >= A.nstrips) return;
-    c = s % A.C;
-    const int bp = s / A.C;
-    const int py = bp % A.Hp, b = bp / A.Hp;
-    const int y0 = py * A.ph;
-    rows = min(A.Hf, y0 + A.ph) - y0;
-    r0 = 0;
-    orow = ((size_t)b * A.Hp + py) * A.Wp;
-    base = reinterpret_cast<const TX*>(A.x) + (((size_t)b * A.C + c) * A.Hf + y0) * A.Wf;
-  }
-  __device__ __forceinline__ bool valid(const PoolTmaArgs& A) const { return s < A.nstrips; }
-  // advance by one chunk; returns true when the strip is exhausted (the caller then sets s and calls load)
-  __device__ __forceinline__ bool advance(const PoolTmaArgs& A) {
-    r0 += A.rpc;
-    return r0 >= rows;
-  }
-};
-
-template <typename TX, typename TO, bool DYN>
-__global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(const PoolTmaArgs A) {
-  constexpr int VEC = Vec16<TX>::N;
-  extern __shared__ __align__(128) unsigned char pt_smem[];
-  const int q = A.stages;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* ring = pt_smem + (size_t)warp * q * A.stage_bytes;
-  const uint32_t ring0 = pt_smem_u32(ring);
-  const uint32_t full0 = pt_smem_u32(pt_smem) + (uint32_t)(kPtWarps * q) * (uint32_t)A.stage_bytes + 8u * (uint32_t)(warp * q);
-  if (lane == 0) {
-    for (int i = 0; i < q; ++i) pt_mbar_init(full0 + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  const int row_bytes = A.Wf * (int)sizeof(TX);
-  const int rv = row_bytes >> 4;                              // 16-byte vectors per row
-  const int nvec = A.Wf / VEC;
-  const int passes = ceil_div(nvec, 32);
-  const int lpp = A.pw / VEC;
-  const float inv = 1.f / (float)(A.ph * A.pw);
-  TO* out = reinterpret_cast<TO*>(A.out);
-
-  // Strip order.  Static: warp w of CTA b takes strips b + (w + 8 i) * grid.  Dynamic (A.counters): every warp draws
-  // its next strip from one global counter, so CTAs that become resident late (SMs held by a neighbouring step's
-  // cluster kernel) simply draw fewer strips; the issue cursor draws, the consume cursor follows through a small
-  // per-warp FIFO in shared memory (an id >= nstrips terminates both).
-  constexpr bool dynamic = DYN;                              // the static instantiation carries none of the dynamic code
-  int* fifo = reinterpret_cast<int*>(pt_smem + (size_t)kPtWarps * q * (A.stage_bytes + 8)) + warp * kPtFifo;
-  int tail = 0, head = 0;
-  auto draw = [&]() -> int {                                    // issue side: next strip id
-    int s = 0;
-    if (lane == 0) {
-      s = atomicAdd(A.counters, 1);
-      fifo[tail & (kPtFifo - 1)] = s;
-    }
-    ++tail;
-    __syncwarp();
-    return __shfl_sync(kFull, s, 0);
-  };
-  auto follow = [&]() -> int {                                  // consume side: same sequence, later
-    const int s = fifo[head & (kPtFifo - 1)];
-    ++head;
-    return s;
-  };
-  PtCursor<TX> ic, cc;                                        // issue cursor (q chunks ahead), consume cursor
-  ic.step = cc.step = kPtWarps * gridDim.x;
-  if constexpr (dynamic) {
-    ic.s = draw();
-    cc.s = follow();
-  } else {
-    ic.s = cc.s = blockIdx.x + warp * gridDim.x;
-  }
-  ic.load(A);
-  cc.load(A);
-  int issued = 0;
-  auto issue = [&]() {
-    if (!ic.valid(A)) return;
-    if (lane == 0) {
-      const int st = issued % q;
-      const uint32_t bytes = (uint32_t)(min(A.rpc, ic.rows - ic.r0) * row_bytes);
-      pt_mbar_expect_tx(full0 + 8 * st, bytes);
-      pt_bulk_g2s(ring0 + (uint32_t)st * (uint32_t)A.stage_bytes, ic.base + (size_t)ic.r0 * A.Wf, bytes, full0 + 8 * st, policy);
-    }
-    ++issued;
-    if (ic.advance(A)) {
-      if constexpr (dynamic) ic.s = draw();
-      else ic.s += ic.step;
-      ic.load(A);
-    }
-  };
-  for (int t = 0; t < q; ++t) issue();
-
-  int consumed = 0;
-  float acc[kPtMaxPasses];
-  while (cc.valid(A)) {
-    if (cc.r0 == 0) {
-#pragma unroll
-      for (int p = 0; p < kPtMaxPasses; ++p) acc[p] = 0.f;
-    }
-    const int st = consumed % q;
-    pt_mbar_wait(full0 + 8 * st, (uint32_t)((consumed / q) & 1));
-    const int nr = min(A.rpc, cc.rows - cc.r0);
-    const uint4* sp = reinterpret_cast<const uint4*>(ring + (size_t)st * A.stage_bytes) + lane;
-    // runtime loop over the 512-byte column passes (ONE copy of the summing code: fully unrolling it per pass made the
-    // kernel instruction-cache bound); the pass's register accumulator is selected by predicated adds
-    for (int p = 0; p < passes; ++p) {
-      float part = 0.f;
-      if (p * 32 + lane < nvec) {
-        const uint4* a0 = sp + p * 32;
-        int r = 0;
-        for (; r + kPtUnroll <= nr; r += kPtUnroll) {
-          uint4 u[kPtUnroll];
-#pragma unroll
-          for (int j = 0; j < kPtUnroll; ++j) u[j] = a0[(r + j) * rv];
-          float t[kPtUnroll];
-#pragma unroll
-          for (int j = 0; j < kPtUnroll; ++j) t[j] = pt_sum16<TX>(u[j]);
-#pragma unroll
-          for (int h = kPtUnroll / 2; h > 0; h >>= 1)
-#pragma unroll
-            for (int j = 0; j < h; ++j) t[j] += t[j + h];
-          part += t[0];
-        }
-        for (; r < nr; ++r) part += pt_sum16<TX>(a0[r * rv]);
-      }
-#pragma unroll
-      for (int pp = 0; pp < kPtMaxPasses; ++pp)
-        if (pp == p) acc[pp] += part;
-    }
-    __syncwarp();                                             // every lane has read the buffer: lane 0 may re-arm it
-    issue();
-    ++consumed;
-    const bool last = cc.r0 + A.rpc >= cc.rows;
-    if (last) {
-#pragma unroll
-      for (int p = 0; p < kPtMaxPasses; ++p) {
-        if (p < passes) {
-          float v = acc[p];
-          for (int o = 1; o < lpp; o <<= 1) v += __shfl_xor_sync(kFull, v, o);
-          const int px = (p * 32 + lane) / lpp;
-          if ((lane & (lpp - 1)) == 0 && p * 32 + lane < nvec && px < A.Wp)
-            out[(cc.orow + px) * A.C + cc.c] = from_f32<TO>(v * inv);
-        }
-      }
-    }
-    if (cc.advance(A)) {
-      if constexpr (dynamic) cc.s = follow();
-      else cc.s += cc.step;
-      cc.load(A);
-    }
-  }
-  if constexpr (dynamic) {                                    // the last CTA to finish re-arms the counters
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(A.counters + 1, 1) == (int)gridDim.x - 1) {
-        A.counters[0] = 0;
-        A.counters[1] = 0;
-        __threadfence();
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Tensor-core summation (opt-in, MG_POOL_MMA=1; bf16 maps, pw == 16, Wf % 256 == 0).  STATUS: written after the
-// round-1 GPU budget was spent — compiles, NOT yet run on hardware, off by default.
-// Why: the bulk-copy kernel above always finds its data landed (long-scoreboard stalls 2 % of samples) and spends its
-// time ISSUING the sum — ~21 warp instructions per 512 bytes (shift / mask / add per bf16 pair) with two warps per
-// scheduler (profiles/r1_pool_tma.md).  A patch row of 16 bf16 pixels is 32 contiguous bytes, so 512 contiguous bytes
-// of an image row are a 16 x 16 row-major matrix A (row = patch, column = pixel); with B = ones,
-// mma.m16n8k16 (bf16 x bf16 -> fp32) adds that image row's 16 patch-row sums into D, and accumulating D over the ph
-// image rows of the strip gives the 16 patch sums: ONE ldmatrix.x4 + ONE mma per 512 bytes.  Products with 1.0 are
-// exact and the accumulation is fp32, like the scalar code (different summation order).
-// Same persistent per-warp TMA rings and static strip order as pool_patches_tma_kernel; only the consumer differs.
-// ldmatrix lane addresses: matrix m = lane / 8 covers A rows (lane % 8) + 8 (m & 1); the two 16-byte halves of an A row
-// may go to either k half (a sum does not care about k order), so rows 4..7 of every 8-row phase take the other half:
-// the 8 addresses of a phase then fall into 8 different 16-byte bank groups (rows are only 32 bytes apart).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pt_ldmatrix_x4(uint32_t addr, uint32_t (&a)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
-               : "r"(addr)
-               : "memory");
-}
-__device__ __forceinline__ void pt_mma_ones(float (&d)[4], const uint32_t (&a)[4]) {
-  const uint32_t ones = 0x3F803F80u;                          // bf16 (1.0, 1.0)
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(ones), "r"(ones));
-}
-
-template <typename TO>
-__global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_mma_kernel(const PoolTmaArgs A) {
-  using TX = __nv_bfloat16;
-  extern __shared__ __align__(128) unsigned char pt_smem[];
-  const int q = A.stages;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* ring = pt_smem + (size_t)warp * q * A.stage_bytes;
-  const uint32_t ring0 = pt_smem_u32(ring);
-  const uint32_t full0 = pt_smem_u32(pt_smem) + (uint32_t)(kPtWarps * q) * (uint32_t)A.stage_bytes + 8u * (uint32_t)(warp * q);
-  if (lane == 0) {
-    for (int i = 0; i < q; ++i) pt_mbar_init(full0 + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  const int row_bytes = A.Wf * (int)sizeof(TX);
-  const int tiles = A.Wf >> 8;                               // 16 patches x 16 pixels = 512 bytes per tile and image row
-  const float inv = 1.f / (float)(A.ph * A.pw);
-  TO* out = reinterpret_cast<TO*>(A.out);
-  const uint32_t lane_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * 32 + ((((lane >> 4) & 1) ^ ((lane >> 2) & 1)) * 16));
-
-  PtCursor<TX> ic, cc;                                        // issue cursor (q chunks ahead), consume cursor
-  ic.step = cc.step = kPtWarps * gridDim.x;
-  ic.s = cc.s = blockIdx.x + warp * gridDim.x;
-  ic.load(A);
-  cc.load(A);
-  int issued = 0;
-  auto issue = [&]() {
-    if (!ic.valid(A)) return;
-    if (lane == 0) {
-      const int st = issued % q;
-      const uint32_t bytes = (uint32_t)(min(A.rpc, ic.rows - ic.r0) * row_bytes);
-      pt_mbar_expect_tx(full0 + 8 * st, bytes);
-      pt_bulk_g2s(ring0 + (uint32_t)st * (uint32_t)A.stage_bytes, ic.base + (size_t)ic.r0 * A.Wf, bytes, full0 + 8 * st, policy);
-    }
-    ++issued;
-    if (ic.advance(A)) {
-      ic.s += ic.step;
-      ic.load(A);
-    }
-  };
-  for (int t = 0; t < q; ++t) issue();
-
-  int consumed = 0;
-  float d[kPtMaxPasses][4];
-  while (cc.valid(A)) {
-    if (cc.r0 == 0) {
-#pragma unroll
-      for (int p = 0; p < kPtMaxPasses; ++p) d[p][0] = d[p][1] = d[p][2] = d[p][3] = 0.f;
-    }
-    const int st = consumed % q;
-    pt_mbar_wait(full0 + 8 * st, (uint32_t)((consumed / q) & 1));
-    const int nr = min(A.rpc, cc.rows - cc.r0);
-    const uint32_t buf = ring0 + (uint32_t)st * (uint32_t)A.stage_bytes + lane_off;
-    for (int r = 0; r < nr; ++r) {
-#pragma unroll
-      for (int p = 0; p < kPtMaxPasses; ++p) {
-        if (p < tiles) {
-          uint32_t a[4];
-          pt_ldmatrix_x4(buf + (uint32_t)(r * row_bytes + p * 512), a);
-          pt_mma_ones(d[p], a);
-        }
-      }
-    }
-    __syncwarp();                                             // every lane has read the buffer: lane 0 may re-arm it
-    issue();
-    ++consumed;
-    if (cc.r0 + A.rpc >= cc.rows) {                           // strip complete: D rows g and g + 8 of lanes with t == 0
-      if ((lane & 3) == 0) {
-        const int g = lane >> 2;
-#pragma unroll
-        for (int p = 0; p < kPtMaxPasses; ++p) {
-          if (p < tiles) {
-            const int px = p * 16 + g;
-            if (px < A.Wp) out[(cc.orow + px) * A.C + cc.c] = from_f32<TO>(d[p][0] * inv);
-            if (px + 8 < A.Wp) out[(cc.orow + px + 8) * A.C + cc.c] = from_f32<TO>(d[p][2] * inv);
-          }
-        }
-      }
-    }
-    if (cc.advance(A)) {
-      cc.s += cc.step;
-      cc.load(A);
-    }
-  }
 }
 
 // generic path: any window; one thread per output element (px fastest so window reads share lines)

@@ -43,8 +43,10 @@ static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+#ifndef MG_EMU_WARP   // (cuda_warp_shim.h provides real lock-step versions)
 // common.cuh helpers that are compiled but not executed by the emulated kernels
 static inline float __shfl_xor_sync(unsigned, float v, int, int = 32) { abort(); return v; }
+#endif
 static inline int atomicMax(int* a, int v) { int o = *a; if (v > o) *a = v; return o; }
 static inline unsigned atomicMin(unsigned* a, unsigned v) { unsigned o = *a; if (v < o) *a = v; return o; }
 
