@@ -18,6 +18,17 @@ namespace mg {
 
 constexpr int kPushThreads = 512;
 
+#ifndef MG_HOST_EMULATION   // tests/emu provides host versions (tests/test_peer_emulation.py)
+__device__ __forceinline__ void peer_st_release_sys(uint32_t* flag, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t peer_ld_acquire_sys(const uint32_t* flag) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  return v;
+}
+#endif
+
 __global__ void __launch_bounds__(kPushThreads) peer_push_kernel(const uint4* __restrict__ src, int64_t nvec,
                                                                  void* const* __restrict__ peer_bufs, int64_t dst_off_bytes,
                                                                  uint32_t* const* __restrict__ peer_signals, int64_t flag_index,
@@ -30,8 +41,7 @@ __global__ void __launch_bounds__(kPushThreads) peer_push_kernel(const uint4* __
   if (threadIdx.x == 0) {
     const uint32_t v = seq[p] + 1u;                            // CTA p owns seq[p]: launches of one slot are serialised
     seq[p] = v;
-    uint32_t* flag = peer_signals[p] + flag_index;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+    peer_st_release_sys(peer_signals[p] + flag_index, v);
   }
 }
 
@@ -44,8 +54,7 @@ __global__ void peer_wait_kernel(const uint32_t* __restrict__ my_signals, int64_
   wseq[r] = need;
   const uint32_t* flag = my_signals + first_flag + r;
   for (unsigned long long spin = 0; spin < max_spins; ++spin) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    const uint32_t v = peer_ld_acquire_sys(flag);
     if ((int32_t)(v - need) >= 0) return;                      // wrap-safe v >= need
     __nanosleep(64);
   }
@@ -54,6 +63,7 @@ __global__ void peer_wait_kernel(const uint32_t* __restrict__ my_signals, int64_
 
 }  // namespace mg
 
+#ifndef MG_HOST_EMULATION
 using namespace mg;
 
 extern "C" {
@@ -79,3 +89,4 @@ int mg_peer_wait(const uint32_t* my_signals, int64_t first_flag, int world, uint
 }
 
 }  // extern "C"
+#endif  // MG_HOST_EMULATION
