@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B matrix for the variants written after the round-1 GPU budget was spent.  Every command is wrapped in `timeout`;
 # results land in gpurun_out/ab_*.log.  Usage (from the repo root):
-#   gpurun --timeout 600 -- 'bash tools/ab_next_round.sh 1'            # one GPU: dynamic strip scheduling of the pool kernel
+#   gpurun --timeout 1200 -- 'bash tools/ab_next_round.sh 1'           # one GPU: fusion gather, pool kernel variants (tensor-core sum, dynamic strips)
 #   gpurun --gpus 2 --timeout 600 -- 'bash tools/ab_next_round.sh 2'   # two GPUs: exchange variants (inline / captured / bucketed / p2p)
 #   gpurun --gpus 8 --timeout 400 -- 'bash tools/ab_next_round.sh 8 inline'   # one variant at a time at 8 GPUs
 N=${1:-1}
