@@ -113,10 +113,7 @@ struct PoolTmaArgs {
   int nstrips;      // B * Hp * C, strip s = (b * Hp + py) * C + c
   int stages;       // ring depth per warp
   int stage_bytes;  // multiple of 128
-  int* counters;    // null: static round-robin strips.  else {next strip, finished CTAs}: dynamic strip scheduling
 };
-
-constexpr int kPtFifo = 16;         // per-warp FIFO of fetched strip ids (dynamic scheduling), > stages + 1
 
 // walks the chunks of one warp's strips in order
 template <typename TX>
@@ -143,7 +140,7 @@ struct PtCursor {
   }
 };
 
-template <typename TX, typename TO, bool DYN>
+template <typename TX, typename TO>
 __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(const PoolTmaArgs A) {
   constexpr int VEC = Vec16<TX>::N;
   extern __shared__ __align__(128) unsigned char pt_smem[];
@@ -166,36 +163,11 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
   const float inv = 1.f / (float)(A.ph * A.pw);
   TO* out = reinterpret_cast<TO*>(A.out);
 
-  // Strip order.  Static: warp w of CTA b takes strips b + (w + 8 i) * grid.  Dynamic (A.counters): every warp draws
-  // its next strip from one global counter, so CTAs that become resident late (SMs held by a neighbouring step's
-  // cluster kernel) simply draw fewer strips; the issue cursor draws, the consume cursor follows through a small
-  // per-warp FIFO in shared memory (an id >= nstrips terminates both).
-  constexpr bool dynamic = DYN;                              // the static instantiation carries none of the dynamic code
-  int* fifo = reinterpret_cast<int*>(pt_smem + (size_t)kPtWarps * q * (A.stage_bytes + 8)) + warp * kPtFifo;
-  int tail = 0, head = 0;
-  auto draw = [&]() -> int {                                    // issue side: next strip id
-    int s = 0;
-    if (lane == 0) {
-      s = atomicAdd(A.counters, 1);
-      fifo[tail & (kPtFifo - 1)] = s;
-    }
-    ++tail;
-    __syncwarp();
-    return __shfl_sync(kFull, s, 0);
-  };
-  auto follow = [&]() -> int {                                  // consume side: same sequence, later
-    const int s = fifo[head & (kPtFifo - 1)];
-    ++head;
-    return s;
-  };
+  // Strip order: warp w of CTA b takes strips b + (w + 8 i) * grid.  (A global strip counter and a tensor-core summation
+  // were measured in round 2 and lost: 42.7 us and 50.2 us against 40.6 us, profiles/r2_pool_variants.md.)
   PtCursor<TX> ic, cc;                                        // issue cursor (q chunks ahead), consume cursor
   ic.step = cc.step = kPtWarps * gridDim.x;
-  if constexpr (dynamic) {
-    ic.s = draw();
-    cc.s = follow();
-  } else {
-    ic.s = cc.s = blockIdx.x + warp * gridDim.x;
-  }
+  ic.s = cc.s = blockIdx.x + warp * gridDim.x;
   ic.load(A);
   cc.load(A);
   int issued = 0;
@@ -209,8 +181,7 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
     }
     ++issued;
     if (ic.advance(A)) {
-      if constexpr (dynamic) ic.s = draw();
-      else ic.s += ic.step;
+      ic.s += ic.step;
       ic.load(A);
     }
   };
@@ -266,137 +237,6 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
           const int px = (p * 32 + lane) / lpp;
           if ((lane & (lpp - 1)) == 0 && p * 32 + lane < nvec && px < A.Wp)
             out[(cc.orow + px) * A.C + cc.c] = from_f32<TO>(v * inv);
-        }
-      }
-    }
-    if (cc.advance(A)) {
-      if constexpr (dynamic) cc.s = follow();
-      else cc.s += cc.step;
-      cc.load(A);
-    }
-  }
-  if constexpr (dynamic) {                                    // the last CTA to finish re-arms the counters
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(A.counters + 1, 1) == (int)gridDim.x - 1) {
-        A.counters[0] = 0;
-        A.counters[1] = 0;
-        __threadfence();
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Tensor-core summation (opt-in, MG_POOL_MMA=1; bf16 maps, pw == 16, Wf % 256 == 0).  STATUS: written after the
-// round-1 GPU budget was spent — NOT yet run on hardware, off by default; its control flow and indexing are checked by
-// the host emulation (tests/test_pool_emulation.py), its fragment mapping by tests/test_pool_schedule_model.py.
-// Why: the bulk-copy kernel above always finds its data landed (long-scoreboard stalls 2 % of samples) and spends its
-// time ISSUING the sum — ~21 warp instructions per 512 bytes (shift / mask / add per bf16 pair) with two warps per
-// scheduler (profiles/r1_pool_tma.md).  A patch row of 16 bf16 pixels is 32 contiguous bytes, so 512 contiguous bytes
-// of an image row are a 16 x 16 row-major matrix A (row = patch, column = pixel); with B = ones,
-// mma.m16n8k16 (bf16 x bf16 -> fp32) adds that image row's 16 patch-row sums into D, and accumulating D over the ph
-// image rows of the strip gives the 16 patch sums: ONE ldmatrix.x4 + ONE mma per 512 bytes.  Products with 1.0 are
-// exact and the accumulation is fp32, like the scalar code (different summation order).
-// Same persistent per-warp TMA rings and static strip order as pool_patches_tma_kernel; only the consumer differs.
-// ldmatrix lane addresses: matrix m = lane / 8 covers A rows (lane % 8) + 8 (m & 1); the two 16-byte halves of an A row
-// may go to either k half (a sum does not care about k order), so rows 4..7 of every 8-row phase take the other half:
-// the 8 addresses of a phase then fall into 8 different 16-byte bank groups (rows are only 32 bytes apart).
-// ------------------------------------------------------------------------------------------
-#ifndef MG_HOST_EMULATION
-__device__ __forceinline__ void pt_ldmatrix_x4(uint32_t addr, uint32_t (&a)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
-               : "r"(addr)
-               : "memory");
-}
-__device__ __forceinline__ void pt_mma_ones(float (&d)[4], const uint32_t (&a)[4]) {
-  const uint32_t ones = 0x3F803F80u;                          // bf16 (1.0, 1.0)
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(ones), "r"(ones));
-}
-#endif
-
-template <typename TO>
-__global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_mma_kernel(const PoolTmaArgs A) {
-  using TX = __nv_bfloat16;
-  extern __shared__ __align__(128) unsigned char pt_smem[];
-  const int q = A.stages;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* ring = pt_smem + (size_t)warp * q * A.stage_bytes;
-  const uint32_t ring0 = pt_smem_u32(ring);
-  const uint32_t full0 = pt_smem_u32(pt_smem) + (uint32_t)(kPtWarps * q) * (uint32_t)A.stage_bytes + 8u * (uint32_t)(warp * q);
-  if (lane == 0) {
-    for (int i = 0; i < q; ++i) pt_mbar_init(full0 + 8 * i, 1);
-    pt_fence_mbar_init();
-  }
-  __syncwarp();
-  const uint64_t policy = pt_policy_evict_first();
-  const int row_bytes = A.Wf * (int)sizeof(TX);
-  const int tiles = A.Wf >> 8;                               // 16 patches x 16 pixels = 512 bytes per tile and image row
-  const float inv = 1.f / (float)(A.ph * A.pw);
-  TO* out = reinterpret_cast<TO*>(A.out);
-  const uint32_t lane_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * 32 + ((((lane >> 4) & 1) ^ ((lane >> 2) & 1)) * 16));
-
-  PtCursor<TX> ic, cc;                                        // issue cursor (q chunks ahead), consume cursor
-  ic.step = cc.step = kPtWarps * gridDim.x;
-  ic.s = cc.s = blockIdx.x + warp * gridDim.x;
-  ic.load(A);
-  cc.load(A);
-  int issued = 0;
-  auto issue = [&]() {
-    if (!ic.valid(A)) return;
-    if (lane == 0) {
-      const int st = issued % q;
-      const uint32_t bytes = (uint32_t)(min(A.rpc, ic.rows - ic.r0) * row_bytes);
-      pt_mbar_expect_tx(full0 + 8 * st, bytes);
-      pt_bulk_g2s(ring0 + (uint32_t)st * (uint32_t)A.stage_bytes, ic.base + (size_t)ic.r0 * A.Wf, bytes, full0 + 8 * st, policy);
-    }
-    ++issued;
-    if (ic.advance(A)) {
-      ic.s += ic.step;
-      ic.load(A);
-    }
-  };
-  for (int t = 0; t < q; ++t) issue();
-
-  int consumed = 0;
-  float d[kPtMaxPasses][4];
-  while (cc.valid(A)) {
-    if (cc.r0 == 0) {
-#pragma unroll
-      for (int p = 0; p < kPtMaxPasses; ++p) d[p][0] = d[p][1] = d[p][2] = d[p][3] = 0.f;
-    }
-    const int st = consumed % q;
-    pt_mbar_wait(full0 + 8 * st, (uint32_t)((consumed / q) & 1));
-    const int nr = min(A.rpc, cc.rows - cc.r0);
-    const uint32_t buf = ring0 + (uint32_t)st * (uint32_t)A.stage_bytes + lane_off;
-    for (int r = 0; r < nr; ++r) {
-#pragma unroll
-      for (int p = 0; p < kPtMaxPasses; ++p) {
-        if (p < tiles) {
-          uint32_t a[4];
-          pt_ldmatrix_x4(buf + (uint32_t)(r * row_bytes + p * 512), a);
-          pt_mma_ones(d[p], a);
-        }
-      }
-    }
-    __syncwarp();                                             // every lane has read the buffer: lane 0 may re-arm it
-    issue();
-    ++consumed;
-    if (cc.r0 + A.rpc >= cc.rows) {                           // strip complete: D rows g and g + 8 of lanes with t == 0
-      if ((lane & 3) == 0) {
-        const int g = lane >> 2;
-#pragma unroll
-        for (int p = 0; p < kPtMaxPasses; ++p) {
-          if (p < tiles) {
-            const int px = p * 16 + g;
-            if (px < A.Wp) out[(cc.orow + px) * A.C + cc.c] = from_f32<TO>(d[p][0] * inv);
-            if (px + 8 < A.Wp) out[(cc.orow + px + 8) * A.C + cc.c] = from_f32<TO>(d[p][2] * inv);
-          }
         }
       }
     }

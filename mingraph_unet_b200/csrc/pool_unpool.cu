@@ -4,8 +4,6 @@
 #include <stdlib.h>
 
 #include <algorithm>
-#include <atomic>
-#include <type_traits>
 
 #include "common.cuh"
 
@@ -68,36 +66,6 @@ __global__ void __launch_bounds__(256) pool_patches_vec_kernel(const TX* __restr
   }
 }
 
-
-// Dynamic strip scheduling (MG_POOL_DYNAMIC=1; off by default: written after the round-1 GPU budget was spent, not yet
-// measured).  Counter pairs live in a small per-device array; the kernel's last CTA re-arms the pair it used.  A launch
-// recorded into a CUDA graph OWNS its pair for the life of the process (its replays are serialised by the graph's
-// stream; pairs 32..63, static scheduling once they are used up), eager launches take pairs 0..31 round-robin — so an
-// eager launch can never share a pair with a concurrently replaying graph.
-__device__ int g_pool_counters[64][2];
-static int* pool_counters(cudaStream_t st) {
-  static const int enabled = getenv("MG_POOL_DYNAMIC") ? atoi(getenv("MG_POOL_DYNAMIC")) : 0;
-  if (!enabled) return nullptr;
-  constexpr int kMaxDev = 64;
-  static int* base[kMaxDev] = {};                            // the symbol has one instance per device
-  static std::atomic<unsigned> next_eager[kMaxDev], next_captured[kMaxDev];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
-  if (!base[dev] && cudaGetSymbolAddress(reinterpret_cast<void**>(&base[dev]), g_pool_counters) != cudaSuccess) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  if (cs == cudaStreamCaptureStatusActive) {
-    const unsigned i = next_captured[dev].fetch_add(1);
-    return i < 32 ? base[dev] + 2 * (32 + i) : nullptr;
-  }
-  return base[dev] + 2 * (next_eager[dev].fetch_add(1) % 32);
-}
 
 // generic path: any window; one thread per output element (px fastest so window reads share lines)
 template <typename TX, typename TO>
@@ -340,8 +308,8 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
     int stages = std::max(2, std::min(8, stages_env));
     int stage_bytes = std::max(row_bytes, std::max(1024, chunk_env)) / 128 * 128;
     stage_bytes = std::max(stage_bytes, (row_bytes + 127) / 128 * 128);
-    while (stages > 2 && (size_t)kPtWarps * stages * (stage_bytes + 8) + kPtWarps * kPtFifo * 4 > (size_t)kPtSmemBytes) --stages;
-    const size_t smem = (size_t)kPtWarps * stages * (stage_bytes + 8) + kPtWarps * kPtFifo * 4;
+    while (stages > 2 && (size_t)kPtWarps * stages * (stage_bytes + 8) > (size_t)kPtSmemBytes) --stages;
+    const size_t smem = (size_t)kPtWarps * stages * (stage_bytes + 8);
     if (fast && variant == 0 && smem <= (size_t)kPtSmemBytes && ceil_div(Wf / VEC, 32) <= kPtMaxPasses && lpp <= 32) {
       PoolTmaArgs A;
       A.x = x; A.out = out; A.C = C; A.Hf = Hf; A.Wf = Wf; A.ph = ph; A.pw = pw; A.Hp = Hp; A.Wp = Wp;
@@ -349,22 +317,7 @@ static int launch_pool(const void* x, int B, int C, int Hf, int Wf, int ph, int 
       A.nstrips = B * Hp * C;
       A.stages = stages;
       A.stage_bytes = stage_bytes;
-      // MG_POOL_MMA=1 (opt-in, not yet run on hardware): tensor-core summation for bf16 maps with 16-pixel-wide patches
-      static const int use_mma = getenv("MG_POOL_MMA") ? atoi(getenv("MG_POOL_MMA")) : 0;
-      if constexpr (std::is_same<TX, __nv_bfloat16>::value) {
-        if (use_mma && pw == 16 && Wf % 256 == 0 && Wf / 256 <= kPtMaxPasses) {
-          A.counters = nullptr;
-          auto mk = pool_patches_mma_kernel<TO>;
-          if (cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes) != cudaSuccess) {
-            set_error("mg_pool_patches: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
-            return MG_ERR_CUDA;
-          }
-          mk<<<std::min(num_sms(), ceil_div(A.nstrips, kPtWarps)), kPtWarps * 32, smem, st>>>(A);
-          return check_launch("pool_patches_mma_kernel");
-        }
-      }
-      A.counters = pool_counters(st);
-      auto kern = A.counters ? pool_patches_tma_kernel<TX, TO, true> : pool_patches_tma_kernel<TX, TO, false>;
+      auto kern = pool_patches_tma_kernel<TX, TO>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes) != cudaSuccess) {
         set_error("mg_pool_patches: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
         return MG_ERR_CUDA;

@@ -2,20 +2,15 @@
 untouched reference (tests/golden/fusion.npz) and the CPU oracle: the per-region gather is bit-exact in fp32 (it moves
 values), bf16 output equals the rounded fp32 result, the dense branches equal torch's own cat / bilinear resize.
 
-OPT-IN for now: the kernel was written after the round-1 GPU budget was spent and has not run on hardware yet, so
-these tests only run with ``MG_TEST_UNVERIFIED=1`` (first thing to run in the next round:
-``MG_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_zfusion.py -m gpu -q``).  On the CPU the kernel SOURCE is compiled for the host
-and executed thread by thread (tests/test_fusion_emulation.py, which also drives the module and the ctypes wrapper end to
-end on the emulated kernel), and tests/test_oracle_fusion.py models its index arithmetic."""
-import os
+First run on hardware in round 2 (12 passed; rates in profiles/r2_fusion_gather.md).  On the CPU the kernel SOURCE is
+also compiled for the host and executed thread by thread (tests/test_fusion_emulation.py), and
+tests/test_oracle_fusion.py models its index arithmetic."""
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MG_TEST_UNVERIFIED", "0") != "1",
-                                 reason="csrc/fusion.cu has not run on hardware yet: set MG_TEST_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 
 from oracle import restate as O  # noqa: E402
 
