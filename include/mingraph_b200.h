@@ -245,28 +245,53 @@ MG_API int mg_tv_loss_backward(const void* x, int dtype, int B, int C, int H, in
  * table (R, D) f32 = f_g; map (B,H,W) MG_I32 | MG_I64 = region_to_pixel_map (the reference calls .long() on it);
  * out: image b at out + b*out_batch_stride elements, (D,H,W) contiguous planes f32|bf16 — i.e. the channel slice
  * [C_u : C_u + D] of the fused (B, C_u + D, H, W) buffer, so Concat(F_u, F_g) (:143) needs no extra pass.
- * STATUS: compiled, not yet run on hardware (written after the round-1 GPU budget was spent). */
+ * First run on a B200 in round 2: parity green, 0.80-0.87 of the measured HBM peak (profiles/r2_fusion_gather.md). */
 MG_API int mg_region_map_gather(const float* table, int R, int D, const void* map, int map_dtype, int B, int H, int W,
                                 void* out, int out_dtype, int64_t out_batch_stride, mg_stream_t stream);
 
 /* ---- peer-memory exchange of the small per-image outputs (multi-GPU, scope row (e)) ----------------
  * The batch shards by image (scripts/train_end_to_end.py:300-425 builds one graph per image), so the only
- * per-step exchange is an all-gather of l_partition | region_features | hard_labels.  These two entry points do it
- * over NVLink peer mappings instead of a collective call: every rank owns a symmetric "gathered" buffer and a
- * signal pad, both mapped into every peer (peer_bufs_dev / peer_signals_dev: DEVICE arrays of `world` pointers,
- * entry p = rank p's buffer / signal pad as seen from this GPU).
- * mg_peer_push: copy nbytes from src into [dst_offset_bytes, +nbytes) of EVERY peer's buffer, then publish a
- *   sequence number (seq[p] is incremented on the device, so the call is graph-replayable) at
- *   peer_signals[p][flag_index] with a system-scope release.  seq: `world` uint32 owned by the caller, zeroed once.
- *   Waits for nothing.
- * mg_peer_wait: block the stream until my_signals[first_flag + r] has reached this consumer's own count for every
- *   source rank r (wseq: `world` uint32, zeroed once); bounded spin (a few seconds), on expiry status[0] = 1 (nullable).
- * STATUS: compiled but not yet run on hardware (round-1 GPU budget was spent); opt-in. */
-MG_API int mg_peer_push(const void* src, int64_t nbytes, const void* const* peer_bufs_dev, int world,
-                        int64_t dst_offset_bytes, const void* const* peer_signals_dev, int64_t flag_index, uint32_t* seq,
+ * per-step exchange is an all-gather of l_partition | region_features | hard_labels (74 KB per rank at cfg 2).  It is
+ * FUSED into the block kernel: mg_block_forward_push is mg_block_forward plus, while it computes, stores of that
+ * payload into slice `rank` of every rank's gathered buffer over NVLink peer mappings, and a sequence number published
+ * in every rank's flag array by the last CTA (system-scope release).  No collective call, nothing waits for a peer.
+ *
+ * Buffers.  Every rank allocates one gathered buffer and one flag array with mg_peer_mem_alloc (cudaMalloc, zeroed,
+ * plus a 64-byte CUDA IPC handle), ranks exchange the handles (any host channel) and map each other's allocations
+ * with mg_peer_mem_open.  mg_peer_mem_* are host calls for set-up / tear-down: they allocate and synchronise, unlike
+ * everything else in this header.  Gathered buffer layout (floats): [2 parity][slots][world][slice], one slice =
+ * loss [B] | region_out [B][K][D] | labels [B][N] (int32 bits), the layout of mg_block_forward's small outputs.
+ * Flags: [slots][world] uint32.
+ *
+ * mg_peer_out_t describes one (slot, rank): peer_bufs_dev / peer_flags_dev are DEVICE arrays of `world` pointers
+ * (entry p = rank p's allocation as mapped on this GPU; entry `rank` = the local one); slice_offset = (slot * world +
+ * rank) * slice floats; parity_stride = slots * world * slice; flag_index = slot * world + rank; seq, done = one
+ * uint32 each on this device, zeroed once (seq counts the slot's completed steps and selects the parity half).
+ * Step s of a slot lands in parity half s & 1 with flag value s + 1; see csrc/peer_exchange.cu for why that needs no
+ * acknowledgement.  The launch must cover the slot's whole batch (B = images of the slice).
+ *
+ * mg_peer_wait: consumer side — the stream continues once my_flags[first_flag + r] >= *seq for every source rank r
+ * (enqueue it after the slot's mg_block_forward_push on the same stream); bounded spin of a few seconds, on expiry
+ * status[0] = 1 (nullable). */
+typedef struct mg_peer_out {
+  const void* const* peer_bufs_dev;
+  const void* const* peer_flags_dev;
+  int32_t world, rank;
+  int64_t slice_offset, parity_stride, flag_index;
+  uint32_t* seq;
+  uint32_t* done;
+} mg_peer_out_t;
+
+MG_API int mg_block_forward_push(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2,
+                                 int H3, int K, float slope1, float slope2, float slope3, const float* prep, float* h,
+                                 float* q_work, float* S, int32_t* labels, float* loss, float* region_in,
+                                 float* region_out, const mg_peer_out_t* peer, mg_stream_t stream);
+MG_API int mg_peer_wait(const uint32_t* my_flags, int64_t first_flag, int world, const uint32_t* seq, int32_t* status,
                         mg_stream_t stream);
-MG_API int mg_peer_wait(const uint32_t* my_signals, int64_t first_flag, int world, uint32_t* wseq, int32_t* status,
-                        mg_stream_t stream);
+MG_API int mg_peer_mem_alloc(int64_t nbytes, void** ptr_host, unsigned char* handle64_host);
+MG_API int mg_peer_mem_open(const unsigned char* handle64_host, void** ptr_host);
+MG_API int mg_peer_mem_close(void* ptr);
+MG_API int mg_peer_mem_free(void* ptr);
 
 #ifdef __cplusplus
 }

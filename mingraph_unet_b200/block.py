@@ -63,14 +63,16 @@ class GraphBlock(nn.Module):
                 feature_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, _block_outs=None,
                 f_unet_patches: Optional[torch.Tensor] = None, patch_labels_y: Optional[torch.Tensor] = None,
-                feature_loss_margin: float = 1.0, _after_block=None) -> GraphBlockOutput:
+                feature_loss_margin: float = 1.0, _after_block=None, _peer=None) -> GraphBlockOutput:
         """Either ``node_features (B,N,in)`` + ``image_size (H,W)`` or a per-pixel ``feature_map
         (B,in,H,W)`` (patch-mean pooled to node features).  ``out`` may be a channel slice of a fusion
         buffer ``(B,Ctot,H,W)[:, c0:c0+D]``; the dense map is written there directly.
         ``f_unet_patches (B,N,D)`` + ``patch_labels_y (B,N)``: also return ``l_feature``, the reference's
         feature-consistency loss between them and the patch-GAT output (train_end_to_end.py:344,
-        batch mean of the per-image sums)."""
-        res = self._forward(node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs, _after_block)
+        batch mean of the per-image sums).  ``_peer``: a ``distributed.PeerExchange.slot(i)`` descriptor — the block
+        kernel then also pushes the small outputs to every rank (multi-GPU exchange fused into the launch)."""
+        res = self._forward(node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs, _after_block,
+                            _peer)
         if f_unet_patches is None:
             return res
         if patch_labels_y is None:
@@ -82,7 +84,7 @@ class GraphBlock(nn.Module):
                                                          float(feature_loss_margin)))
 
     def _forward(self, node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs,
-                 _after_block=None) -> GraphBlockOutput:
+                 _after_block=None, _peer=None) -> GraphBlockOutput:
         if (node_features is None) == (feature_map is None):
             raise ValueError("pass exactly one of node_features / feature_map")
         if feature_map is not None:
@@ -121,11 +123,14 @@ class GraphBlock(nn.Module):
         use_fused = (self.fused and not needs_autograd and not (self.training and any(l.dropout_rate > 0 for l in layers))
                      and ops.block_supported(B, nph, npw, node_features.shape[-1], D, layers[0].num_heads,
                                              layers[1].num_heads, layers[2].num_heads, K))
+        if _peer is not None and not use_fused:
+            raise RuntimeError("the fused peer exchange needs the one-launch block kernel (inference, supported shape); "
+                               "use distributed.InlineGather otherwise")
         if use_fused:
             # ONE launch: patch GAT -> predictor GAT -> softmax/argmax -> N-cut -> region pool -> region GAT
             h, S, labels, loss, _, G = ops.block_forward(
                 node_features, nph, npw, self._prepared(), D, layers[0].num_heads, layers[1].num_heads,
-                layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers), outs=_block_outs)
+                layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers), outs=_block_outs, peer=_peer)
             if _after_block is not None:
                 _after_block()          # the small outputs are final here; the un-pool below only reads them
         elif needs_autograd or (self.training and any(l.dropout_rate > 0 for l in layers)):

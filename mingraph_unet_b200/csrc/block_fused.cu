@@ -91,8 +91,24 @@ __host__ __device__ inline SmemLayout smem_layout(const BlockShape& s) {
   return L;
 }
 
+// Multi-GPU exchange fused into the kernel (mg_block_forward_push): while it computes, the kernel also stores the small
+// per-image outputs (loss | region_out | labels, the layout of one packed buffer) into slice `rank` of EVERY rank's
+// gathered buffer through NVLink peer mappings, and the last CTA to finish publishes the step's sequence number in every
+// rank's flag array with a system-scope release.  Nothing here waits for another GPU.
+struct PeerOut {
+  float* const* bufs;       // DEVICE array [world]: rank p's gathered buffer as mapped into this GPU (own rank included)
+  uint32_t* const* flags;   // DEVICE array [world]: rank p's flag array
+  int world;                // 0: no exchange
+  long long slice_off;      // floats: offset of this (slot, rank) slice inside one parity half
+  long long parity_stride;  // floats between the two parity halves (steps alternate: a slice is rewritten every 2nd step)
+  long long flag_index;     // this (slot, rank) flag
+  uint32_t* seq;            // device: steps this slot has completed (advanced by the last CTA)
+  uint32_t* done;           // device: CTAs of the current launch that have finished (re-armed by the last CTA)
+};
+
 struct BlockArgs {
   BlockShape s;
+  PeerOut peer;
   const void* x;            // (B, N, in) f32|bf16
   const float* prep;        // prepared weights (mg_block_prepare)
   float* h;                 // (B, N, D)   patch-GAT output
@@ -171,6 +187,29 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// destination of this step's payload in rank p's gathered buffer
+__device__ __forceinline__ float* peer_slice(const PeerOut& po, int p, uint32_t parity) {
+  return po.bufs[p] + po.slice_off + (long long)parity * po.parity_stride;
+}
+// every thread of the CTA has issued its peer stores: make them visible system-wide, count the CTA in, and let the last
+// CTA of the launch publish the sequence number on every rank (fence / atomic / fence / release chain)
+__device__ __forceinline__ void peer_cta_done(const PeerOut& po, uint32_t seq_now) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t old = atomicAdd(po.done, 1u);
+    if (old == gridDim.x - 1) {
+      __threadfence_system();
+      *po.done = 0u;
+      *po.seq = seq_now + 1u;
+      for (int p = 0; p < po.world; ++p) st_release_sys_u32(po.flags[p] + po.flag_index, seq_now + 1u);
+    }
+  }
 }
 
 template <typename TX>
@@ -298,6 +337,11 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
   float* red = sm + L.red;
   void* barA = sm;
   void* barB = sm + 2;
+  const PeerOut& po = A.peer;
+  // steps this slot has completed so far: its parity selects the half of the peers' buffers this launch writes (the
+  // last CTA advances it only after every CTA has read it: a CTA counts itself in after this load)
+  const uint32_t seq_now = po.world > 0 ? *reinterpret_cast<volatile const uint32_t*>(po.seq) : 0u;
+  const long long lab_off = (long long)s.B * (1 + K * D);       // labels follow loss [B] | region_out [B][K][D]
 
   // ---- P0: stage the prepared weights with TMA bulk copies (region weights only on rank 0) ------
   if (tid == 0) {
@@ -671,6 +715,8 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
       }
       lab[t] = arg;
       A.labels[gb + n] = arg;
+      for (int p = 0; p < po.world; ++p)                       // consecutive threads, consecutive addresses: full sectors
+        reinterpret_cast<int32_t*>(peer_slice(po, p, seq_now & 1u))[lab_off + (long long)gb + n] = arg;
     }
   }
   cluster.sync();                                                                   // #4: S visible
@@ -753,6 +799,7 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
         if (assoc > 1e-8f) l += cut / assoc;                                       // mincut_refinement.py:151-152
       }
       A.loss[b] = l;
+      for (int p = 0; p < po.world; ++p) peer_slice(po, p, seq_now & 1u)[b] = l;
     }
     for (int idx = tid; idx < K * D; idx += kBT) {
       const int c = idx / D;
@@ -767,7 +814,10 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
     }
   }
   cluster.sync();                                                                   // #6: remote smem no longer needed
-  if (crank != 0) return;
+  if (crank != 0) {
+    if (po.world > 0) peer_cta_done(po, seq_now);               // its peer stores were the labels of P4
+    return;
+  }
 
   float* s3 = R + K * D;
   float* a3 = s3 + round_up4(K * 2 * H3);
@@ -836,11 +886,17 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
       const int j = idx / D, f = idx - j * D;
       float t = 0.f;
       for (int h = 0; h < H3; ++h) t += y3[(j * H3 + h) * D + f];
-      A.region_out[(size_t)b * K * D + idx] = t * inv_h3;
+      const float y = t * inv_h3;
+      A.region_out[(size_t)b * K * D + idx] = y;
+      for (int p = 0; p < po.world; ++p) peer_slice(po, p, seq_now & 1u)[s.B + (long long)b * K * D + idx] = y;
     }
   } else {
-    for (int idx = tid; idx < K * D; idx += kBT) A.region_out[(size_t)b * K * D + idx] = R[idx];   // :387-389 passthrough
+    for (int idx = tid; idx < K * D; idx += kBT) {             // :387-389 passthrough
+      A.region_out[(size_t)b * K * D + idx] = R[idx];
+      for (int p = 0; p < po.world; ++p) peer_slice(po, p, seq_now & 1u)[s.B + (long long)b * K * D + idx] = R[idx];
+    }
   }
+  if (po.world > 0) peer_cta_done(po, seq_now);
 }
 
 static bool shape_supported(const BlockShape& s, const char** why) {
@@ -959,9 +1015,10 @@ int mg_block_prepare(const float* W1, const float* a1, const float* W2, const fl
   return check_launch("block_prepare_kernel");
 }
 
-int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K,
-                     float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work, float* S,
-                     int32_t* labels, float* loss, float* region_in, float* region_out, mg_stream_t stream) {
+int mg_block_forward_push(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K,
+                          float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work, float* S,
+                          int32_t* labels, float* loss, float* region_in, float* region_out, const mg_peer_out_t* peer,
+                          mg_stream_t stream) {
   MG_REQUIRE(x && prep && h && q_work && S && labels && loss && region_out, MG_ERR_INVALID, "mg_block_forward: null pointer");
   MG_REQUIRE(B > 0 && Hp > 0 && Wp > 0, MG_ERR_INVALID, "mg_block_forward: bad sizes");
   MG_REQUIRE(x_dtype == MG_F32 || x_dtype == MG_BF16, MG_ERR_INVALID, "mg_block_forward: x dtype");
@@ -979,6 +1036,21 @@ int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, int in_d
   BlockArgs A;
   A.s = s; A.x = x; A.prep = prep; A.h = h; A.q = q_work; A.S = S; A.labels = labels; A.loss = loss;
   A.region_in = region_in; A.region_out = region_out;
+  A.peer.world = 0;
+  if (peer) {
+    MG_REQUIRE(peer->peer_bufs_dev && peer->peer_flags_dev && peer->seq && peer->done && peer->world > 0 && peer->world <= 64,
+               MG_ERR_INVALID, "mg_block_forward_push: bad peer descriptor");
+    MG_REQUIRE(peer->slice_offset >= 0 && peer->parity_stride >= 0 && peer->flag_index >= 0, MG_ERR_INVALID,
+               "mg_block_forward_push: negative peer offsets");
+    A.peer.bufs = reinterpret_cast<float* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer->peer_bufs_dev)));
+    A.peer.flags = reinterpret_cast<uint32_t* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer->peer_flags_dev)));
+    A.peer.world = peer->world;
+    A.peer.slice_off = peer->slice_offset;
+    A.peer.parity_stride = peer->parity_stride;
+    A.peer.flag_index = peer->flag_index;
+    A.peer.seq = peer->seq;
+    A.peer.done = peer->done;
+  }
 
   auto kern = x_dtype == MG_F32 ? block_forward_kernel<float> : block_forward_kernel<__nv_bfloat16>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess) {
@@ -1004,6 +1076,13 @@ int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, int in_d
     return MG_ERR_CUDA;
   }
   return check_launch("block_forward_kernel");
+}
+
+int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K,
+                     float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work, float* S,
+                     int32_t* labels, float* loss, float* region_in, float* region_out, mg_stream_t stream) {
+  return mg_block_forward_push(x, x_dtype, B, Hp, Wp, in_dim, D, H1, H2, H3, K, slope1, slope2, slope3, prep, h, q_work, S,
+                               labels, loss, region_in, region_out, nullptr, stream);
 }
 
 }  // extern "C"

@@ -109,7 +109,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // Order-preserving float atomic max (deterministic: max is order independent).
 __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
-  if (v >= 0.f)
+  if (!(__float_as_uint(v) >> 31))        // branch on the sign bit: -0.0f must take the unsigned-min branch
     atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else
     atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));

@@ -111,112 +111,13 @@ def allreduce_graph_grads(module: torch.nn.Module, group: Optional[dist.ProcessG
     return off
 
 
-class OverlappedGather:
-    """Per-step all-gather of the small per-image outputs, issued on a side stream so that it overlaps
-    the next step's kernels instead of extending the step by the collective's launch latency.
-
-    ``push(out)`` packs ``(l_partition | region_features | hard_labels)`` of the local shard into one of
-    two rotating buffers on the current stream and enqueues ONE ``all_gather_into_tensor`` on the side
-    stream; ``latest()`` makes the current stream wait for the most recent gather and returns
-    :class:`GatheredOutputs` views of its result.  With two buffers a step never waits for its own
-    gather, only (at most) for the one issued two steps earlier.  Equal shard sizes are required
-    (``global_batch % world == 0``); use :func:`gather_block_outputs` otherwise."""
-
-    def __init__(self, B: int, N: int, K: int, D: int, device, group: Optional[dist.ProcessGroup] = None):
-        self.B, self.N, self.K, self.D, self.group = B, N, K, D, group
-        self.world = dist.get_world_size(group)
-        self.n_small = B * (1 + K * D + N)
-        self.packed = [torch.empty(self.n_small, dtype=torch.float32, device=device) for _ in range(2)]
-        self.gathered = [torch.empty(self.world * self.n_small, dtype=torch.float32, device=device) for _ in range(2)]
-        self.done = [None, None]
-        self.side = torch.cuda.Stream(device=device)
-        self.turn = 0
-
-    def push(self, l_partition: torch.Tensor, region_features: torch.Tensor, hard_labels: torch.Tensor) -> None:
-        i = self.turn
-        cur = torch.cuda.current_stream()
-        if self.done[i] is not None:
-            cur.wait_event(self.done[i])              # the gather that last read this buffer (two steps ago)
-        B, K, D, N = self.B, self.K, self.D, self.N
-        buf = self.packed[i]
-        torch.cat([l_partition.reshape(-1), region_features.reshape(-1), hard_labels.reshape(-1).view(torch.float32)],
-                  out=buf)
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ready)
-            dist.all_gather_into_tensor(self.gathered[i], buf, group=self.group)
-            ev = torch.cuda.Event()
-            ev.record(self.side)
-        self.done[i] = ev
-        self.turn = 1 - i
-
-    def latest(self) -> GatheredOutputs:
-        i = 1 - self.turn
-        if self.done[i] is None:
-            raise RuntimeError("OverlappedGather.latest() before any push()")
-        torch.cuda.current_stream().wait_event(self.done[i])
-        B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
-        g = self.gathered[i].view(W, self.n_small)
-        loss = g[:, :B].reshape(W * B)
-        reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
-        lab = g[:, B + B * K * D:].reshape(W * B, N).view(torch.int32)
-        return GatheredOutputs(loss, reg, lab)
-
-    def drain(self) -> None:
-        for ev in self.done:
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
-
-
-class CapturedGather:
-    """The per-step all-gather of the small per-image outputs recorded INSIDE each pipeline slot's CUDA graph.
-
-    ``OverlappedGather`` costs the host a pack kernel launch, two event operations and one NCCL enqueue per step; at
-    cfg 2 a pipelined step is ~130 us of GPU time, so that host work (not the 74 KB transfer) set the multi-GPU step
-    time.  Here the block kernel writes ``l_partition | region_features | hard_labels`` straight into the slot's
-    packed buffer (``CapturedGraphBlock(packed_small=...)``: the outputs are views of it, no pack kernel) and the graph
-    ends with ONE ``all_gather_into_tensor`` of that buffer, so a step stays a single ``cudaGraphLaunch`` on every
-    rank.  Each slot has its own communicator: graphs of different slots replay concurrently on different streams, and
-    collectives of ONE communicator must not be issued concurrently."""
-
-    def __init__(self, B: int, N: int, K: int, D: int, device, depth: int):
-        self.B, self.N, self.K, self.D, self.depth = B, N, K, D, depth
-        self.world = dist.get_world_size()
-        self.n_small = B * (1 + K * D + N)
-        self.packed = [torch.zeros(self.n_small, dtype=torch.float32, device=device) for _ in range(depth)]
-        self.gathered = [torch.zeros(self.world * self.n_small, dtype=torch.float32, device=device) for _ in range(depth)]
-        self.groups = [dist.new_group(backend="nccl") for _ in range(depth)]        # collective: same order on all ranks
-
-    def epilogue(self, slot: int):
-        def run(_outputs) -> None:
-            dist.all_gather_into_tensor(self.gathered[slot], self.packed[slot], group=self.groups[slot])
-        return run
-
-    def epilogues(self):
-        return [self.epilogue(i) for i in range(self.depth)]
-
-    def views(self, slot: int) -> GatheredOutputs:
-        """The slot's gathered result (valid on the slot's stream after its replay)."""
-        B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
-        g = self.gathered[slot].view(W, self.n_small)
-        loss = g[:, :B].reshape(W * B)
-        reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
-        lab = g[:, B + B * K * D:].reshape(W * B, N).view(torch.int32)
-        return GatheredOutputs(loss, reg, lab)
-
-
 class InlineGather:
-    """The per-step all-gather issued straight from the step's own stream, on ONE communicator, with no pack kernel:
-    ``gather(slot, stream)`` all-gathers the slot's packed small-output buffer (the block kernel wrote
-    ``l_partition | region_features | hard_labels`` into it in place, ``CapturedGraphBlock(packed_small=...)``).
-
-    ``torch.distributed`` runs every collective of a process group on the group's internal NCCL stream, in issue order:
-    that stream waits for the caller's stream (the step's replay), and the caller's stream — whose next work is the
-    slot's replay ``depth`` steps later — waits for the collective.  So the gathers of all slots are serialised on one
-    communicator in step order (no concurrent collectives, unlike :class:`CapturedGather`), nothing blocks the other
-    slots, and the host pays one collective enqueue per step (``OverlappedGather`` additionally launches a pack kernel
-    and four event operations)."""
+    """NCCL fallback of :class:`PeerExchange` (shapes the fused block kernel does not take, or no peer access): one
+    ``all_gather_into_tensor`` per step of the slot's packed small-output buffer, issued from the step's own stream on
+    ONE communicator.  ``torch.distributed`` runs a group's collectives on its internal NCCL stream in issue order, so
+    the gathers of all slots are totally ordered (concurrent collectives of several communicators hung an 8-GPU run in
+    round 1).  Costs the host one collective enqueue per step and every rank one rendezvous per step: 0.129 -> 0.155
+    ms/step from 1 to 8 GPUs (SCALE_r01), which is why the peer exchange replaced it as the default."""
 
     def __init__(self, B: int, N: int, K: int, D: int, device, depth: int, group: Optional[dist.ProcessGroup] = None):
         self.B, self.N, self.K, self.D, self.depth, self.group = B, N, K, D, depth, group
@@ -242,168 +143,161 @@ class InlineGather:
         return GatheredOutputs(loss, reg, lab)
 
 
-class BucketedGather:
-    """The exchange of several consecutive steps in ONE collective (opt-in, ``bench.py --exchange bucketed``; written
-    after the round-1 GPU budget was spent — host logic covered by the gloo world-2 test, not yet timed on hardware).
+class PeerExchange:
+    """The per-step all-gather of the small per-image outputs WITHOUT a collective call: fused into the block kernel.
 
-    The per-step payload is 74 KB at cfg 2 while a pipelined step is ~125 us of GPU time: a per-step collective costs
-    the host one NCCL enqueue and every rank one rendezvous per step.  Here the ``depth`` pipeline slots' packed
-    buffers are consecutive views of ONE ring; the ring is cut into buckets of ``bucket`` consecutive slots and a
-    bucket is gathered with one ``all_gather_into_tensor`` on a side stream after its LAST slot's step was enqueued
-    (the side stream waits for the events of exactly the bucket's steps).  A slot's next replay (``depth`` steps later)
-    waits for the gather that read its buffer, so with ``depth >= 2 * bucket`` that gather has the other buckets' steps
-    as slack.  One communicator, collectives in step order (same liveness argument as :class:`InlineGather`); results
-    of a step become visible up to ``bucket - 1`` steps late — a throughput, not a latency, optimisation.
+    Every rank owns one gathered buffer ``[2 parity][depth slots][world][slice]`` and one flag array ``[depth][world]``
+    (``ops.peer_mem_alloc``: cudaMalloc + CUDA IPC handle); the handles are exchanged once over the process group and
+    every rank maps every other rank's allocations (NVLink / NVSwitch peer access).  ``slot(i)`` is the descriptor the
+    block kernel of pipeline slot ``i`` takes (``GraphBlock(..., _peer=...)`` -> ``mg_block_forward_push``): while it
+    computes, the kernel stores ``l_partition | region_features | hard_labels`` of its images into slice ``rank`` of every
+    rank's buffer and its last CTA publishes the slot's step number in every rank's flag array.  No kernel of the step
+    waits for another GPU, so a slow rank never makes a fast one hold SMs (what concurrent NCCL kernels did at 8 GPUs).
 
-    Use: ``before(slot, stream)`` ahead of the slot's submit, ``after(slot, stream)`` behind it; ``flush()`` gathers a
-    partly filled bucket (end of a run); ``views(slot)`` as for the other variants."""
+    Consumer: ``wait(slot)`` enqueues a one-CTA kernel on the current stream that returns once every rank's flag has
+    reached this rank's own step count of the slot (bounded: ``status`` turns 1 instead of hanging); ``views(slot)`` are
+    the gathered tensors of the slot's latest step.  Consumers must be stream-ordered before the slot's next step (the
+    parity double buffer then makes acknowledgements unnecessary, csrc/peer_exchange.cu).  ``epilogues()`` are
+    ``wait`` closures to record at the end of each slot's CUDA graph.
 
-    def __init__(self, B: int, N: int, K: int, D: int, device, depth: int, bucket: Optional[int] = None,
-                 group: Optional[dist.ProcessGroup] = None):
-        if bucket is None:
-            bucket = max(1, depth // 2)
-        if bucket < 1 or depth % bucket != 0:
-            raise ValueError("depth must be a multiple of bucket")
-        self.B, self.N, self.K, self.D, self.depth, self.bucket, self.group = B, N, K, D, depth, bucket, group
-        self.world = dist.get_world_size(group)
-        self.n_small = B * (1 + K * D + N)
-        self._cuda = torch.device(device).type == "cuda"
-        self._ring = torch.zeros(depth * self.n_small, dtype=torch.float32, device=device)
-        self.packed = [self._ring[i * self.n_small:(i + 1) * self.n_small] for i in range(depth)]
-        nb = depth // bucket
-        self.gathered = [torch.zeros(self.world * bucket * self.n_small, dtype=torch.float32, device=device)
-                         for _ in range(nb)]
-        self.side = torch.cuda.Stream(device=device) if self._cuda else None
-        self._ready = [torch.cuda.Event() for _ in range(depth)] if self._cuda else None
-        self._done = [torch.cuda.Event() for _ in range(nb)] if self._cuda else None
-        self._done_valid = [False] * nb
-        self._pending: List[int] = []            # slots stepped since the last gather, in step order
+    Call ``reset()`` (collective) after the step graphs were built: their warm-up passes push as well.  ``close()``
+    (collective) unmaps and frees."""
 
-    def before(self, slot: int, stream=None) -> None:
-        """The slot's stream waits for the gather that last read the slot's packed buffer."""
-        b = slot // self.bucket
-        if self._cuda and self._done_valid[b]:
-            stream.wait_event(self._done[b])
-
-    def after(self, slot: int, stream=None) -> None:
-        """Call after the slot's step was enqueued on ``stream``; gathers the bucket when this was its last slot."""
-        if self._pending and (slot != self._pending[-1] + 1 or slot // self.bucket != self._pending[0] // self.bucket):
-            raise RuntimeError("BucketedGather: slots must be stepped round-robin (0, 1, ..., depth-1, 0, ...)")
-        if self._cuda:
-            self._ready[slot].record(stream)
-        self._pending.append(slot)
-        if (slot + 1) % self.bucket == 0:
-            self._gather()
-
-    def flush(self) -> None:
-        """Gather a partly filled bucket (collective: every rank must call it at the same step)."""
-        if self._pending:
-            self._gather()
-
-    def _gather(self) -> None:
-        b = self._pending[0] // self.bucket
-        src = self._ring[b * self.bucket * self.n_small:(b + 1) * self.bucket * self.n_small]
-        if self._cuda:
-            for s in self._pending:
-                self.side.wait_event(self._ready[s])
-            with torch.cuda.stream(self.side):
-                dist.all_gather_into_tensor(self.gathered[b], src, group=self.group)
-                self._done[b].record(self.side)
-            self._done_valid[b] = True
-        else:
-            dist.all_gather_into_tensor(self.gathered[b], src, group=self.group)
-        self._pending = []
-
-    def drain(self) -> None:
-        """Current stream waits for every gather issued so far."""
-        if self._cuda:
-            cur = torch.cuda.current_stream()
-            for ok, ev in zip(self._done_valid, self._done):
-                if ok:
-                    cur.wait_event(ev)
-
-    def views(self, slot: int) -> GatheredOutputs:
-        """The gathered result of the slot's most recent GATHERED step (valid after ``drain()`` / on the side stream)."""
-        B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
-        g = self.gathered[slot // self.bucket].view(W, self.bucket, self.n_small)[:, slot % self.bucket]
-        loss = g[:, :B].reshape(W * B)
-        reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
-        lab = g[:, B + B * K * D:].view(torch.int32).reshape(W * B, N)
-        return GatheredOutputs(loss, reg, lab)
-
-
-class PeerGather:
-    """EXPERIMENTAL — compiled and wired, not yet run on hardware (the round-1 GPU budget was spent); opt-in via
-    ``bench.py --exchange p2p`` / ``tools/check_captured_gather.py --mode p2p``.
-
-    The per-step exchange of the small outputs as plain NVLink stores (``csrc/peer_push.cu``) instead of a collective:
-    every rank owns a symmetric gathered buffer (``depth`` slots x ``world`` slices) mapped into all peers through
-    ``torch.distributed._symmetric_memory``; the epilogue of a step's graph is ONE kernel that stores the slot's packed
-    payload into slice ``rank`` of every peer's buffer and publishes a sequence number.  No kernel of this scheme waits
-    for another GPU, so a slow rank never makes a fast rank hold SMs (the failure mode of concurrent NCCL kernels).
-    Call ``reset()`` once after the step graphs were built (their warm-up passes push too).
-    Consumers call ``wait(slot)`` exactly once per step before reading ``views(slot)``.  Flow control is the caller's:
-    a producer may overwrite slot ``s`` of a peer ``depth`` steps later, so a consumer that reads the gathered data must
-    keep ranks within ``depth`` steps of each other (the bench does not read it; its end-of-region barrier closes it)."""
-
-    def __init__(self, B: int, N: int, K: int, D: int, device, depth: int, group: Optional[dist.ProcessGroup] = None):
-        import torch.distributed._symmetric_memory as symm
+    def __init__(self, B: int, N: int, K: int, D: int, device, depth: int, group: Optional[dist.ProcessGroup] = None,
+                 _local=None):
         from . import ops
         self._ops = ops
-        group = group if group is not None else dist.group.WORLD
         self._group = group
         self.B, self.N, self.K, self.D, self.depth = B, N, K, D, depth
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device)
         self.n_small = B * (1 + K * D + N)
-        self.n_pad = (self.n_small + 3) // 4 * 4                      # 16-byte payloads
-        self._packed = [torch.zeros(self.n_pad, dtype=torch.float32, device=device) for _ in range(depth)]
-        self.packed = [p[:self.n_small] for p in self._packed]       # what the block kernel writes (views)
-        self._gathered = symm.empty(depth * self.world * self.n_pad, dtype=torch.float32, device=device)
-        self._flags = symm.empty(depth * self.world, dtype=torch.int32, device=device)
-        self._gathered.zero_()
-        self._flags.zero_()
-        self._h_buf = symm.rendezvous(self._gathered, group)
-        self._h_flag = symm.rendezvous(self._flags, group)
-        self._seq = torch.zeros(depth, self.world, dtype=torch.int32, device=device)
-        self._wseq = torch.zeros(depth, self.world, dtype=torch.int32, device=device)
+        self.n_pad = (self.n_small + 31) // 32 * 32                   # 128-byte slices
+        self.packed = [torch.zeros(self.n_small, dtype=torch.float32, device=device) for _ in range(depth)]
+        if _local is not None:                                        # local_group(): all "ranks" in this process
+            self.rank, self.world, bufs, flags = _local
+            self._own, self._opened = None, []
+        else:
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            buf_bytes, flag_bytes = self._sizes(self.world)
+            self._own = [ops.peer_mem_alloc(buf_bytes, device), ops.peer_mem_alloc(flag_bytes, device)]
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (self._own[0][1], self._own[1][1]), group=group)
+            self._opened = []
+            bufs, flags = [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    bufs.append(self._own[0][0])
+                    flags.append(self._own[1][0])
+                else:
+                    pb, pf = ops.peer_mem_open(handles[r][0], device), ops.peer_mem_open(handles[r][1], device)
+                    self._opened += [pb, pf]
+                    bufs.append(pb)
+                    flags.append(pf)
+        self._map(bufs, flags)
+        if _local is None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)                                       # every mapping exists before anybody pushes
+
+    def _sizes(self, world: int):
+        return 2 * self.depth * world * self.n_pad * 4, max(256, self.depth * world * 4)
+
+    def _map(self, bufs, flags) -> None:
+        from . import _lib
+        ops, W, depth, device = self._ops, self.world, self.depth, self.device
+        buf_bytes, flag_bytes = self._sizes(W)
+        self._gathered = ops.tensor_from_ptr(bufs[self.rank], buf_bytes, device).view(torch.float32).view(2, depth, W, self.n_pad)
+        self._flags = ops.tensor_from_ptr(flags[self.rank], flag_bytes, device).view(torch.int32)
+        self._ptr_bufs = torch.tensor(bufs, dtype=torch.int64, device=device)
+        self._ptr_flags = torch.tensor(flags, dtype=torch.int64, device=device)
+        self._seq = torch.zeros(depth, dtype=torch.int32, device=device)
+        self._done = torch.zeros(depth, dtype=torch.int32, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
-        torch.cuda.synchronize(device)
-        dist.barrier(group)                                            # nobody pushes before every flag is zeroed
+        self._slots = []
+        for i in range(depth):
+            d = _lib.PeerOut()
+            d.peer_bufs_dev, d.peer_flags_dev = self._ptr_bufs.data_ptr(), self._ptr_flags.data_ptr()
+            d.world, d.rank = W, self.rank
+            d.slice_offset = (i * W + self.rank) * self.n_pad
+            d.parity_stride = depth * W * self.n_pad
+            d.flag_index = i * W + self.rank
+            d.seq, d.done = self._seq[i:].data_ptr(), self._done[i:].data_ptr()
+            self._slots.append(d)
+        self._steps = [0] * depth                                     # host mirror of seq (steps since reset)
+
+    @classmethod
+    def local_group(cls, world: int, B: int, N: int, K: int, D: int, device, depth: int):
+        """``world`` exchange endpoints inside ONE process on ONE device (tests, single-GPU checks): the same kernels
+        and index arithmetic, the "peers" being plain allocations of the same GPU.  Steps of different endpoints must
+        be enqueued before any ``wait`` that needs them (one GPU cannot be relied on to run kernels that wait for each
+        other concurrently)."""
+        from . import ops
+        probe = cls.__new__(cls)
+        probe.depth, probe.n_pad = depth, (B * (1 + K * D + N) + 31) // 32 * 32
+        buf_bytes, flag_bytes = cls._sizes(probe, world)
+        allocs = [(ops.peer_mem_alloc(buf_bytes, device)[0], ops.peer_mem_alloc(flag_bytes, device)[0]) for _ in range(world)]
+        bufs, flags = [a[0] for a in allocs], [a[1] for a in allocs]
+        group = [cls(B, N, K, D, device, depth, _local=(r, world, bufs, flags)) for r in range(world)]
+        group[0]._local_allocs = bufs + flags                         # freed by group[0].close()
+        return group
+
+    def slot(self, i: int):
+        return self._slots[i]
+
+    def slots(self):
+        return list(self._slots)
 
     def reset(self) -> None:
-        """Collective.  Zero every sequence counter and flag once all ranks are idle.  Must be called after the graphs
-        that contain the push were built: building a ``CapturedGraphBlock`` runs its epilogue eagerly ``warmup`` times,
-        so without this the producers' counters would start ahead of the consumers' and the first ``wait`` of a slot
-        would be satisfied by a warm-up push (stale payload)."""
-        torch.cuda.synchronize(self._flags.device)
-        dist.barrier(self._group)                                      # every rank's warm-up pushes have landed
+        """Collective.  Zero the step counters and flags once all ranks are idle (after the graphs were built)."""
+        torch.cuda.synchronize(self.device)
+        self._barrier()                                               # every rank's warm-up pushes have landed
         self._flags.zero_()
         self._seq.zero_()
-        self._wseq.zero_()
+        self._done.zero_()
         self.status.zero_()
-        torch.cuda.synchronize(self._flags.device)
-        dist.barrier(self._group)                                      # nobody pushes before every flag is zeroed
+        self._steps = [0] * self.depth
+        torch.cuda.synchronize(self.device)
+        self._barrier()                                               # nobody pushes before every flag is zeroed
 
-    def epilogue(self, slot: int):
-        off = (slot * self.world + self.rank) * self.n_pad * 4
-        flag = slot * self.world + self.rank
+    def _barrier(self) -> None:
+        if self._own is not None:
+            dist.barrier(self._group)
 
-        def run(_outputs) -> None:
-            self._ops.peer_push(self._packed[slot], self._h_buf.buffer_ptrs_dev, self.world, off,
-                                self._h_flag.buffer_ptrs_dev, flag, self._seq[slot])
-        return run
-
-    def epilogues(self):
-        return [self.epilogue(i) for i in range(self.depth)]
+    def stepped(self, slot: int) -> None:
+        """Tell the host mirror that one step of ``slot`` was enqueued (``views`` needs its parity)."""
+        self._steps[slot] += 1
 
     def wait(self, slot: int) -> None:
-        """Current stream waits for every rank's payload of this slot's next step (call once per step)."""
-        self._ops.peer_wait(self._flags, slot * self.world, self.world, self._wseq[slot], self.status)
+        """Current stream waits for every rank's payload of the slot's latest enqueued step."""
+        self._ops.peer_wait(self._flags, slot * self.world, self.world, self._seq[slot:slot + 1], self.status)
+
+    def epilogues(self):
+        return [(lambda _outputs, i=i: self.wait(i)) for i in range(self.depth)]
 
     def views(self, slot: int) -> GatheredOutputs:
+        """Gathered outputs of the slot's latest step (valid on the stream that ran ``wait(slot)``)."""
+        if self._steps[slot] < 1:
+            raise RuntimeError("PeerExchange.views() before the slot's first step (call stepped(slot) per submit)")
         B, K, D, N, W = self.B, self.K, self.D, self.N, self.world
-        g = self._gathered[slot * W * self.n_pad:(slot + 1) * W * self.n_pad].view(W, self.n_pad)
+        g = self._gathered[(self._steps[slot] - 1) & 1, slot]
         loss = g[:, :B].reshape(W * B)
         reg = g[:, B:B + B * K * D].reshape(W * B, K, D)
-        lab = g[:, B + B * K * D:self.n_small].reshape(W * B, N).view(torch.int32)
+        lab = g[:, B + B * K * D:self.n_small].view(torch.int32).reshape(W * B, N)
         return GatheredOutputs(loss, reg, lab)
+
+    def close(self) -> None:
+        """Collective.  Unmap the peers' allocations, then free the own ones."""
+        torch.cuda.synchronize(self.device)
+        self._gathered = self._flags = None
+        if self._own is None:                                         # local_group(): endpoint 0 owns every allocation
+            for ptr in getattr(self, "_local_allocs", []):
+                self._ops.peer_mem_free(ptr)
+            self._local_allocs = []
+            return
+        dist.barrier(self._group)
+        for p in self._opened:
+            self._ops.peer_mem_close(p)
+        self._opened = []
+        dist.barrier(self._group)                                     # nobody maps the buffers any more
+        for ptr, _ in self._own:
+            self._ops.peer_mem_free(ptr)
+        self._own = None

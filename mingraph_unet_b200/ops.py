@@ -6,6 +6,7 @@ raises otherwise (no CPU fallback).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Tuple
 
 import torch
@@ -410,9 +411,12 @@ def block_prepare(W1, a1, W2, a2, W3, a3, out: Optional[torch.Tensor] = None) ->
 
 
 def block_forward(x: torch.Tensor, Hp: int, Wp: int, prep: torch.Tensor, D: int, H1: int, H2: int, H3: int, K: int,
-                  slopes=(0.2, 0.2, 0.2), want_region_in: bool = False, outs=None):
+                  slopes=(0.2, 0.2, 0.2), want_region_in: bool = False, outs=None, peer=None):
     """One launch for the whole per-image pipeline.  ``x (B,N,in)`` f32|bf16.  Returns
-    ``h (B,N,D), S (B,N,K), labels (B,N) int32, loss (B,), region_in|None, region_out (B,K,D)``."""
+    ``h (B,N,D), S (B,N,K), labels (B,N) int32, loss (B,), region_in|None, region_out (B,K,D)``.
+    ``peer``: a ``_lib.PeerOut`` (``distributed.PeerExchange.slot(i)``) — the kernel then also stores
+    ``loss | region_out | labels`` into every rank's gathered buffer over NVLink and publishes the step
+    (``mg_block_forward_push``)."""
     _need_cuda(x, prep)
     x = x.contiguous()
     B, N, in_dim = x.shape
@@ -434,9 +438,10 @@ def block_forward(x: torch.Tensor, Hp: int, Wp: int, prep: torch.Tensor, D: int,
     q = torch.empty((B, N, 2 * H2 + H2 * K), **f32)
     rin = torch.empty((B, K, D), **f32) if want_region_in else None
     with torch.cuda.device(dev):
-        call("mg_block_forward", x.data_ptr(), _dtype_code(x.dtype), B, Hp, Wp, in_dim, D, H1, H2, H3, K,
+        call("mg_block_forward_push", x.data_ptr(), _dtype_code(x.dtype), B, Hp, Wp, in_dim, D, H1, H2, H3, K,
              float(slopes[0]), float(slopes[1]), float(slopes[2]), prep.data_ptr(), h.data_ptr(), q.data_ptr(),
-             S.data_ptr(), labels.data_ptr(), loss.data_ptr(), _ptr(rin), rout.data_ptr(), _stream())
+             S.data_ptr(), labels.data_ptr(), loss.data_ptr(), _ptr(rin), rout.data_ptr(),
+             None if peer is None else C.addressof(peer), _stream())
     return h, S, labels, loss, rin, rout
 
 
@@ -548,25 +553,49 @@ def region_map_gather(table: torch.Tensor, region_map: torch.Tensor, out: Option
 
 
 # ---------------------------------------------------------------------------------------------
-# peer-memory exchange (multi-GPU; csrc/peer_push.cu) — compiled, not yet run on hardware (opt-in)
+# peer-memory exchange (multi-GPU; csrc/peer_exchange.cu, the push itself is inside block_forward)
 # ---------------------------------------------------------------------------------------------
-def peer_push(src: torch.Tensor, peer_bufs_dev: int, world: int, dst_offset_bytes: int, peer_signals_dev: int,
-              flag_index: int, seq: torch.Tensor) -> None:
-    """Store ``src`` (contiguous, a multiple of 16 bytes) into ``[dst_offset_bytes, +nbytes)`` of every peer's symmetric
-    buffer and publish the next sequence number at ``flag_index`` of every peer's flag buffer.  ``peer_bufs_dev`` /
-    ``peer_signals_dev``: device addresses of the per-rank pointer arrays (``_SymmetricMemory.buffer_ptrs_dev``);
-    ``seq``: ``world`` int32 on this device, zeroed once, advanced by the kernel."""
-    dev = _need_cuda(src, seq)
-    if not src.is_contiguous() or seq.numel() != world or seq.dtype != torch.int32:
-        raise ValueError("peer_push: src must be contiguous, seq must be `world` int32")
+def peer_wait(flags: torch.Tensor, first_flag: int, world: int, seq: torch.Tensor, status: Optional[torch.Tensor] = None) -> None:
+    """Make the current stream wait until ``flags[first_flag + r] >= seq[0]`` for every source rank ``r`` (``seq``: the
+    slot's device-side step counter, advanced by the block kernel).  Bounded spin; ``status[0] = 1`` on expiry."""
+    dev = _need_cuda(flags, seq, status)
     with torch.cuda.device(dev):
-        call("mg_peer_push", src.data_ptr(), src.numel() * src.element_size(), int(peer_bufs_dev), int(world),
-             int(dst_offset_bytes), int(peer_signals_dev), int(flag_index), seq.data_ptr(), _stream())
+        call("mg_peer_wait", flags.data_ptr(), int(first_flag), int(world), seq.data_ptr(), _ptr(status), _stream())
 
 
-def peer_wait(flags: torch.Tensor, first_flag: int, world: int, wseq: torch.Tensor, status: Optional[torch.Tensor] = None) -> None:
-    """Make the current stream wait until ``flags[first_flag + r]`` has reached this consumer's own count for every source
-    rank ``r`` (``wseq``: ``world`` int32, zeroed once, advanced by the kernel).  Bounded spin; ``status[0] = 1`` on expiry."""
-    dev = _need_cuda(flags, wseq, status)
-    with torch.cuda.device(dev):
-        call("mg_peer_wait", flags.data_ptr(), int(first_flag), int(world), wseq.data_ptr(), _ptr(status), _stream())
+def peer_mem_alloc(nbytes: int, device) -> Tuple[int, bytes]:
+    """cudaMalloc + zero + CUDA IPC handle on ``device``: ``(device pointer, 64-byte handle)``.  Set-up call (synchronises)."""
+    ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    with torch.cuda.device(device):
+        call("mg_peer_mem_alloc", int(nbytes), C.addressof(ptr), C.addressof(handle))
+    return int(ptr.value), bytes(handle)
+
+
+def peer_mem_open(handle: bytes, device) -> int:
+    """Map another process's ``peer_mem_alloc`` allocation into this process; returns the device pointer."""
+    ptr, h = C.c_void_p(), (C.c_ubyte * 64).from_buffer_copy(handle)
+    with torch.cuda.device(device):
+        call("mg_peer_mem_open", C.addressof(h), C.addressof(ptr))
+    return int(ptr.value)
+
+
+def peer_mem_close(ptr: int) -> None:
+    call("mg_peer_mem_close", int(ptr))
+
+
+def peer_mem_free(ptr: int) -> None:
+    call("mg_peer_mem_free", int(ptr))
+
+
+class _DeviceMemory:
+    """``__cuda_array_interface__`` view of a raw allocation, so torch can wrap it without owning it."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def tensor_from_ptr(ptr: int, nbytes: int, device) -> torch.Tensor:
+    """uint8 tensor over ``[ptr, ptr + nbytes)`` on ``device`` (memory stays owned by the caller)."""
+    with torch.cuda.device(device):
+        return torch.as_tensor(_DeviceMemory(ptr, nbytes), device=torch.device(device))

@@ -31,15 +31,14 @@ class CapturedGraphBlock:
     def __init__(self, block: GraphBlock, example: torch.Tensor, image_size: Optional[Tuple[int, int]] = None,
                  out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, want_dense: bool = True,
                  warmup: int = 2, shards: int = 1, packed_small: Optional[torch.Tensor] = None, epilogue=None,
-                 epilogue_parallel: bool = False):
+                 epilogue_parallel: bool = False, peer=None):
         """``packed_small``: flat fp32 buffer of ``B*(1 + K*D + N)`` elements; the small per-image outputs
         (``l_partition | region_features | hard_labels``) are then VIEWS of it, i.e. the block kernel writes the
-        multi-GPU exchange payload in place (``distributed.CapturedGather``).  ``epilogue(outputs)``: recorded at the
-        end of the graph (e.g. the all-gather of ``packed_small``), so a step stays ONE driver call.
-        ``epilogue_parallel``: record the epilogue on its own branch right after the block kernel, beside the un-pool
-        (it only needs the small outputs).  Measured with the NCCL all-gather as epilogue: fine at 2 GPUs (256k images/s),
-        but one 8-GPU run HUNG (three slots = three communicators whose collectives then overlap each other and every
-        HBM kernel); undiagnosed, hence off by default."""
+        multi-GPU exchange payload in place.  ``peer``: ``distributed.PeerExchange.slot(i)`` — the block kernel also
+        pushes that payload to every rank (needs ``packed_small`` and ``shards == 1``).  ``epilogue(outputs)``: recorded
+        at the end of the graph (e.g. ``PeerExchange.wait``), so a step stays ONE driver call.  ``epilogue_parallel``:
+        record the epilogue on its own branch right after the block kernel, beside the un-pool (it only needs the small
+        outputs)."""
         if not example.is_cuda:
             raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
         if block.training and torch.is_grad_enabled():
@@ -51,7 +50,9 @@ class CapturedGraphBlock:
         dev = example.device
         B = example.shape[0]
         self.shards = max(1, min(int(shards), B))
-        self._packed, self._epilogue, self._epi_stream = packed_small, epilogue, None
+        self._packed, self._epilogue, self._epi_stream, self._peer = packed_small, epilogue, None, peer
+        if peer is not None and (packed_small is None or self.shards != 1):
+            raise ValueError("peer needs packed_small and shards == 1 (the push covers the slot's whole batch)")
         self._epi_parallel = bool(epilogue_parallel)
         if self.shards > 1 and not self._shardable(example, image_size, want_dense, out):
             self.shards = 1
@@ -158,7 +159,8 @@ class CapturedGraphBlock:
                 kw["out"] = self._dense[lo:hi] if self._dense is not None else None
                 self.block(**{self.kind: self.static_in[lo:hi]}, **kw,
                            _block_outs=(self._h[lo:hi], self._S[lo:hi], self._labels[lo:hi], self._loss[lo:hi], self._rout[lo:hi]),
-                           _after_block=after_block if (self._epilogue is not None and self._epi_parallel) else None)
+                           _after_block=after_block if (self._epilogue is not None and self._epi_parallel) else None,
+                           _peer=self._peer)
                 ev = torch.cuda.Event()
                 ev.record(st)
                 joins.append(ev)
@@ -206,7 +208,8 @@ class PipelinedGraphBlock:
 
     def __init__(self, block: GraphBlock, example: torch.Tensor, image_size: Optional[Tuple[int, int]] = None,
                  outs=None, out_dtype: Optional[torch.dtype] = None, want_dense: bool = True, depth: int = 2,
-                 shards: int = 1, warmup: int = 2, packed_small=None, epilogues=None, epilogue_parallel: bool = False):
+                 shards: int = 1, warmup: int = 2, packed_small=None, epilogues=None, epilogue_parallel: bool = False,
+                 peers=None):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         if outs is not None and len(outs) != depth:
@@ -217,7 +220,8 @@ class PipelinedGraphBlock:
                                            out_dtype=out_dtype, want_dense=want_dense, warmup=warmup, shards=shards,
                                            packed_small=None if packed_small is None else packed_small[i],
                                            epilogue=None if epilogues is None else epilogues[i],
-                                           epilogue_parallel=epilogue_parallel)
+                                           epilogue_parallel=epilogue_parallel,
+                                           peer=None if peers is None else peers[i])
                         for i in range(depth)]
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
         self.done = [None] * depth
@@ -276,19 +280,20 @@ class CapturedTrainStep:
       block), issued eagerly on the same stream;
     * graph B: ``optimizer.step()`` (the optimizer must be built with ``capturable=True``).
 
-    With a single rank A and B are recorded as one graph.  ``loss_fn`` maps a :class:`GraphBlockOutput` to a scalar and may
+    With a single rank (or ``allreduce=False``: this rank trains alone) A and B are recorded as one graph.  ``loss_fn`` maps a :class:`GraphBlockOutput` to a scalar and may
     close over other static tensors.  Attention-dropout masks differ from replay to replay (device-side seed addend) and
     are regenerated exactly by the backward of the same replay."""
 
     def __init__(self, block: GraphBlock, optimizer: torch.optim.Optimizer, example_feature_map: torch.Tensor,
-                 image_size: Tuple[int, int], loss_fn, out_dtype: Optional[torch.dtype] = None, group=None, warmup: int = 3):
+                 image_size: Tuple[int, int], loss_fn, out_dtype: Optional[torch.dtype] = None, group=None, warmup: int = 3,
+                 allreduce: bool = True):
         import torch.distributed as dist
         from . import ops
         from .autograd import advance_dropout_counter
         if not example_feature_map.is_cuda:
             raise RuntimeError("mingraph_unet_b200 runs on CUDA tensors only (there is no CPU fallback)")
         self.block, self.opt, self.group = block, optimizer, group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size(group) if (allreduce and dist.is_available() and dist.is_initialized()) else 1
         dev = example_feature_map.device
         self.static_in = example_feature_map.clone()
         params = [p for p in block.parameters() if p.requires_grad]

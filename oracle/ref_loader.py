@@ -1,8 +1,8 @@
-"""Import the UNTOUCHED reference classes when the reference tree is mounted
-(TEST INFRASTRUCTURE).  ``/root/reference`` exists only in the build container,
-never on the GPU box, so everything that runs there uses the committed fixtures
-in ``tests/golden/`` instead.  Nothing is copied: the reference root is put on
-``sys.path`` and its modules are imported in place.
+"""Import the UNTOUCHED reference classes (TEST INFRASTRUCTURE).  Probed, in order: ``$MINGRAPH_REFERENCE_ROOT``,
+``/root/reference/MinGraph-UNet`` (build container only), ``oracle/_ref/MinGraph-UNet`` (the verbatim, git-ignored copy
+``oracle/fetch_ref.py`` makes in ``__graft_entry__.build()`` — the one that travels to the GPU box) and
+``baseline/_ref/MinGraph-UNet``.  The root is put on ``sys.path`` and the modules are imported in place, unmodified.
+Only ``tests/``, ``smoke()`` and ``bench.py``'s CPU legs may use this.
 """
 from __future__ import annotations
 
@@ -11,11 +11,21 @@ import os
 import sys
 import warnings
 
-REF_ROOT = os.environ.get("MINGRAPH_REFERENCE_ROOT", "/root/reference/MinGraph-UNet")
+_REPO = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+CANDIDATES = [p for p in (os.environ.get("MINGRAPH_REFERENCE_ROOT"), "/root/reference/MinGraph-UNet",
+                          os.path.join(_REPO, "oracle", "_ref", "MinGraph-UNet"),
+                          os.path.join(_REPO, "baseline", "_ref", "MinGraph-UNet")) if p]
+
+
+def _is_ref(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "model", "gat", "graph_attention.py"))
+
+
+REF_ROOT = next((p for p in CANDIDATES if _is_ref(p)), CANDIDATES[0])
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "model", "gat", "graph_attention.py"))
+    return _is_ref(REF_ROOT)
 
 
 def load():

@@ -656,13 +656,53 @@ def test_pipelined_graph_block_matches_eager(mg, depth, shards):
     pipe.host_wait(0)
 
 
-def test_captured_gather_single_rank_group():
-    """The in-graph exchange (block kernel writes the packed payload in place, NCCL all-gather recorded in the step's
-    graph) on a 1-rank NCCL group, in a subprocess; the same script checks any world size under torchrun."""
+@pytest.mark.parametrize("mode", ["p2p", "inline"])
+def test_exchange_single_rank_group(mode):
+    """The multi-GPU exchange on a 1-rank NCCL group, in a subprocess (p2p: payload pushed by the block kernel into the
+    CUDA-IPC exchange buffers + flag wait recorded in the step's graph; inline: NCCL fallback); the same script checks
+    any world size under torchrun (tools/check_exchange.py)."""
     import os, subprocess, sys
     root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
-    env["MASTER_PORT"] = "29541"
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_captured_gather.py")], env=env, capture_output=True,
-                       text=True, timeout=300)
+    env["MASTER_PORT"] = "29541" if mode == "p2p" else "29542"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_exchange.py"), "--mode", mode], env=env,
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("world,B,H,W", [(3, 4, 128, 96), (8, 2, 64, 48), (2, 16, 512, 512)])
+def test_peer_exchange_local_group(world, B, H, W):
+    """The push fused into block_forward_kernel with ``world`` endpoints on ONE GPU (the peers are plain allocations of
+    the same device): every endpoint's gathered buffer must hold every endpoint's loss / region features / labels of the
+    step, bit for bit, in both parity halves and every slot, and the flag wait must pass without hitting its bound."""
+    import mingraph_unet_b200 as mg
+    from mingraph_unet_b200.distributed import PeerExchange
+    dev = torch.device("cuda")
+    C, D, K, depth = 20, 64, 2, 2
+    N = (H // 16) * (W // 16)
+    torch.manual_seed(1234)
+    blk = mg.GraphBlock(node_feature_dim=C, num_segments=K).to(dev).eval()
+    group = PeerExchange.local_group(world, B, N, K, D, dev, depth)
+    try:
+        with torch.no_grad():
+            for step in range(5):
+                slot = step % depth
+                outs = []
+                for r in range(world):
+                    x = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(100 * step + r)).to(dev)
+                    outs.append(blk(feature_map=x, image_size=(H, W), want_dense=False, _peer=group[r].slot(slot)))
+                    group[r].stepped(slot)
+                loss = torch.cat([o.l_partition for o in outs])
+                reg = torch.cat([o.region_features for o in outs])
+                lab = torch.cat([o.hard_labels for o in outs])
+                for r in range(world):
+                    group[r].wait(slot)
+                    g = group[r].views(slot)
+                    assert torch.equal(g.l_partition, loss) and torch.equal(g.region_features, reg)
+                    assert torch.equal(g.hard_labels, lab) and g.hard_labels.dtype == torch.int32
+        torch.cuda.synchronize()
+        assert all(int(e.status.item()) == 0 for e in group)
+        assert all(int(e._seq[s]) == (5 - s + depth - 1) // depth for e in group for s in range(depth))
+    finally:
+        for e in reversed(group):
+            e.close()

@@ -175,43 +175,6 @@ if Bg % world == 0:
         ig.gather(slot)
         v = ig.views(slot)
         assert torch.equal(v.l_partition, loss + step) and torch.equal(v.region_features, reg) and torch.equal(v.hard_labels, lab)
-# BucketedGather: the slots' payloads are views of one ring; one collective per bucket of consecutive steps
-from mingraph_unet_b200.distributed import BucketedGather
-if Bg % world == 0:
-    B = Bg // world
-    bg = BucketedGather(B, N, K, D, "cpu", depth=4)          # buckets of 2 slots
-    assert bg.bucket == 2 and all(p.data_ptr() == bg._ring.data_ptr() + 4 * i * bg.n_small for i, p in enumerate(bg.packed))
-    sl = slice(rank * B, (rank + 1) * B)
-    def fill(slot, step):
-        pk = bg.packed[slot]
-        pk[:B] = loss[sl] + step
-        pk[B:B + B * K * D] = (reg[sl] * (step + 1)).reshape(-1)
-        pk[B + B * K * D:].view(torch.int32).copy_(((lab[sl] + step) % K).reshape(-1))
-    def check(slot, step):
-        v = bg.views(slot)
-        assert torch.equal(v.l_partition, loss + step) and torch.equal(v.region_features, reg * (step + 1))
-        assert torch.equal(v.hard_labels, (lab + step) % K) and v.hard_labels.dtype == torch.int32
-    for step in range(7):
-        slot = step % 4
-        bg.before(slot)
-        fill(slot, step)
-        bg.after(slot)
-        if slot % 2 == 1:                                    # the bucket's last slot: both of its steps are gathered
-            check(slot - 1, step - 1); check(slot, step)
-    assert bg._pending == [2]
-    bg.flush(); bg.drain()
-    check(2, 6); check(3, 3)                                 # slot 3 still holds step 3 (re-gathered unchanged)
-    try:
-        bg.after(2)                                          # out of round-robin order inside a bucket
-        bg.after(2)
-        raise SystemExit("expected RuntimeError")
-    except RuntimeError:
-        pass
-    try:
-        BucketedGather(B, N, K, D, "cpu", depth=3, bucket=2)
-        raise SystemExit("expected ValueError")
-    except ValueError:
-        pass
 dist.destroy_process_group()
 print("OK", rank)
 """
