@@ -139,10 +139,12 @@ class _UnpoolFn(torch.autograd.Function):
 def unpool_apply(table, labels, Hp, Wp, H, W, out=None, out_dtype=torch.float32):
     if _wants_grad(table):
         if out is not None:
-            # writing into a caller-owned slice under autograd: produce a fresh tensor, then copy (keeps the graph simple)
-            res = _UnpoolFn.apply(table.contiguous(), labels, Hp, Wp, H, W, None, out.dtype)
-            out.copy_(res.detach())
-            return res
+            # writing into a caller-owned slice (the fusion buffer) under autograd: an in-place op on `out` (mark_dirty),
+            # so a head that reads the BUFFER back-propagates into the region rows — the gradient path is the buffer's
+            # own history, not a detached copy
+            if out.requires_grad and out.is_leaf:
+                raise RuntimeError("unpool_apply: `out` is a leaf that requires grad; pass a buffer (slice) that does not")
+            return _UnpoolFn.apply(table.contiguous(), labels, Hp, Wp, H, W, out, out.dtype)
         return _UnpoolFn.apply(table.contiguous(), labels, Hp, Wp, H, W, None, out_dtype)
     return ops.unpool_nearest(table, labels, Hp, Wp, H, W, out=out, out_dtype=out_dtype)
 
@@ -164,10 +166,40 @@ class _NcutFn(torch.autograd.Function):
         return gh, gS, None
 
 
+class _EdgeWeightFn(torch.autograd.Function):
+    """``w_e = exp(-|h_src - h_tgt|^2 / 2)`` (mincut_refinement.py:43-51), differentiable w.r.t. ``h`` like the reference
+    method.  The backward of this stand-alone accessor is index glue in torch (the block's own N-cut backward is
+    ``mg_ncut_backward``)."""
+
+    @staticmethod
+    def forward(ctx, h, edge_index):
+        w = ops.ncut_edge_weights(h, edge_index)
+        ctx.save_for_backward(h, edge_index, w)
+        return w
+
+    @staticmethod
+    def backward(ctx, grad_w):
+        h, ei, w = ctx.saved_tensors
+        c = (grad_w * w).unsqueeze(1) * (h[ei[0]] - h[ei[1]])          # d w_e / d h_src = -w_e (h_src - h_tgt)
+        gh = torch.zeros_like(h)
+        gh.index_add_(0, ei[0], -c)
+        gh.index_add_(0, ei[1], c)
+        return gh, None
+
+
+def edge_weights_apply(h: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    if _wants_grad(h):
+        return _EdgeWeightFn.apply(h.contiguous(), edge_index)
+    return ops.ncut_edge_weights(h, edge_index)
+
+
 def ncut_loss_apply(h: torch.Tensor, S: torch.Tensor, g: Graph) -> torch.Tensor:
     """Per-graph soft N-cut loss ``(G,)``; differentiable w.r.t. ``h`` and ``S``."""
     g.need_out_csr()
     if _wants_grad(h, S):
+        D = h.shape[-1]
+        if D % 4 != 0 or D > 128:       # what mg_ncut_backward takes: fail at the forward, not in the middle of backward()
+            raise RuntimeError(f"the N-cut backward kernel needs a feature width that is a multiple of 4 and <= 128 (got {D})")
         return _NcutFn.apply(h.contiguous(), S.contiguous(), g)
     return ops.ncut_loss(h, S, g.rowptr_out, g.col_out, g.nodes_per_graph)
 

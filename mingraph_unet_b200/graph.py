@@ -81,7 +81,11 @@ class Graph:
         g = cls(N, int(edge_index.shape[1]), edge_index.device)
         g.edge_index = edge_index
         if g.E > 0:
-            g.rowptr_in, g.col_in, g.eid_in = ops.csr_from_coo(edge_index, N, by_target=True)
+            # a caller-supplied edge list: node ids outside [0, N) raise IndexError like the reference's indexing does
+            # (one device sync per NEW edge_index tensor, amortised by this cache; not possible while a CUDA graph is
+            # being captured, where the caller is responsible for having validated the tensor before)
+            check = edge_index.is_cuda and not torch.cuda.is_current_stream_capturing()
+            g.rowptr_in, g.col_in, g.eid_in = ops.csr_from_coo(edge_index, N, by_target=True, check=check)
         register(edge_index, g)
         return g
 

@@ -28,7 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .autograd import feature_loss_apply, gat_layer_apply, ncut_loss_apply, softmax_rows, tv_loss_apply
+from .autograd import edge_weights_apply, feature_loss_apply, gat_layer_apply, ncut_loss_apply, softmax_rows, tv_loss_apply
 from .graph import Graph, register
 
 
@@ -232,8 +232,9 @@ class MinCutRefinement(nn.Module):
         self.sigma_features = sigma_features
 
     def compute_edge_weights_for_ncut(self, node_features, edge_index):
-        """``exp(-|f_src - f_tgt|^2 / 2)`` per edge (:30-52; sigma hard-coded to 1.0 at :50)."""
-        return ops.ncut_edge_weights(node_features.float(), edge_index)
+        """``exp(-|f_src - f_tgt|^2 / 2)`` per edge (:30-52; sigma hard-coded to 1.0 at :50); differentiable with
+        respect to ``node_features`` like the reference's."""
+        return edge_weights_apply(node_features.float(), edge_index)
 
     def normalized_cut_loss(self, node_features, edge_index, segment_assignments_soft, num_segments_k):
         """(:55-160).  Returns a 0-dim tensor; where the reference returns the Python float ``0.0``

@@ -210,11 +210,14 @@ def nearest_index(out_size: int, in_size: int) -> np.ndarray:
 
 
 def graph_block_image(x, H: int, W: int, params: Dict[str, torch.Tensor], K: int = 2,
-                      patch: int = 16, alpha: float = 0.2, want_dense: bool = True):
+                      patch: int = 16, alpha: float = 0.2, want_dense: bool = True, hard=None):
     """One image through the block, stage order of train_end_to_end.py:318-421
     (node features passed in instead of ``randn`` :326; the crashing feature-loss
     call :344 omitted).  ``params`` holds ``patch_W/patch_a``, ``pred_W/pred_a``,
-    ``region_W/region_a`` head stacks.  Returns a dict of every intermediate."""
+    ``region_W/region_a`` head stacks.  Returns a dict of every intermediate.
+    ``hard``: take these patch labels instead of ``argmax(S)`` for everything downstream of :356 (the
+    parity tests re-derive the tail from the labels the device produced, so an argmax flip at a
+    numerical tie cannot hide the region / un-pool stages from the comparison)."""
     nph, npw = grid_dims(H, W, patch)
     if x.shape[0] != nph * npw:                                           # patch_graph_construction.py:71-74
         raise ValueError("patch feature count does not match the patch grid")
@@ -225,7 +228,8 @@ def graph_block_image(x, H: int, W: int, params: Dict[str, torch.Tensor], K: int
     logits = gat_network(h, ei, params["pred_W"], params["pred_a"], alpha)
     S = F.softmax(logits, dim=1)                                          # mincut_refinement.py:193
     loss = ncut_loss(h, ei, S, K)                                         # :196
-    hard = torch.argmax(S, dim=1)                                         # train_end_to_end.py:356
+    hard_own = torch.argmax(S, dim=1)                                     # train_end_to_end.py:356
+    hard = hard_own if hard is None else torch.as_tensor(hard).long()
     R = region_mean_pool(h, hard, K)                                      # :368-373
     rei = torch.from_numpy(complete_edge_index(K))                       # :376-380
     if K > 0 and rei.numel() > 0:                                         # :383-389
@@ -233,7 +237,7 @@ def graph_block_image(x, H: int, W: int, params: Dict[str, torch.Tensor], K: int
     else:
         G = R
     P = G[hard]                                                           # :403-406
-    out = dict(edge_index=ei, h=h, logits=logits, S=S, loss=loss, hard=hard,
+    out = dict(edge_index=ei, h=h, logits=logits, S=S, loss=loss, hard=hard, hard_argmax=hard_own,
                region_in=R, region_out=G, f_patch=P, grid=(nph, npw))
     if want_dense:
         out["f_g"] = unpool_nearest(P, nph, npw, H, W)                    # :411-421

@@ -361,3 +361,63 @@ def test_captured_train_step_matches_eager(mg):
     tr = mg.CapturedTrainStep(drop, opt_d, fm, (H, W), loss_fn, warmup=3)
     vals = {round(float(tr()), 7) for _ in range(4)}
     assert len(vals) >= 3
+
+
+def test_unpool_into_fusion_buffer_keeps_gradient_path():
+    """a training user hands the block a slice of the fusion buffer and feeds the BUFFER to the head; the
+    gradient has to reach the region rows through the buffer (in-place autograd op), and match the stand-alone result."""
+    import mingraph_unet_b200 as mg
+    from mingraph_unet_b200.autograd import unpool_apply
+    B, K, D, nph, npw, H, W = 2, 3, 8, 4, 5, 64, 80
+    gen = torch.Generator().manual_seed(3)
+    labels = torch.randint(0, K, (B, nph * npw), generator=gen).int().cuda()
+    t1 = torch.randn(B, K, D, generator=gen).cuda().requires_grad_(True)
+    t2 = t1.detach().clone().requires_grad_(True)
+    wgt = torch.randn(B, 5 + D, H, W, generator=gen).cuda()
+    # (a) reference: fresh tensor, concatenated by torch
+    dense = unpool_apply(t1, labels, nph, npw, H, W)
+    buf_a = torch.cat([torch.ones(B, 5, H, W, device="cuda"), dense], 1)
+    (buf_a * wgt).sum().backward()
+    # (b) written straight into the buffer slice; the loss reads the buffer, not the returned tensor
+    buf_b = torch.ones(B, 5 + D, H, W, device="cuda")
+    res = unpool_apply(t2, labels, nph, npw, H, W, out=buf_b[:, 5:])
+    assert res.data_ptr() == buf_b[:, 5:].data_ptr() and buf_b.requires_grad
+    assert torch.equal(buf_b.detach(), buf_a.detach())
+    (buf_b * wgt).sum().backward()
+    assert t2.grad is not None and torch.allclose(t2.grad, t1.grad, rtol=1e-5, atol=1e-6)
+    # whole block in training mode: F_g written into the fusion buffer, loss on the buffer -> every net gets a gradient
+    torch.manual_seed(0)
+    blk = mg.GraphBlock(node_feature_dim=6, num_segments=2, dropout_rate=0.0).cuda().train()
+    x = torch.randn(2, 16, 6, generator=gen).cuda()
+    fusion = torch.zeros(2, 4 + 64, 64, 64, device="cuda")
+    out = blk(node_features=x, image_size=(64, 64), out=fusion[:, 4:])
+    (fusion * torch.randn(fusion.shape, generator=gen).cuda()).sum().backward()
+    grads = [p.grad for p in blk.region_gat_model.parameters()]
+    assert all(g is not None and float(g.abs().sum()) > 0 for g in grads)
+
+
+def test_edge_weights_are_differentiable_and_bad_edges_raise():
+    """MinCutRefinement.compute_edge_weights_for_ncut is differentiable w.r.t. the features (as in the
+    reference, mincut_refinement.py:43-51); a caller-supplied edge_index with ids outside [0, N) raises IndexError."""
+    import mingraph_unet_b200 as mg
+    gen = torch.Generator().manual_seed(5)
+    N, D, E = 37, 12, 150
+    h = (0.3 * torch.randn(N, D, generator=gen))
+    ei = torch.randint(0, N, (2, E), generator=gen)
+    hg = h.clone().cuda().requires_grad_(True)
+    w = mg.MinCutRefinement().compute_edge_weights_for_ncut(hg, ei.cuda())
+    cot = torch.randn(E, generator=gen)
+    (w * cot.cuda()).sum().backward()
+    hr = h.clone().requires_grad_(True)
+    wr = torch.exp(-((hr[ei[0]] - hr[ei[1]]) ** 2).sum(1) / 2.0)
+    (wr * cot).sum().backward()
+    assert torch.allclose(w.detach().cpu(), wr.detach(), atol=1e-6)
+    assert torch.allclose(hg.grad.cpu(), hr.grad, atol=1e-5, rtol=1e-4)
+    bad = ei.clone()
+    bad[0, 3] = N + 2
+    with pytest.raises(IndexError):
+        mg.GATNetwork(D, 8, 8, 2).cuda().eval()(h.cuda(), bad.cuda())
+    with pytest.raises(RuntimeError):                       # D = 6 is not a width the N-cut backward kernel takes
+        mc = mg.MinCutRefinement()
+        x6 = torch.randn(N, 6, device="cuda", requires_grad=True)
+        mc.normalized_cut_loss(x6, ei.cuda(), torch.softmax(torch.randn(N, 2, device="cuda"), 1), 2)

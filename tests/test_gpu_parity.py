@@ -321,25 +321,41 @@ def _block_from_params(mg, params, in_dim, K, fused=True):
     return blk.cuda().eval()
 
 
-def _check_block(out, refs, tol, dense_tol):
-    """refs: list of oracle dicts per image.  Labels must agree wherever the oracle's top-2 soft
-    assignments are separated by more than the tolerance; dense maps are compared on those images
-    whose labels agree everywhere (the usual case)."""
-    B = len(refs)
+def _label_flips(gpu_labels, ref, margin_tol, max_frac=1e-3):
+    """Labels are an argmax: they must equal the oracle's except at numerical ties.  Returns the number of flips after
+    asserting BOTH bounds: every flipped node's top-2 soft assignments (oracle) are within ``margin_tol`` of each
+    other, and at most ``max(1, max_frac * N)`` nodes of the image flip."""
+    lab = gpu_labels.cpu().long()
+    diff = lab != ref["hard_argmax"]
+    n = int(diff.sum())
+    if n:
+        S = ref["S"]
+        assert S.shape[1] > 1
+        top2 = torch.topk(S, 2, dim=1).values
+        worst = float((top2[diff, 0] - top2[diff, 1]).abs().max())
+        assert worst <= margin_tol, f"{n} label flips, worst top-2 margin {worst:.3e} > {margin_tol:.1e}"
+        assert n <= max(1, int(max_frac * lab.numel())), f"{n} label flips of {lab.numel()} nodes"
+    return n
+
+
+def _check_block(out, refs, tol, dense_tol, retail, flip_margin=None):
+    """refs: oracle dicts per image; ``retail(b, labels)`` re-runs the oracle for image b with the DEVICE's labels.
+    h, S and the loss never depend on the labels and are always compared.  Labels: ``_label_flips`` (zero flips, or
+    flips only at ties within ``flip_margin`` = 2 tol by default and a count bound).  Region features and the dense map
+    are ALWAYS compared, against the oracle tail re-derived from the device's own labels when a label flipped."""
+    flips = 0
     for b, r in enumerate(refs):
         assert maxabs(out.patch_features[b], r["h"]) <= tol
         assert maxabs(out.soft_assignments[b], r["S"]) <= tol
-        top2 = torch.topk(r["S"], 2, dim=1).values if r["S"].shape[1] > 1 else None
-        lab = out.hard_labels[b].cpu().long()
-        diff = lab != r["hard"]
-        if diff.any():
-            assert top2 is not None and float((top2[diff, 0] - top2[diff, 1]).abs().max()) <= 4 * tol
-            continue
         assert float(out.l_partition[b]) == pytest.approx(float(r["loss"]), rel=1e-4, abs=1e-7)
+        nflip = _label_flips(out.hard_labels[b], r, 2 * tol if flip_margin is None else flip_margin)
+        flips += nflip
+        if nflip:
+            r = retail(b, out.hard_labels[b].cpu().long())
         assert maxabs(out.region_features[b], r["region_out"]) <= tol
         if out.f_g is not None and "f_g" in r:
             assert maxabs(out.f_g[b], r["f_g"]) <= dense_tol
-    return B
+    return flips
 
 
 @pytest.mark.parametrize("fused", [True, False])
@@ -375,13 +391,17 @@ def test_block_batched_vs_oracle(mg, B, H, W, K, dtype, fused):
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(B, nph * npw, in_dim, generator=gen)
     xin = x.to(dtype)
-    want_dense_ref = H * W <= 512 * 512
-    refs = [O.graph_block_image(xin[b].float(), H, W, params, K=K, want_dense=want_dense_ref and b < 2) for b in range(B)]
+    # dense map of EVERY image up to and including 512^2; at 1024^2 the first image (268 MB of fp32 each on the CPU) plus
+    # the replication property below for all of them
+    def oracle(b, hard=None):
+        return O.graph_block_image(xin[b].float(), H, W, params, K=K, want_dense=H * W <= 512 * 512 or b == 0, hard=hard)
+    refs = [oracle(b) for b in range(B)]
     with torch.no_grad():
         out = blk(node_features=xin.cuda(), image_size=(H, W))
     assert out.f_g.dtype == dtype and tuple(out.f_g.shape) == (B, 64, H, W)
-    tol = FP32_TOL
-    _check_block(out, refs, tol, FP32_TOL if dtype == torch.float32 else BF16_TOL)
+    tol = FP32_TOL                      # bf16 storage: the oracle sees the same rounded input, the math is fp32 on both sides
+    flips = _check_block(out, refs, tol, FP32_TOL if dtype == torch.float32 else BF16_TOL, oracle)
+    print(f"label flips at ties: {flips} of {B * nph * npw} nodes")
     # size-independent property at full size: the dense map is the per-patch map replicated
     if H % 16 == 0 and W % 16 == 0:
         fp = torch.gather(out.region_features, 1, out.hard_labels.long().unsqueeze(-1).expand(-1, -1, 64))
@@ -426,10 +446,12 @@ def test_block_fused_other_widths(mg, in_dim, D, heads, K):
     # (64,128,4,2) needs 128 KB of weights + 128 KB of tile: beyond the fused kernel's budget -> composed path
     assert mg.ops.block_supported(B, nph, npw, in_dim, D, heads, max(1, heads // 2), heads, K) == (D < 128)
     x = torch.randn(B, nph * npw, in_dim, generator=torch.Generator().manual_seed(1))
-    refs = [O.graph_block_image(x[b], H, W, params, K=K) for b in range(B)]
+    def oracle(b, hard=None):
+        return O.graph_block_image(x[b], H, W, params, K=K, hard=hard)
+    refs = [oracle(b) for b in range(B)]
     with torch.no_grad():
         out = blk(node_features=x.cuda(), image_size=(H, W))
-    _check_block(out, refs, FP32_TOL, FP32_TOL)
+    _check_block(out, refs, FP32_TOL, FP32_TOL, oracle)
 
 
 def test_block_feature_map_input(mg):
@@ -438,10 +460,12 @@ def test_block_feature_map_input(mg):
     params = O.init_block_params(C, 64, 4, K, seed=7)
     blk = _block_from_params(mg, params, C, K)
     fm = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(3))
-    refs = [O.graph_block_image(O.patch_mean_pool(fm[b], 16), H, W, params, K=K) for b in range(B)]
+    def oracle(b, hard=None):
+        return O.graph_block_image(O.patch_mean_pool(fm[b], 16), H, W, params, K=K, hard=hard)
+    refs = [oracle(b) for b in range(B)]
     with torch.no_grad():
         out = blk(feature_map=fm.cuda())
-    _check_block(out, refs, FP32_TOL, FP32_TOL)
+    _check_block(out, refs, FP32_TOL, FP32_TOL, oracle)
 
 
 def test_block_errors(mg):
@@ -595,13 +619,14 @@ def test_block_on_bottleneck_features_in512(mg, dtype, tol):
     for b in range(B):
         x = bott[b].float().reshape(C, -1).t().contiguous()                 # (N, 512): pooling window 1x1 = transpose
         ref = O.graph_block_image(x, H, W, P, K=K, want_dense=False)
-        worst = max(worst, maxabs(out.patch_features[b], ref["h"]))
-        if torch.equal(out.hard_labels[b].cpu().long(), ref["hard"]):
-            worst = max(worst, maxabs(out.region_features[b], ref["region_out"]))
-        else:
-            # bf16 rounding may flip an argmax whose two probabilities are (almost) equal: only there
-            flips = out.hard_labels[b].cpu().long() != ref["hard"]
-            assert dtype == torch.bfloat16 and float((ref["S"][flips, 0] - 0.5).abs().max()) < 5e-2
+        worst = max(worst, maxabs(out.patch_features[b], ref["h"]), maxabs(out.soft_assignments[b], ref["S"]))
+        assert float(out.l_partition[b]) == pytest.approx(float(ref["loss"]), rel=10 * tol, abs=tol)
+        # fp32: flips only at ties within 2 tol; bf16 (tensor-pipe transform, 2e-2 budget): an argmax may flip where the
+        # two probabilities are within 2 tol of each other, and on at most 2 % of the nodes
+        nflip = _label_flips(out.hard_labels[b], ref, 2 * tol, max_frac=1e-3 if dtype == torch.float32 else 2e-2)
+        if nflip:                                                           # the tail from the device's own labels
+            ref = O.graph_block_image(x, H, W, P, K=K, want_dense=False, hard=out.hard_labels[b].cpu().long())
+        worst = max(worst, maxabs(out.region_features[b], ref["region_out"]))
     assert worst <= tol, worst
 
 
@@ -706,3 +731,46 @@ def test_peer_exchange_local_group(world, B, H, W):
     finally:
         for e in reversed(group):
             e.close()
+
+
+@pytest.mark.parametrize("B,H,W,dtype", [(1, 256, 256, torch.float32), (3, 512, 512, torch.float32), (2, 512, 512, torch.bfloat16),
+                                         (2, 200, 136, torch.float32)])
+def test_block_vs_live_reference(mg, B, H, W, dtype):
+    """The CUDA block against the UNTOUCHED reference classes themselves (oracle/_ref, the copy build() ships to the GPU
+    box; oracle/ref_block.py drives them as scripts/train_end_to_end.py:318-421): reference state_dicts loaded unchanged,
+    feature maps pooled by the reference's own image_to_patches, edge_index bit-exact, labels equal (ties aside), features
+    / assignments / loss / dense map within 1e-5 (bf16 storage: dense map within 2e-2 of the fp32 reference)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no reference copy (oracle/_ref is made by __graft_entry__.build() in the build container)")
+    from oracle.ref_block import RefGraphBlock
+    rb = RefGraphBlock(seed=99)
+    blk = mg.GraphBlock(node_feature_dim=20, num_segments=2)
+    blk.patch_gat_model.load_state_dict(rb.patch_gat_model.state_dict())
+    blk.segment_predictor.gnn_predictor.load_state_dict(rb.predictor_net.state_dict())
+    blk.region_gat_model.load_state_dict(rb.region_gat_model.state_dict())
+    blk = blk.cuda().eval()
+    gen = torch.Generator().manual_seed(11)
+    fm = torch.randn(B, 20, H, W, generator=gen).to(dtype)
+    with torch.no_grad():
+        out = blk(feature_map=fm.cuda())
+    nph, npw = out.grid
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    for b in range(B):
+        ref = rb.image(H, W, feature_map=fm[b].float())
+        assert ref["grid"] == (nph, npw)
+        if b == 0:
+            assert torch.equal(mg.ops.grid_edge_index(nph, npw, "cuda").cpu(), ref["edge_index"])
+        # bf16 storage: the pooled node features are rounded to bf16 (5e-3 .. 1.4e-2 of the 2e-2 budget, SURVEY App. B)
+        assert maxabs(out.patch_features[b], ref["h"]) <= tol
+        assert maxabs(out.soft_assignments[b], ref["S"]) <= tol
+        lab = out.hard_labels[b].cpu().long()
+        diff = lab != ref["hard"]
+        if diff.any():
+            top2 = torch.topk(ref["S"], 2, dim=1).values
+            assert float((top2[diff, 0] - top2[diff, 1]).abs().max()) <= 2 * tol
+            assert int(diff.sum()) <= max(1, int((1e-3 if dtype == torch.float32 else 2e-2) * lab.numel()))
+            continue            # (the tail for flipped labels is covered against the oracle port in _check_block)
+        assert float(out.l_partition[b]) == pytest.approx(float(ref["loss"]), rel=10 * tol, abs=tol)
+        assert maxabs(out.region_features[b], ref["G"]) <= tol
+        assert maxabs(out.f_g[b].float(), ref["f_g"]) <= tol
