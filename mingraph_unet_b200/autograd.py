@@ -121,7 +121,9 @@ class _UnpoolFn(torch.autograd.Function):
     reduction of the dense gradient back onto the K region rows."""
 
     @staticmethod
-    def forward(ctx, table, labels, Hp, Wp, H, W, out, out_dtype):
+    def forward(ctx, out, table, labels, Hp, Wp, H, W, out_dtype):
+        # `out` (the tensor modified in place) is the FIRST argument: autograd's CopySlices, which wraps this function when
+        # `out` is a view of a larger buffer, takes input 0 to be the modified tensor
         res = ops.unpool_nearest(table, labels, Hp, Wp, H, W, out=out, out_dtype=out_dtype)
         ctx.save_for_backward(labels)
         ctx.dims = (table.shape[1], Hp, Wp)
@@ -133,7 +135,8 @@ class _UnpoolFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         (labels,) = ctx.saved_tensors
         K, Hp, Wp = ctx.dims
-        return ops.unpool_nearest_backward(grad_out, labels, K, Hp, Wp), None, None, None, None, None, None, None
+        # gradient w.r.t. the previous content of `out`: none (it was overwritten; CopySlices reads None as zeros)
+        return None, ops.unpool_nearest_backward(grad_out, labels, K, Hp, Wp), None, None, None, None, None, None
 
 
 def unpool_apply(table, labels, Hp, Wp, H, W, out=None, out_dtype=torch.float32):
@@ -144,8 +147,8 @@ def unpool_apply(table, labels, Hp, Wp, H, W, out=None, out_dtype=torch.float32)
             # own history, not a detached copy
             if out.requires_grad and out.is_leaf:
                 raise RuntimeError("unpool_apply: `out` is a leaf that requires grad; pass a buffer (slice) that does not")
-            return _UnpoolFn.apply(table.contiguous(), labels, Hp, Wp, H, W, out, out.dtype)
-        return _UnpoolFn.apply(table.contiguous(), labels, Hp, Wp, H, W, None, out_dtype)
+            return _UnpoolFn.apply(out, table.contiguous(), labels, Hp, Wp, H, W, out.dtype)
+        return _UnpoolFn.apply(None, table.contiguous(), labels, Hp, Wp, H, W, out_dtype)
     return ops.unpool_nearest(table, labels, Hp, Wp, H, W, out=out, out_dtype=out_dtype)
 
 
