@@ -426,7 +426,7 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   // bf16 storage, inference: score pre-pass + transform on the tensor pipe (gat_tc.cu)
   if (x_dtype == MG_BF16 && dropout_p == 0.f && !save_den && !save_z &&
       gat_tc_supported(N, in_dim, out_dim, heads, concat ? 1 : 0, out_dtype == MG_BF16 ? 1 : 0))
-    return gat_tc_launch(x, rowptr, col, s, gmax, u, W, a, N, in_dim, out_dim, heads, concat ? 1 : 0, slope, nodes_per_graph, out,
+    return gat_tc_launch(x, rowptr, col, s, gmax, u, W, a, N, E, in_dim, out_dim, heads, concat ? 1 : 0, slope, nodes_per_graph, out,
                          out_dtype == MG_BF16 ? 1 : 0, st);
 
   if ((rc = gat_scores_and_max(x, x_dtype, rowptr, col, N, W, a, in_dim, out_dim, heads, nodes_per_graph, s, gmax, u, st)))

@@ -27,7 +27,7 @@ int gat_transform_tma_launch(const void* z_bf16, const float* W, void* w_bf16, i
 bool gat_tc_supported(int N, int in_dim, int F, int heads, int concat, int out_bf16);
 // (runs its own score / edge-max pre-pass into s (N, 2*heads) and gmax (G, heads))
 int gat_tc_launch(const void* x, const int32_t* rowptr, const int32_t* col, float* s, float* gmax, float* u, const float* W,
-                  const float* a, int N, int in_dim, int F, int heads, int concat, float slope, int nodes_per_graph, void* out,
+                  const float* a, int N, int64_t E, int in_dim, int F, int heads, int concat, float slope, int nodes_per_graph, void* out,
                   int out_bf16, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------

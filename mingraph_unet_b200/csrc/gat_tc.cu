@@ -39,6 +39,7 @@ struct GatTcArgs {
   const float* W;          // (heads, F, in)
   void* out;
   int N, F, concat, out_bf16, nodes_per_graph, tmem_cols;
+  int64_t E;
   float slope;
 };
 
@@ -279,74 +280,100 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
 }
 
 // ---- pre-pass 2: exact per-graph maximum of s_src[i] + s_tgt[j] over the edges (graph_attention.py:86) ----------
-// 8 lanes per destination; each block owns a contiguous node range and issues one atomic max per head when the
-// range lies in one graph (order-independent, hence deterministic).
-template <int NH>
-__global__ void __launch_bounds__(256, 8) tc_edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                          const float* __restrict__ s, int N, int nodes_per_graph,
-                                                          int nodes_per_block, float* __restrict__ gmax) {
+// Thread per destination, 32 consecutive destinations per warp step; a thread walks its in-edges four at a time with
+// the four column loads and then the four 16-byte score gathers all in flight (the round-1 kernel put 8 lanes on a
+// destination: one edge per lane, three dependent round trips per destination and a full-mask shuffle inside a loop
+// that not every group of the last warp entered — a hang for N % 4 != 0).  Maxima are order-independent, so the warp
+// reduction + one atomic max per (warp, graph, head) is deterministic.
+template <int NH, int UN>
+__global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                       const float* __restrict__ s, int N, int nodes_per_graph,
+                                                       float* __restrict__ gmax) {
   constexpr int NQ = 2 * NH;
   __shared__ float red[8][NH];
+  __shared__ int red_g[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gl = threadIdx.x & 7, gi = threadIdx.x >> 3;                       // 32 groups of 8 lanes
-  const int start = blockIdx.x * nodes_per_block, stop = min(N, start + nodes_per_block);
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  // running maxima of the warp for graph g_run (flushed with one atomic per head when the graph changes / at the end:
+  // atomics on the same four addresses serialise in L2, so there must be few of them)
   float m_run[NH];
 #pragma unroll
   for (int h = 0; h < NH; ++h) m_run[h] = -INFINITY;
   int g_run = -1;
-  for (int j = start + gi; j < stop; j += 32) {
-    const int g = nodes_per_graph > 0 ? j / nodes_per_graph : 0;
-    if (g != g_run) {
-      if (g_run >= 0 && gl == 0) {
-#pragma unroll
-        for (int h = 0; h < NH; ++h)
-          if (m_run[h] > -INFINITY) atomic_max_f32(gmax + (size_t)g_run * NH + h, m_run[h]);
-      }
-#pragma unroll
-      for (int h = 0; h < NH; ++h) m_run[h] = -INFINITY;
-      g_run = g;
-    }
-    const int beg = __ldg(rowptr + j), end = __ldg(rowptr + j + 1);
+  for (int base = wid * 32; base < N; base += nw * 32) {       // warp-uniform trip count: the shuffles below are safe
+    const int j = base + lane;
+    const bool ok = j < N;
     float m[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) m[h] = -INFINITY;
-    for (int k = beg + gl; k < end; k += 8) {
-      float sv[NH];
-      load_scores<NH>(s + (size_t)__ldg(col + k) * NQ, sv);
+    if (ok) {
+      const int beg = __ldg(rowptr + j), end = __ldg(rowptr + j + 1);
+      for (int k = beg; k < end; k += UN) {                    // UN column loads, then UN score gathers, all in flight
+        int c[UN];
 #pragma unroll
-      for (int h = 0; h < NH; ++h) m[h] = fmaxf(m[h], sv[h]);
+        for (int e = 0; e < UN; ++e) c[e] = k + e < end ? __ldg(col + k + e) : -1;
+        float sv[UN][NH];
+#pragma unroll
+        for (int e = 0; e < UN; ++e) {
+#pragma unroll
+          for (int h = 0; h < NH; ++h) sv[e][h] = -INFINITY;
+          if (c[e] >= 0) load_scores<NH>(s + (size_t)c[e] * NQ, sv[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < UN; ++e)
+#pragma unroll
+          for (int h = 0; h < NH; ++h) m[h] = fmaxf(m[h], sv[e][h]);
+      }
+      float st[NH];
+      load_scores<NH>(s + (size_t)j * NQ + NH, st);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) m[h] += st[h];                                 // -inf stays -inf for isolated nodes
     }
-    float st[NH];
-    load_scores<NH>(s + (size_t)j * NQ + NH, st);
+    const int g = (nodes_per_graph > 0 && ok) ? j / nodes_per_graph : 0;
+    const int g_first = __shfl_sync(kFull, g, 0);
+    const bool uniform = __all_sync(kFull, !ok || g == g_first);
+    if (uniform) {
+      if (g_first != g_run) {                                  // warp-uniform: flush the previous graph's maxima
+        if (g_run >= 0 && lane == 0) {
 #pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      m[h] = fmaxf(m[h], __shfl_xor_sync(kFull, m[h], 1, 8));
-      m[h] = fmaxf(m[h], __shfl_xor_sync(kFull, m[h], 2, 8));
-      m[h] = fmaxf(m[h], __shfl_xor_sync(kFull, m[h], 4, 8));
-      m_run[h] = fmaxf(m_run[h], m[h] + st[h]);                                // -inf stays -inf for isolated nodes
+          for (int h = 0; h < NH; ++h)
+            if (m_run[h] > -INFINITY) atomic_max_f32(gmax + (size_t)g_run * NH + h, m_run[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) m_run[h] = -INFINITY;
+        g_run = g_first;
+      }
+#pragma unroll
+      for (int h = 0; h < NH; ++h) m_run[h] = fmaxf(m_run[h], warp_max(m[h]));
+    } else if (ok) {                                           // a graph boundary inside the warp's 32 nodes (rare)
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+        if (m[h] > -INFINITY) atomic_max_f32(gmax + (size_t)g * NH + h, m[h]);
     }
   }
-  const int g_first = nodes_per_graph > 0 ? start / nodes_per_graph : 0;
-  const bool uniform = __syncthreads_and(g_run < 0 || g_run == g_first) != 0;
-  if (uniform) {
+  // block level: when every warp ended on the same graph, one atomic per head for the whole block
+  if (lane == 0) {
+    red_g[warp] = g_run;
 #pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      float v = m_run[h];
+    for (int h = 0; h < NH; ++h) red[warp][h] = m_run[h];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int gw = lane < 8 ? red_g[lane] : -1;
+    const int g0 = __shfl_sync(kFull, gw, 0);
+    const bool same = __all_sync(kFull, lane >= 8 || gw == g0 || gw < 0);
+    if (same) {
+      if (lane < NH && g0 >= 0) {
+        float v = red[0][lane];
 #pragma unroll
-      for (int o = 8; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
-      if (lane == 0) red[warp][h] = v;
+        for (int w = 1; w < 8; ++w) v = fmaxf(v, red_g[w] >= 0 ? red[w][lane] : -INFINITY);
+        if (v > -INFINITY) atomic_max_f32(gmax + (size_t)g0 * NH + lane, v);
+      }
+    } else if (lane < 8 && gw >= 0) {
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+        if (red[lane][h] > -INFINITY) atomic_max_f32(gmax + (size_t)gw * NH + h, red[lane][h]);
     }
-    __syncthreads();
-    if (threadIdx.x < NH) {
-      float v = red[0][threadIdx.x];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w][threadIdx.x]);
-      if (v > -INFINITY && start < N) atomic_max_f32(gmax + (size_t)g_first * NH + threadIdx.x, v);
-    }
-  } else if (g_run >= 0 && gl == 0) {
-#pragma unroll
-    for (int h = 0; h < NH; ++h)
-      if (m_run[h] > -INFINITY) atomic_max_f32(gmax + (size_t)g_run * NH + h, m_run[h]);
   }
 }
 
@@ -674,6 +701,486 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
   }
 }
 
+
+// =====================================================================================================================
+// Aggregation ON THE TENSOR CORES (heads = 4, in = 64; round 2).  The FFMA2 gather warps above spend ~280 warp
+// instructions per destination (bf16 -> fp32 conversion, one FFMA2 per (edge, head, feature pair), a shuffle per (edge,
+// head)); at N = 262 144, k = 8 that alone is 63 us of issue slots.  Here the weighted sum itself is an MMA:
+//   rows    (destination d, head h) of 4 destinations x 4 heads = 16          (M)
+//   columns edge slots: 8 per destination, two destinations per k-step        (K = 16)
+//   A       block-diagonal attention numerators p[d][h][e] (bf16 hi + lo parts: 16 mantissa bits, two MMAs)
+//   B       the 32 gathered source rows (bf16, exact), staged in shared memory by cp.async (zero-filled where a slot
+//           has no edge) and read back with ldmatrix.trans
+//   C       z[(d,h)][0..64) in fp32 fragments: 32 mma.m16n8k16 per 4 destinations and 8 edges each
+// so a destination costs ~45 warp instructions.  A warp owns "steps" of 4 consecutive destinations (step g of the CTA
+// -> warp g % 12) and walks each step's edges in chunks of 8 per destination; source rows are double-buffered per warp
+// and software-pipelined three deep (column indices of item n+2, rows + attention scalars of item n+1 in flight while
+// item n runs on the tensor cores).  The normalised z goes to shared memory as the bf16 K-major UMMA A operand
+// (128-byte swizzle), the transform W_h z runs on tcgen05 (kind::f16, M128 x N=F x K16, fp32 accumulators in TMEM,
+// double-buffered over tiles) and the 4 epilogue warps are those of gat_tc_kernel.
+// Precision: p carries 16 mantissa bits, x is exact, sums are fp32; z and W are rounded to bf16 for the transform
+// (fp32 accumulate) — measured against the fp32 oracle in tests/test_gpu_tc.py (budget 2e-2).
+// =====================================================================================================================
+constexpr int kAgWarps = 12;
+constexpr int kAgThreads = (kAgWarps + 4) * 32;            // 512 -> up to 128 registers per thread
+constexpr int kAgIn = 64, kAgNH = 4;
+constexpr int kAgRowBytes = kAgIn * 2;                      // 128
+constexpr int kAgStageBytes = 32 * kAgRowBytes;             // 4 KB: 4 destinations x 8 edge slots
+constexpr int kAgStages = 2;
+constexpr int kAgStepsPerTile = kTcTile / 4;                // 32
+
+struct AgSmem {
+  int a_off, b_off, ring_off, stage_off, total;
+};
+__host__ __device__ inline AgSmem ag_smem_layout(int F, bool staged) {
+  AgSmem L;
+  int o = kTcHeader;
+  L.a_off = o;     o += kAgNH * kTcTile * 128;              // 4 head blocks of 128 rows x 64 bf16
+  L.b_off = o;     o += kAgNH * F * 128;
+  L.ring_off = o;  o += kAgWarps * kAgStages * kAgStageBytes;
+  o = (o + 1023) & ~1023;
+  L.stage_off = o; o += staged ? kTcTile * F * 2 : 0;
+  L.total = o + 1024;
+  return L;
+}
+
+__device__ __forceinline__ void ag_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void ag_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ag_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ag_ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void ag_mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ag_pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// bf16 hi parts of (a, b) and the bf16 of the remainders
+__device__ __forceinline__ void ag_split(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo = ag_pack_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcArgs A) {
+  constexpr int NH = kAgNH, IN = kAgIn;
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  const bool staged = A.out_bf16 && !A.concat;
+  const AgSmem L = ag_smem_layout(A.F, staged);
+  const uint32_t bar_a_empty = tc_smem_u32(sm + 8);
+  const uint32_t bar_t_full0 = tc_smem_u32(sm + 16), bar_t_empty0 = tc_smem_u32(sm + 32);   // [2] each, 8 B apart
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sm + 64);
+  int* arrive_cnt = reinterpret_cast<int*>(sm + 72);        // steps of the CTA whose z rows are in the A operand
+  unsigned char* As = sm + L.a_off;
+  unsigned char* Bs = sm + L.b_off;
+  unsigned char* Ss = sm + L.stage_off;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = A.F;
+  const int ntiles = ceil_div(A.N, kTcTile);
+  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+    *arrive_cnt = 0;
+    tc_mbar_init(bar_a_empty, 1);
+    tc_mbar_init(bar_t_full0, 1);
+    tc_mbar_init(bar_t_full0 + 8, 1);
+    tc_mbar_init(bar_t_empty0, 4);
+    tc_mbar_init(bar_t_empty0 + 8, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kAgWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_ptr_s)),
+                 "r"(A.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // W (fp32) -> bf16 B operand: element (h, f, i) -> block h, row f, 16-byte chunk (i / 8) ^ (f & 7)
+  for (int idx = tid; idx < NH * F * (IN / 8); idx += kAgThreads) {
+    const int c8 = idx % (IN / 8);
+    const int f = (idx / (IN / 8)) % F;
+    const int h = idx / ((IN / 8) * F);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(A.W + ((size_t)h * F + f) * IN) + 2 * c8);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(A.W + ((size_t)h * F + f) * IN) + 2 * c8 + 1);
+    uint4 pk;
+    pk.x = ag_pack_bf16(w0.x, w0.y); pk.y = ag_pack_bf16(w0.z, w0.w);
+    pk.z = ag_pack_bf16(w1.x, w1.y); pk.w = ag_pack_bf16(w1.z, w1.w);
+    *reinterpret_cast<uint4*>(Bs + (size_t)h * F * 128 + f * 128 + ((c8 ^ (f & 7)) << 4)) = pk;
+  }
+  tc_fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  // instruction descriptor: D = f32, A = B = bf16, both K-major, N = F, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+
+  auto issue_mma = [&](int it) {                            // one thread: tile `it` of this CTA, A operand complete
+    const int stg = it & 1, n = it >> 1;
+    if (n > 0) tc_mbar_wait(bar_t_empty0 + 8 * stg, (uint32_t)((n - 1) & 1));
+    tc_fence_after();
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h) {
+      const uint32_t d_tmem = tmem_base + (uint32_t)(stg * NH * F + h * F);
+      const uint64_t ad = tc_desc_sw128(tc_smem_u32(As + (size_t)h * kTcTile * 128));
+      const uint64_t bd = tc_desc_sw128(tc_smem_u32(Bs + (size_t)h * F * 128));
+#pragma unroll
+      for (int k = 0; k < IN / 16; ++k)                     // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
+        tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+    }
+    tc_commit(bar_a_empty);                                 // A may be overwritten once these MMAs retire
+    tc_commit(bar_t_full0 + 8 * stg);                       // accumulators of this tile are complete
+  };
+
+  if (warp < kAgWarps) {
+    // ======================= aggregation warps: gathered rows x attention -> z -> A operand =======================
+    // (written flat, with every lane-constant address term hoisted: the first version spent ~950 instructions per item
+    //  on index arithmetic, runtime divisions and pipeline bookkeeping for 32 HMMA)
+    const int g8 = lane >> 2, t4 = lane & 3;                  // MMA fragment coordinates
+    const int hd = g8 & 3, dsel = g8 >> 2;                    // fragment row g8 = (destination dsel, head hd); row g8 + 8 = (dsel + 2, hd)
+    const int r4 = lane >> 3, ch8 = lane & 7;                 // loader role: destination of the step / row within a 4-row group, 16-byte chunk
+    const uint32_t ring0 = tc_smem_u32(sm + L.ring_off + (size_t)warp * kAgStages * kAgStageBytes);
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float slope = A.slope;
+    const int npg = A.nodes_per_graph;
+    const int tile_stride = (int)gridDim.x * kTcTile;
+    const int n_end = ntiles * kTcTile;                       // a cursor is exhausted once its tile base reaches this
+    // lane constants
+    const uint32_t cp_off_even = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ r4) << 4));          // rows 8m + r4
+    const uint32_t cp_off_odd = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ (r4 | 4)) << 4));      // rows 8m + 4 + r4
+    const char* x_lane = reinterpret_cast<const char*>(A.x) + ch8 * 16;
+    const float* s_src_lane = A.s + hd;                       // + node * 8
+    const float* s_tgt_lane = A.s + NH + hd;
+    uint32_t ld_off[4];                                       // ldmatrix.x4.trans lane addresses for the 4 feature pairs (k-step 0)
+#pragma unroll
+    for (int np = 0; np < 4; ++np)
+      ld_off[np] = (uint32_t)((((r4 & 1) * 8 + ch8) * kAgRowBytes) + ((((np << 1) | (r4 >> 1)) ^ ch8) << 4));
+    const uint32_t mask_d0 = dsel == 0 ? 0xffffffffu : 0u, mask_d1 = ~mask_d0;
+    const uint32_t z_lane = tc_smem_u32(As) + (uint32_t)(hd * kTcTile * 128 + dsel * 128 + t4 * 4);
+    const int slotA = dsel * 8 + 2 * t4, slotB = slotA + 16;  // the lane's (destination, edge) slots: A rows 0-7, B rows 8-15
+    const float M_single = npg > 0 ? 0.f : leaky_relu(__ldg(A.gmax + hd), slope);     // one graph: the shift is a lane constant
+
+    // ---- cursor over the warp's steps (warp-uniform), loader-lane row ranges ----
+    int cur_tb = (int)blockIdx.x * kTcTile, cur_step = warp, cur_it = 0;     // tile base node, step in tile, tile ordinal
+    int cur_c = 0, cur_nch = 1, cur_beg = 0, cur_end = 0, nxt_beg = 0, nxt_end = 0;
+#define AG_NEXT_STEP(tb, st, it)  \
+  do {                            \
+    st += kAgWarps;               \
+    if (st >= kAgStepsPerTile) {  \
+      st -= kAgStepsPerTile;      \
+      tb += tile_stride;          \
+      ++it;                       \
+    }                             \
+  } while (0)
+#define AG_FETCH_RP(tb, st, b, e)                       \
+  do {                                                  \
+    b = 0; e = 0;                                       \
+    const int j_ = tb + st * 4 + r4;                    \
+    if (tb < n_end && j_ < A.N) {                       \
+      b = __ldg(A.rowptr + j_);                         \
+      e = __ldg(A.rowptr + j_ + 1);                     \
+    }                                                   \
+  } while (0)
+    AG_FETCH_RP(cur_tb, cur_step, cur_beg, cur_end);
+    {
+      int tb = cur_tb, st = cur_step, it = cur_it;
+      AG_NEXT_STEP(tb, st, it);
+      AG_FETCH_RP(tb, st, nxt_beg, nxt_end);
+    }
+    cur_nch = max(1, __reduce_max_sync(kFull, (cur_end - cur_beg + 7) >> 3));
+    // advance the cursor by one item; rowptr of the step after the next one is prefetched
+#define AG_ADVANCE()                                                            \
+  do {                                                                          \
+    if (++cur_c >= cur_nch) {                                                   \
+      AG_NEXT_STEP(cur_tb, cur_step, cur_it);                                   \
+      cur_beg = nxt_beg; cur_end = nxt_end;                                     \
+      int tb = cur_tb, st = cur_step, it = cur_it;                              \
+      AG_NEXT_STEP(tb, st, it);                                                 \
+      AG_FETCH_RP(tb, st, nxt_beg, nxt_end);                                    \
+      cur_c = 0;                                                                \
+      cur_nch = max(1, __reduce_max_sync(kFull, (cur_end - cur_beg + 7) >> 3)); \
+    }                                                                           \
+  } while (0)
+    // loader lane: source node of its slot in the cursor's item (-1: no edge)
+#define AG_LOAD_SRC(dst)                                             \
+  do {                                                               \
+    const int k_ = cur_beg + 8 * cur_c + ch8;                        \
+    dst = (cur_tb < n_end && k_ < cur_end) ? __ldg(A.col + k_) : -1; \
+  } while (0)
+    // 32 rows x 8 chunks of 16 B into ring stage `stg`; lanes 8r .. 8r+7 read one 128-byte row; empty slots are zero-filled
+#define AG_ISSUE_ROWS(src, stg)                                                                       \
+  do {                                                                                                \
+    const uint32_t sb_ = ring0 + (uint32_t)(stg) * kAgStageBytes;                                      \
+    _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) {                                                 \
+      const int sn_ = __shfl_sync(kFull, src, i_ * 4 + r4);                                            \
+      ag_cp_async16(sb_ + (uint32_t)(i_ * 4 * kAgRowBytes) + ((i_ & 1) ? cp_off_odd : cp_off_even),   \
+                    x_lane + (size_t)(unsigned)max(sn_, 0) * kAgRowBytes, sn_ >= 0 ? 16u : 0u);        \
+    }                                                                                                 \
+  } while (0)
+    // attention scalars of an item: s_src of the lane's 4 slots (-inf: empty), s_tgt and shift of its two destinations
+#define AG_LOAD_ATT(src, node0, sv, st2, M2)                                                           \
+  do {                                                                                                 \
+    const int n0_ = __shfl_sync(kFull, src, slotA), n1_ = __shfl_sync(kFull, src, slotA + 1);           \
+    const int n2_ = __shfl_sync(kFull, src, slotB), n3_ = __shfl_sync(kFull, src, slotB + 1);           \
+    sv[0] = n0_ >= 0 ? __ldg(s_src_lane + (size_t)(unsigned)n0_ * (2 * NH)) : -INFINITY;                 \
+    sv[1] = n1_ >= 0 ? __ldg(s_src_lane + (size_t)(unsigned)n1_ * (2 * NH)) : -INFINITY;                 \
+    sv[2] = n2_ >= 0 ? __ldg(s_src_lane + (size_t)(unsigned)n2_ * (2 * NH)) : -INFINITY;                 \
+    sv[3] = n3_ >= 0 ? __ldg(s_src_lane + (size_t)(unsigned)n3_ * (2 * NH)) : -INFINITY;                 \
+    const int ja_ = node0 + dsel, jb_ = ja_ + 2;                                                        \
+    const bool va_ = node0 >= 0 && ja_ < A.N, vb_ = node0 >= 0 && jb_ < A.N;                             \
+    st2[0] = va_ ? __ldg(s_tgt_lane + (size_t)(unsigned)ja_ * (2 * NH)) : 0.f;                           \
+    st2[1] = vb_ ? __ldg(s_tgt_lane + (size_t)(unsigned)jb_ * (2 * NH)) : 0.f;                           \
+    M2[0] = M_single; M2[1] = M_single;                                                                 \
+    if (npg > 0) {                                                                                      \
+      M2[0] = va_ ? leaky_relu(__ldg(A.gmax + (size_t)(ja_ / npg) * NH + hd), slope) : 0.f;              \
+      M2[1] = vb_ ? leaky_relu(__ldg(A.gmax + (size_t)(jb_ / npg) * NH + hd), slope) : 0.f;              \
+    }                                                                                                   \
+  } while (0)
+
+    // ---- software pipeline: item n on the tensor cores, rows + scalars of item n+1 and columns of item n+2 in flight ----
+    // item descriptor: node0 = first destination of its step (-1: past the end), row0 = step * 4, it, first / last chunk flags
+    int node0_0 = cur_tb < n_end ? cur_tb + cur_step * 4 : -1, row0_0 = cur_step * 4, it_0 = cur_it;
+    bool first_0 = true, last_0 = cur_nch == 1;
+    int src0;
+    AG_LOAD_SRC(src0);
+    float sv0[4], st0[2], M0[2];
+    AG_LOAD_ATT(src0, node0_0, sv0, st0, M0);
+    AG_ISSUE_ROWS(src0, 0);
+    ag_cp_commit();
+    AG_ADVANCE();
+    int node0_1 = cur_tb < n_end ? cur_tb + cur_step * 4 : -1, row0_1 = cur_step * 4, it_1 = cur_it;
+    bool first_1 = cur_c == 0, last_1 = cur_c == cur_nch - 1;
+    int src1;
+    AG_LOAD_SRC(src1);
+    float acc[8][4];
+    float den0 = 0.f, den1 = 0.f;
+    uint32_t stage = 0;
+    while (node0_0 >= 0) {
+      // A. rows of item n+1
+      if (node0_1 >= 0) AG_ISSUE_ROWS(src1, stage ^ 1u);
+      ag_cp_commit();
+      // B. columns of item n+2
+      AG_ADVANCE();
+      const int node0_2 = cur_tb < n_end ? cur_tb + cur_step * 4 : -1, row0_2 = cur_step * 4, it_2 = cur_it;
+      const bool first_2 = cur_c == 0, last_2 = cur_c == cur_nch - 1;
+      int src2;
+      AG_LOAD_SRC(src2);
+      // C. attention scalars of item n+1
+      float sv1[4], st1[2], M1[2];
+      AG_LOAD_ATT(src1, node0_1, sv1, st1, M1);
+      // D. rows of item n have landed
+      ag_cp_wait<1>();
+      __syncwarp();
+      if (first_0) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        den0 = den1 = 0.f;
+      }
+      // E. attention numerators (graph_attention.py:61-65,86) and the block-diagonal A fragments
+      float p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float e = sv0[i] + st0[i >> 1];
+        p[i] = tc_ex2((fmaxf(e, e * slope) - M0[i >> 1]) * kLog2e);                 // LeakyReLU (0 <= slope <= 1); empty slot: ex2(-inf) = 0
+      }
+      den0 += p[0] + p[1];
+      den1 += p[2] + p[3];
+      uint32_t hiA, loA, hiB, loB;
+      ag_split(p[0], p[1], hiA, loA);
+      ag_split(p[2], p[3], hiB, loB);
+      const uint32_t sb = ring0 + stage * kAgStageBytes;
+      {
+        // k-step 0: slots of destinations 0 (k 0-7) and 1 (k 8-15) feed fragment rows 0-7 only
+        const uint32_t a0h = hiA & mask_d0, a0l = loA & mask_d0, a2h = hiA & mask_d1, a2l = loA & mask_d1;
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b[4];
+          ag_ldmatrix_x4_trans(sb + ld_off[np], b);
+          ag_mma_bf16(acc[2 * np], a0h, 0u, a2h, 0u, b[0], b[1]);
+          ag_mma_bf16(acc[2 * np], a0l, 0u, a2l, 0u, b[0], b[1]);
+          ag_mma_bf16(acc[2 * np + 1], a0h, 0u, a2h, 0u, b[2], b[3]);
+          ag_mma_bf16(acc[2 * np + 1], a0l, 0u, a2l, 0u, b[2], b[3]);
+        }
+        // k-step 1: destinations 2, 3 feed fragment rows 8-15
+        const uint32_t a1h = hiB & mask_d0, a1l = loB & mask_d0, a3h = hiB & mask_d1, a3l = loB & mask_d1;
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b[4];
+          ag_ldmatrix_x4_trans(sb + 16 * kAgRowBytes + ld_off[np], b);
+          ag_mma_bf16(acc[2 * np], 0u, a1h, 0u, a3h, b[0], b[1]);
+          ag_mma_bf16(acc[2 * np], 0u, a1l, 0u, a3l, b[0], b[1]);
+          ag_mma_bf16(acc[2 * np + 1], 0u, a1h, 0u, a3h, b[2], b[3]);
+          ag_mma_bf16(acc[2 * np + 1], 0u, a1l, 0u, a3l, b[2], b[3]);
+        }
+      }
+      __syncwarp();                                           // every lane has read the stage: the next issue may refill it
+      // F. last chunk of the step: softmax denominators, z rows -> A operand, hand the tile to the tensor core
+      if (last_0) {
+        float d0 = den0, d1 = den1;
+        d0 += __shfl_xor_sync(kFull, d0, 1); d1 += __shfl_xor_sync(kFull, d1, 1);
+        d0 += __shfl_xor_sync(kFull, d0, 2); d1 += __shfl_xor_sync(kFull, d1, 2);
+        const float inv0 = 1.f / (d0 + 1e-10f), inv1 = 1.f / (d1 + 1e-10f);           // graph_attention.py:96
+        if (it_0 > 0) tc_mbar_wait(bar_a_empty, (uint32_t)((it_0 - 1) & 1));           // previous tile's MMAs have read A
+        // rows qa = row0 + dsel and qa + 2; chunk nt of a row sits at ((nt ^ (row & 7)) << 4)
+        const uint32_t za = z_lane + (uint32_t)row0_0 * 128u;
+        const uint32_t xa = (uint32_t)(((row0_0 + dsel) & 7) << 4), xb = xa ^ 0x20u;   // (row + 2) & 7 = (row & 7) ^ 2 (row & 3 = dsel < 2)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const uint32_t va = ag_pack_bf16(acc[nt][0] * inv0, acc[nt][1] * inv0);
+          const uint32_t vb = ag_pack_bf16(acc[nt][2] * inv1, acc[nt][3] * inv1);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(za + ((uint32_t)(nt << 4) ^ xa)), "r"(va) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(za + 256u + ((uint32_t)(nt << 4) ^ xb)), "r"(vb) : "memory");
+        }
+        tc_fence_async_smem();                                // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          const bool last = atomicAdd(arrive_cnt, 1) == kAgStepsPerTile * (it_0 + 1) - 1;
+          __threadfence_block();
+          if (last) issue_mma(it_0);                          // the LAST step of the tile to arrive issues its MMAs
+        }
+        __syncwarp();
+      }
+      // rotate the pipeline
+      node0_0 = node0_1; row0_0 = row0_1; it_0 = it_1; first_0 = first_1; last_0 = last_1; src0 = src1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sv0[i] = sv1[i];
+      st0[0] = st1[0]; st0[1] = st1[1]; M0[0] = M1[0]; M0[1] = M1[1];
+      node0_1 = node0_2; row0_1 = row0_2; it_1 = it_2; first_1 = first_2; last_1 = last_2; src1 = src2;
+      stage ^= 1u;
+    }
+    ag_cp_wait<0>();
+#undef AG_NEXT_STEP
+#undef AG_FETCH_RP
+#undef AG_ADVANCE
+#undef AG_LOAD_SRC
+#undef AG_ISSUE_ROWS
+#undef AG_LOAD_ATT
+  } else {
+    // ============ epilogue warps: TMEM -> ELU -> head mean / concat -> global (as in gat_tc_kernel) ============
+    const int ew = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;
+    const int et = (warp - kAgWarps) * 32 + lane;             // 0..127 linear id among epilogue threads
+    const float inv_h = 1.f / (float)NH;
+    const int out_w = A.concat ? NH * F : F;
+    const int cpr = F / 8;                                    // 16-byte chunks per staged bf16 row
+    const int swz_mask = ((cpr & (cpr - 1)) == 0) ? (min(cpr, 8) - 1) : 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int stg = it & 1, nn = it >> 1;
+      const int tile_base = tile * kTcTile;
+      const int node = tile_base + row;
+      tc_mbar_wait_relaxed(bar_t_full0 + 8 * stg, (uint32_t)(nn & 1));
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(stg * NH * F);
+      for (int c0 = 0; c0 < F; c0 += 16) {
+        float oacc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) oacc[i] = 0.f;
+#pragma unroll
+        for (int h0 = 0; h0 < NH; h0 += 2) {
+          uint32_t v[2][16];
+          tc_tmem_ld16(t_row + (uint32_t)(h0 * F + c0), v[0]);
+          tc_tmem_ld16(t_row + (uint32_t)((h0 + 1) * F + c0), v[1]);
+          tc_tmem_wait_ld();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float e16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) e16[i] = tc_elu(__uint_as_float(v[hh][i]));          // ELU per head (:118)
+            if (A.concat) {
+              if (node < A.N) {
+                const size_t o = (size_t)node * out_w + (size_t)(h0 + hh) * F + c0;
+                if (A.out_bf16) {
+                  uint4 pk[2];
+                  unsigned* pw = reinterpret_cast<unsigned*>(pk);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) pw[i] = ag_pack_bf16(e16[2 * i], e16[2 * i + 1]);
+                  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + o);
+                  op[0] = pk[0]; op[1] = pk[1];
+                } else {
+                  float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(A.out) + o);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) op[i] = make_float4(e16[4 * i], e16[4 * i + 1], e16[4 * i + 2], e16[4 * i + 3]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) oacc[i] += e16[i];                                  // then the head mean (:158)
+            }
+          }
+        }
+        if (!A.concat) {
+          if (staged) {
+            uint4 pk[2];
+            unsigned* pw = reinterpret_cast<unsigned*>(pk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pw[i] = ag_pack_bf16(oacc[2 * i] * inv_h, oacc[2 * i + 1] * inv_h);
+            const int chunk = c0 >> 3;
+            *reinterpret_cast<uint4*>(Ss + (size_t)row * F * 2 + ((chunk ^ (row & swz_mask)) << 4)) = pk[0];
+            *reinterpret_cast<uint4*>(Ss + (size_t)row * F * 2 + (((chunk + 1) ^ (row & swz_mask)) << 4)) = pk[1];
+          } else if (node < A.N) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(A.out) + (size_t)node * out_w + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              op[i] = make_float4(oacc[4 * i] * inv_h, oacc[4 * i + 1] * inv_h, oacc[4 * i + 2] * inv_h, oacc[4 * i + 3] * inv_h);
+          }
+        }
+      }
+      // TMEM stage drained: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(bar_t_empty0 + 8 * stg);
+      if (staged) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int valid_rows = min(kTcTile, A.N - tile_base);
+        const int nchunks = valid_rows * cpr;
+        uint4* gdst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + (size_t)tile_base * F);
+        for (int idx = et; idx < nchunks; idx += 128) {
+          const int r = idx / cpr, c = idx - r * cpr;
+          gdst[idx] = *reinterpret_cast<const uint4*>(Ss + (size_t)r * F * 2 + ((c ^ (r & swz_mask)) << 4));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kAgWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(A.tmem_cols) : "memory");
+  }
+}
+
+static bool ag_mma_supported(int in_dim, int F, int heads, int concat, int out_bf16) {
+  static const int enabled = getenv("MG_GAT_AGG_MMA") ? atoi(getenv("MG_GAT_AGG_MMA")) : 1;
+  if (!enabled || heads != kAgNH || in_dim != kAgIn) return false;
+  if (F % 16 != 0 || F < 16 || 2 * heads * F > 512) return false;
+  return ag_smem_layout(F, out_bf16 && !concat).total <= 227 * 1024;
+}
+
 template <int NH, int LPN>
 static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, float* u, size_t smem, int grid,
                      cudaStream_t st) {
@@ -690,10 +1197,20 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
   if ((rc = check_launch("tc_u_kernel"))) return rc;
   tc_scores_kernel<NH, LPN><<<sgrid, 256, 0, st>>>(A.x, A.N, u, s);
   if ((rc = check_launch("tc_scores_kernel"))) return rc;
-  const int mblocks = std::min(ceil_div(A.N, 32), num_sms() * 8);
-  const int npb = ceil_div(ceil_div(A.N, mblocks), 32) * 32;
-  tc_edge_max_kernel<NH><<<ceil_div(A.N, npb), 256, 0, st>>>(A.rowptr, A.col, s, A.N, A.nodes_per_graph, npb, gmax);
+  const int mgrid = std::min(ceil_div(A.N, 256), num_sms() * 6);
+  if (A.E > (int64_t)A.N * 12)      // high in-degree: more gathers in flight per destination
+    tc_edge_max_kernel<NH, 8><<<mgrid, 256, 0, st>>>(A.rowptr, A.col, s, A.N, A.nodes_per_graph, gmax);
+  else
+    tc_edge_max_kernel<NH, 4><<<mgrid, 256, 0, st>>>(A.rowptr, A.col, s, A.N, A.nodes_per_graph, gmax);
   if ((rc = check_launch("tc_edge_max_kernel"))) return rc;
+  if (NH == kAgNH && LPN * 8 == kAgIn && ag_mma_supported(LPN * 8, A.F, NH, A.concat, A.out_bf16)) {
+    if (cudaFuncSetAttribute(gat_agg_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("gat_agg_mma_kernel: cannot raise dynamic shared memory");
+      return MG_ERR_CUDA;
+    }
+    gat_agg_mma_kernel<<<grid, kAgThreads, (size_t)ag_smem_layout(A.F, A.out_bf16 && !A.concat).total, st>>>(A);
+    return check_launch("gat_agg_mma_kernel");
+  }
   k<<<grid, kTcThreads, smem, st>>>(A);
   return check_launch("gat_tc_kernel");
 }
@@ -711,12 +1228,12 @@ bool gat_tc_supported(int N, int in_dim, int F, int heads, int concat, int out_b
 }
 
 int gat_tc_launch(const void* x, const int32_t* rowptr, const int32_t* col, float* s, float* gmax, float* u, const float* W,
-                  const float* a, int N, int in_dim, int F, int heads, int concat, float slope, int nodes_per_graph, void* out,
+                  const float* a, int N, int64_t E, int in_dim, int F, int heads, int concat, float slope, int nodes_per_graph, void* out,
                   int out_bf16, cudaStream_t st) {
   GatTcArgs A;
   A.x = reinterpret_cast<const __nv_bfloat16*>(x);
   A.rowptr = rowptr; A.col = col; A.s = s; A.gmax = gmax; A.W = W; A.out = out;
-  A.N = N; A.F = F; A.concat = concat; A.out_bf16 = out_bf16; A.nodes_per_graph = nodes_per_graph; A.slope = slope;
+  A.N = N; A.E = E; A.F = F; A.concat = concat; A.out_bf16 = out_bf16; A.nodes_per_graph = nodes_per_graph; A.slope = slope;
   int cols = 32;
   while (cols < 2 * heads * F) cols <<= 1;
   A.tmem_cols = cols;

@@ -56,9 +56,39 @@ def test_tc_layer_vs_oracle(mg, N, heads, fin, fout, concat, out_dtype):
     assert err <= TOL_BF16, err
     zero_rows = torch.bincount(ei[1], minlength=N) == 0
     assert float(y.float().cpu()[zero_rows].abs().max()) == 0.0
-    # tf32 transform error alone (fp32 output, no bf16 output rounding) is far inside the budget
+    # transform error alone (fp32 output, no bf16 output rounding: tf32 operands, or bf16 operands on the tensor-core
+    # aggregation path for heads = 4, in = 64) is far inside the budget
     if out_dtype == torch.float32:
-        assert err <= 5e-3, err
+        assert err <= 8e-3, err
+
+
+@pytest.mark.parametrize("N,kmin,kmax,fout,concat,out_dtype", [
+    (4096, 0, 40, 64, False, torch.float32),                  # up to 5 chunks of 8 edges per destination, isolated nodes
+    (4099, 8, 8, 64, False, torch.bfloat16),                  # exactly one full chunk, ragged last step (N % 4 != 0)
+    (4096, 17, 33, 32, False, torch.float32),
+    (9000, 1, 3, 48, True, torch.float32),                    # mostly empty slots, concat, F = 48
+    (70000, 8, 8, 64, False, torch.bfloat16),                 # several tiles per CTA: A / TMEM hand-offs wrap
+])
+def test_tensor_core_aggregation_vs_oracle(mg, N, kmin, kmax, fout, concat, out_dtype):
+    """gat_agg_mma_kernel (heads 4, in 64): attention-weighted sums on mma.sync from cp.async-staged source rows."""
+    gen = torch.Generator().manual_seed(N + kmax)
+    deg = torch.randint(kmin, kmax + 1, (N,), generator=gen)
+    deg[::13] = 0
+    tgt = torch.arange(N).repeat_interleave(deg)
+    src = torch.randint(0, N, (int(deg.sum()),), generator=gen)
+    ei = torch.stack([src, tgt])
+    x = torch.randn(N, 64, generator=gen)
+    if concat:
+        x *= 0.5
+    x = x.to(torch.bfloat16)
+    Ws, As = O.init_gat_params(64, fout, 4, gen)
+    ref = O.gat_layer(x.float(), ei, Ws, As, 0.2, concat=concat)
+    rowptr, col, _ = mg.ops.csr_from_coo(ei.cuda(), N, by_target=True)
+    y = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), concat=concat, slope=0.2, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    err = float((y.float().cpu() - ref).abs().max())
+    assert err <= (8e-3 if out_dtype == torch.float32 else TOL_BF16), err
+    assert float(y.float().cpu()[deg == 0].abs().max()) == 0.0
 
 
 def test_tc_batched_grid_per_graph_max(mg):
@@ -81,7 +111,8 @@ def test_tc_batched_grid_per_graph_max(mg):
 
 def test_tc_matches_fp32_pipe_path(mg):
     """Same inputs through the FP32-pipe kernel (N below the tensor-pipe threshold is not possible for the same
-    graph, so compare on the fp32 copy of the bf16 features): the two device paths agree to tf32 accuracy."""
+    graph, so compare on the fp32 copy of the bf16 features): the two device paths agree to the accuracy of the
+    tensor-pipe transform's operands (heads 4 / in 64: z and W rounded to bf16 on the tensor-core aggregation path)."""
     N, heads, fin, fout = 8192, 4, 64, 64
     gen = torch.Generator().manual_seed(9)
     ei = _random_graph(N, 2, 9, gen)
@@ -90,7 +121,7 @@ def test_tc_matches_fp32_pipe_path(mg):
     rowptr, col, _ = mg.ops.csr_from_coo(ei.cuda(), N, by_target=True)
     y_tc = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), out_dtype=torch.float32)
     y_f32 = mg.ops.gat_forward(x.float().cuda(), rowptr, col, Ws.cuda(), As.cuda(), out_dtype=torch.float32)
-    assert float((y_tc - y_f32).abs().max()) <= 5e-3
+    assert float((y_tc - y_f32).abs().max()) <= 1.2e-2
 
 
 # ---------------------------------------------------------------------------------------------
