@@ -530,17 +530,19 @@ def train_leg(ctx, B, steps, warmup, distributed=True, sampler=None, e2e=False):
     gen = torch.Generator().manual_seed(1000 + ctx.rank)
     fm_host = torch.randn(B, IN_DIM, H, W, generator=gen).to(dtype).pin_memory()
     fm_dev = fm_host.to(dev)
-    # stand-in for the downstream heads' loss: a fixed dense cotangent (the conv stack stays stock PyTorch and is
-    # outside the block); d loss / d F_g = wdense
+    # what the downstream heads send back: a dense cotangent d loss / d F_g (the conv stack stays stock PyTorch and is
+    # outside the block), handed to the block's backward as is
     wdense = (torch.randn(B, D_OUT, H, W, generator=gen) / (H * W)).to(dtype).to(dev)
     host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def loss_fn(out):
-        return (out.f_g * wdense).sum(dtype=torch.float32) + out.l_partition.mean()
+    def loss_fn(out):                          # the block's own loss term; the dense map's gradient is the cotangent below
+        return out.l_partition.mean()
 
-    # public API: the whole step (pool -> block fwd -> loss -> backward -> [NCCL all-reduce] -> Adam) as CUDA graphs
+    # public API: the whole step (pool -> block fwd -> loss -> backward from (dL/dF_g, loss) -> [NCCL all-reduce] -> Adam)
+    # as CUDA graphs
     lc0 = _lib.launch_count()
-    trainer = mg.CapturedTrainStep(blk, opt, fm_dev, (H, W), loss_fn, out_dtype=dtype, warmup=3, allreduce=distributed)
+    trainer = mg.CapturedTrainStep(blk, opt, fm_dev, (H, W), loss_fn, out_dtype=dtype, warmup=3, allreduce=distributed,
+                                   dense_cotangent=wdense)
     trainer_launches = (_lib.launch_count() - lc0) // 4                         # 3 warm-up steps + 1 recorded step
     fm_in = trainer.static_in
 

@@ -31,6 +31,30 @@ def _wants_grad(*ts) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
 
 
+class _StackHeadsFn(torch.autograd.Function):
+    """``stack([p.reshape(shape) for p in params])`` of the per-head parameters (the reference keeps one ``nn.Linear``
+    per head, graph_attention.py:28-31,144-148; the kernels take all heads stacked).  The backward hands every head a
+    VIEW of the stacked gradient: no unbind / reshape / accumulate kernels (torch's own ``stack`` + ``view`` graph cost
+    ~60 tiny launches per training step for the block's 20 parameters)."""
+
+    @staticmethod
+    def forward(ctx, shape, *params):
+        ctx.shapes = [p.shape for p in params]
+        return torch.stack([p.reshape(shape) for p in params], 0)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return (None,) + tuple(grad[i].view(s) for i, s in enumerate(ctx.shapes))
+
+
+def stack_heads(params, shape) -> torch.Tensor:
+    """``(H, *shape)`` stack of per-head parameters; differentiable (gradients arrive as views, see above)."""
+    params = list(params)
+    if _wants_grad(*params):
+        return _StackHeadsFn.apply(tuple(shape), *params)
+    return torch.stack([p.detach().reshape(shape) for p in params], 0)
+
+
 class _GATLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, a, g: Graph, concat: bool, slope: float, att_dropout: float, out_dtype=None):

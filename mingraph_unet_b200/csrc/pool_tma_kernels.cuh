@@ -105,6 +105,40 @@ __device__ __forceinline__ float pt_sum16<__nv_bfloat16>(const uint4& u) {
   return lo + hi;
 }
 
+// Packed accumulation (sm_100 add.f32x2): four fp32 pair accumulators per lane take one 16-byte vector per call.
+// bf16: a 32-bit word holds two values whose fp32 images are (w << 16) and (w & 0xffff0000): shift + mask + ONE packed
+// add per word instead of two scalar adds; fp32: the vector is two pairs.  The summing code of this kernel is what
+// limits it (two warps per scheduler), so instructions per byte matter.
+#ifndef MG_HOST_EMULATION
+__device__ __forceinline__ void pt_add2(unsigned long long& acc, uint32_t lo, uint32_t hi) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(v));
+}
+__device__ __forceinline__ float pt_fold2(unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(c) : "l"(d));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(c));
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(a));
+  return __uint_as_float(lo) + __uint_as_float(hi);
+}
+template <typename T>
+__device__ __forceinline__ void pt_acc16(unsigned long long (&q)[4], const uint4& u);
+template <>
+__device__ __forceinline__ void pt_acc16<__nv_bfloat16>(unsigned long long (&q)[4], const uint4& u) {
+  pt_add2(q[0], u.x << 16, u.x & 0xffff0000u);
+  pt_add2(q[1], u.y << 16, u.y & 0xffff0000u);
+  pt_add2(q[2], u.z << 16, u.z & 0xffff0000u);
+  pt_add2(q[3], u.w << 16, u.w & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void pt_acc16<float>(unsigned long long (&q)[4], const uint4& u) {
+  pt_add2(q[0], u.x, u.y);
+  pt_add2(q[1], u.z, u.w);
+}
+#endif
+
 struct PoolTmaArgs {
   const void* x;
   void* out;
@@ -204,21 +238,21 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
       float part = 0.f;
       if (p * 32 + lane < nvec) {
         const uint4* a0 = sp + p * 32;
+#ifndef MG_HOST_EMULATION
+        unsigned long long q[4] = {0ull, 0ull, 0ull, 0ull};     // packed fp32 pair accumulators (independent chains)
         int r = 0;
         for (; r + kPtUnroll <= nr; r += kPtUnroll) {
           uint4 u[kPtUnroll];
 #pragma unroll
           for (int j = 0; j < kPtUnroll; ++j) u[j] = a0[(r + j) * rv];
-          float t[kPtUnroll];
 #pragma unroll
-          for (int j = 0; j < kPtUnroll; ++j) t[j] = pt_sum16<TX>(u[j]);
-#pragma unroll
-          for (int h = kPtUnroll / 2; h > 0; h >>= 1)
-#pragma unroll
-            for (int j = 0; j < h; ++j) t[j] += t[j + h];
-          part += t[0];
+          for (int j = 0; j < kPtUnroll; ++j) pt_acc16<TX>(q, u[j]);
         }
-        for (; r < nr; ++r) part += pt_sum16<TX>(a0[r * rv]);
+        for (; r < nr; ++r) pt_acc16<TX>(q, a0[r * rv]);
+        part = pt_fold2(q[0], q[1], q[2], q[3]);
+#else
+        for (int r = 0; r < nr; ++r) part += pt_sum16<TX>(a0[r * rv]);
+#endif
       }
 #pragma unroll
       for (int pp = 0; pp < kPtMaxPasses; ++pp)

@@ -28,7 +28,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .autograd import edge_weights_apply, feature_loss_apply, gat_layer_apply, ncut_loss_apply, softmax_rows, tv_loss_apply
+from .autograd import (edge_weights_apply, feature_loss_apply, gat_layer_apply, ncut_loss_apply, softmax_rows, stack_heads,
+                       tv_loss_apply)
 from .graph import Graph, register
 
 
@@ -84,8 +85,8 @@ def _layer_forward(heads: List[GraphAttentionLayer], x: torch.Tensor, edge_index
         W = heads[0].W.weight.unsqueeze(0)
         a = heads[0].a.weight.view(1, -1)
     else:
-        W = torch.stack([h.W.weight for h in heads], 0)
-        a = torch.stack([h.a.weight.view(-1) for h in heads], 0)
+        W = stack_heads([h.W.weight for h in heads], heads[0].W.weight.shape)
+        a = stack_heads([h.a.weight for h in heads], (heads[0].a.weight.numel(),))
     xp, Wp = _pad_in_dim(x, W)
     return gat_layer_apply(xp, g, Wp, a, concat, alpha, att_dropout, out_dtype)
 

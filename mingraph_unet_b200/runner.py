@@ -280,13 +280,23 @@ class CapturedTrainStep:
       block), issued eagerly on the same stream;
     * graph B: ``optimizer.step()`` (the optimizer must be built with ``capturable=True``).
 
+    ``dense_cotangent``: the gradient the downstream heads send back into the dense map ``F_g`` (a static ``(B,D,H,W)``
+    tensor the caller refreshes in place).  The backward is then seeded with it directly —
+    ``autograd.backward([out.f_g, loss_fn(out)], [dense_cotangent, 1])`` — instead of through a scalar formed from the
+    dense map, so the block's backward starts at the un-pool's backward scatter with no extra pass over the 134 MB map.
+
+    Gradient plumbing: every ``p.grad`` is dropped before the backward, so autograd hands over the (view of the stacked)
+    gradient it computed instead of launching one accumulate kernel per parameter; ONE multi-tensor copy then gathers
+    the 20 gradients into the flat buffer (the all-reduce payload), and ``p.grad`` is pointed at the flat views for the
+    optimizer.
+
     With a single rank (or ``allreduce=False``: this rank trains alone) A and B are recorded as one graph.  ``loss_fn`` maps a :class:`GraphBlockOutput` to a scalar and may
     close over other static tensors.  Attention-dropout masks differ from replay to replay (device-side seed addend) and
     are regenerated exactly by the backward of the same replay."""
 
     def __init__(self, block: GraphBlock, optimizer: torch.optim.Optimizer, example_feature_map: torch.Tensor,
                  image_size: Tuple[int, int], loss_fn, out_dtype: Optional[torch.dtype] = None, group=None, warmup: int = 3,
-                 allreduce: bool = True):
+                 allreduce: bool = True, dense_cotangent: Optional[torch.Tensor] = None):
         import torch.distributed as dist
         from . import ops
         from .autograd import advance_dropout_counter
@@ -298,19 +308,29 @@ class CapturedTrainStep:
         self.static_in = example_feature_map.clone()
         params = [p for p in block.parameters() if p.requires_grad]
         self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-        off = 0
+        flat_views, off = [], 0
         for p in params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            flat_views.append(self.flat_grad[off:off + p.numel()].view_as(p))
             off += p.numel()
         ph = block.patch_size
 
         def fwd_bwd():
             advance_dropout_counter(dev)
-            self.flat_grad.zero_()
+            for p in params:
+                p.grad = None                      # autograd then hands its gradient over instead of accumulating
             x = ops.pool_patches(self.static_in, ph, ph)
             out = block(node_features=x, image_size=image_size, out_dtype=out_dtype)
             loss = loss_fn(out)
-            loss.backward()
+            if dense_cotangent is not None:
+                torch.autograd.backward([out.f_g, loss], [dense_cotangent, torch.ones_like(loss)])
+            else:
+                loss.backward()
+            have = [i for i, p in enumerate(params) if p.grad is not None]
+            if len(have) != len(params):
+                self.flat_grad.zero_()             # (static decision: the same parameters get gradients in every replay)
+            torch._foreach_copy_([flat_views[i] for i in have], [params[i].grad for i in have])
+            for p, v in zip(params, flat_views):
+                p.grad = v
             return loss.detach()
 
         side = torch.cuda.Stream(device=dev)

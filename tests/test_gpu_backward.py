@@ -355,6 +355,26 @@ def test_captured_train_step_matches_eager(mg):
     assert losses_c == pytest.approx(losses_e, rel=2e-4, abs=1e-6)
     for pc, pe in zip(captured.parameters(), eager.parameters()):
         assert rel_err(pc, pe) <= 2e-3
+    # the same steps with the dense map's gradient handed over directly (dense_cotangent) instead of through a scalar
+    cot = make(0.0)
+    cot.load_state_dict({k: v.clone() for k, v in zip(eager.state_dict().keys(), [None] * 0)} or eager.state_dict())
+    with torch.no_grad():
+        for p, s0 in zip(cot.parameters(), start):
+            p.copy_(s0)
+    opt_k = torch.optim.Adam(cot.parameters(), lr=1e-2, capturable=True)
+    tr_k = mg.CapturedTrainStep(cot, opt_k, fm, (H, W), lambda out: out.l_partition.mean(), warmup=3, dense_cotangent=wd)
+    with torch.no_grad():
+        for p, s0 in zip(cot.parameters(), start):
+            p.copy_(s0)
+    for st in opt_k.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    for _ in range(3):
+        tr_k()
+    for pk, pe in zip(cot.parameters(), eager.parameters()):
+        assert rel_err(pk, pe) <= 2e-3
+    assert all(p.grad is not None and p.grad.data_ptr() >= tr_k.flat_grad.data_ptr() for p in cot.parameters())
     # dropout on: consecutive replays differ (fresh masks from the device-side counter)
     drop = make(0.3)
     opt_d = torch.optim.SGD(drop.parameters(), lr=0.0)
