@@ -67,54 +67,62 @@ __global__ void __launch_bounds__(256) gat_bwd_node_kernel(const BwdArgs A) {
   const int out_w = A.concat ? H * F : F;
   const float ginv = A.concat ? 1.f : 1.f / (float)H;
   const int ntiles = ceil_div(A.N, kBwdTile);
-  for (int h = 0; h < H; ++h) {
+  // grid (tiles, heads): heads are independent, so a small graph (the K-node region graphs of a training shard) still
+  // spreads over heads blocks instead of walking the heads one after the other in a single block
+  const int h = blockIdx.y;
+  for (int idx = threadIdx.x; idx < F * in_dim; idx += blockDim.x) {
+    const int f = idx / in_dim, i = idx - f * in_dim;
+    Ws[f * (in_dim + 1) + i] = __ldg(A.W + (size_t)h * F * in_dim + idx);
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int nb = tile * kBwdTile;
+    const int tn = min(kBwdTile, A.N - nb);           // only the tile's real nodes are worked on
     __syncthreads();
-    for (int idx = threadIdx.x; idx < F * in_dim; idx += blockDim.x) {
-      const int f = idx / in_dim, i = idx - f * in_dim;
-      Ws[f * (in_dim + 1) + i] = __ldg(A.W + (size_t)h * F * in_dim + idx);
+    for (int idx = threadIdx.x; idx < tn * in_dim; idx += blockDim.x) {
+      const int q = idx / in_dim, i = idx - q * in_dim;
+      Zs[q * (in_dim + 1) + i] = __ldg(A.z + ((size_t)(nb + q) * H + h) * in_dim + i);
     }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int nb = tile * kBwdTile;
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < kBwdTile * in_dim; idx += blockDim.x) {
-        const int q = idx / in_dim, i = idx - q * in_dim;
-        const int n = nb + q;
-        Zs[q * (in_dim + 1) + i] = n < A.N ? __ldg(A.z + ((size_t)n * H + h) * in_dim + i) : 0.f;
+    __syncthreads();
+    // y and g_y: thread per (node, f)
+    for (int idx = threadIdx.x; idx < tn * F; idx += blockDim.x) {
+      const int q = idx / F, f = idx - q * F;
+      const int n = nb + q;
+      float y0 = 0.f, y1 = 0.f;
+      int i = 0;
+      for (; i + 1 < in_dim; i += 2) {
+        y0 = fmaf(Zs[q * (in_dim + 1) + i], Ws[f * (in_dim + 1) + i], y0);
+        y1 = fmaf(Zs[q * (in_dim + 1) + i + 1], Ws[f * (in_dim + 1) + i + 1], y1);
       }
-      __syncthreads();
-      // y and g_y: thread per (node, f)
-      for (int idx = threadIdx.x; idx < kBwdTile * F; idx += blockDim.x) {
-        const int q = idx / F, f = idx - q * F;
-        const int n = nb + q;
-        float y = 0.f;
-        for (int i = 0; i < in_dim; ++i) y = fmaf(Zs[q * (in_dim + 1) + i], Ws[f * (in_dim + 1) + i], y);
-        float g = 0.f;
-        if (n < A.N) {
-          const float go = __ldg(A.gout + (size_t)n * out_w + (A.concat ? h * F : 0) + f) * ginv;
-          g = y > 0.f ? go : go * expf(y);                                         // ELU'(y) = exp(y) for y <= 0
-          A.gy[((size_t)n * H + h) * F + f] = g;
-        }
-        Gy[q * (F + 1) + f] = g;
+      if (i < in_dim) y0 = fmaf(Zs[q * (in_dim + 1) + i], Ws[f * (in_dim + 1) + i], y0);
+      const float y = y0 + y1;
+      const float go = __ldg(A.gout + (size_t)n * out_w + (A.concat ? h * F : 0) + f) * ginv;
+      const float g = y > 0.f ? go : go * expf(y);                                 // ELU'(y) = exp(y) for y <= 0
+      A.gy[((size_t)n * H + h) * F + f] = g;
+      Gy[q * (F + 1) + f] = g;
+    }
+    __syncthreads();
+    // g_z: thread per (node, i)
+    for (int idx = threadIdx.x; idx < tn * in_dim; idx += blockDim.x) {
+      const int q = idx / in_dim, i = idx - q * in_dim;
+      float g0 = 0.f, g1 = 0.f;
+      int f = 0;
+      for (; f + 1 < F; f += 2) {
+        g0 = fmaf(Gy[q * (F + 1) + f], Ws[f * (in_dim + 1) + i], g0);
+        g1 = fmaf(Gy[q * (F + 1) + f + 1], Ws[(f + 1) * (in_dim + 1) + i], g1);
       }
-      __syncthreads();
-      // g_z: thread per (node, i)
-      for (int idx = threadIdx.x; idx < kBwdTile * in_dim; idx += blockDim.x) {
-        const int q = idx / in_dim, i = idx - q * in_dim;
-        const int n = nb + q;
-        float g = 0.f;
-        for (int f = 0; f < F; ++f) g = fmaf(Gy[q * (F + 1) + f], Ws[f * (in_dim + 1) + i], g);
-        if (n < A.N) A.gz[((size_t)n * H + h) * in_dim + i] = g;
-        Zs[q * (in_dim + 1) + i] *= g;                                             // z_i * g_z_i, reduced below
-      }
-      __syncthreads();
-      // c = sum_i z_i g_z_i : one warp per node (fixed order)
-      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      for (int q = warp; q < kBwdTile; q += blockDim.x >> 5) {
-        float acc = 0.f;
-        for (int i = lane; i < in_dim; i += 32) acc += Zs[q * (in_dim + 1) + i];
-        acc = warp_sum(acc);
-        if (lane == 0 && nb + q < A.N) A.c[(size_t)(nb + q) * H + h] = acc;
-      }
+      if (f < F) g0 = fmaf(Gy[q * (F + 1) + f], Ws[f * (in_dim + 1) + i], g0);
+      const float g = g0 + g1;
+      A.gz[((size_t)(nb + q) * H + h) * in_dim + i] = g;
+      Zs[q * (in_dim + 1) + i] *= g;                                               // z_i * g_z_i, reduced below
+    }
+    __syncthreads();
+    // c = sum_i z_i g_z_i : one warp per node (fixed order)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = warp; q < tn; q += blockDim.x >> 5) {
+      float acc = 0.f;
+      for (int i = lane; i < in_dim; i += 32) acc += Zs[q * (in_dim + 1) + i];
+      acc = warp_sum(acc);
+      if (lane == 0) A.c[(size_t)(nb + q) * H + h] = acc;
     }
   }
 }
@@ -278,6 +286,7 @@ __global__ void __launch_bounds__(256) gat_bwd_u_kernel(const BwdArgs A) {
   for (int idx = threadIdx.x; idx < twoH * in_dim; idx += blockDim.x) {
     const int q = idx / in_dim, i = idx - q * in_dim;
     float acc = 0.f;
+#pragma unroll 8
     for (int n = nbeg; n < nend; ++n) acc = fmaf(__ldg(A.gs + (size_t)n * twoH + q), to_f32<TX>(x[(size_t)n * in_dim + i]), acc);
     A.partU[((size_t)sp * twoH + q) * in_dim + i] = acc;
   }
@@ -414,7 +423,7 @@ int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in, const 
                                const_cast<float*>(A.s), const_cast<float*>(A.gmax), const_cast<float*>(A.u), st)))
     return rc;
   if (node_smem > 48 * 1024) cudaFuncSetAttribute(gat_bwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int node_grid = std::min(ceil_div(N, kBwdTile), num_sms() * 2);
+  const dim3 node_grid((unsigned)std::min(ceil_div(N, kBwdTile), num_sms() * 2), (unsigned)heads);
   gat_bwd_node_kernel<<<node_grid, 256, node_smem, st>>>(A);
   if ((rc = check_launch("gat_bwd_node_kernel"))) return rc;
   dim3 wgrid(ceil_div(out_dim, kWT) * ceil_div(in_dim, kWT), heads, L.splits);
