@@ -526,7 +526,7 @@ def train_leg(ctx, B, steps, warmup, distributed=True, sampler=None, e2e=False):
     N = nph * npw
     E = 2 * (nph * (npw - 1) + npw * (nph - 1))
     blk = make_block(dev, train=True)          # dropout 0.1 on, as the reference trains (configs/model.yaml)
-    opt = torch.optim.Adam(blk.parameters(), lr=1e-4, capturable=True)
+    opt = torch.optim.Adam(blk.parameters(), lr=1e-4, capturable=True, fused=True)   # one multi-tensor kernel (the foreach path is 56 launches)
     gen = torch.Generator().manual_seed(1000 + ctx.rank)
     fm_host = torch.randn(B, IN_DIM, H, W, generator=gen).to(dtype).pin_memory()
     fm_dev = fm_host.to(dev)

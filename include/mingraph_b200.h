@@ -141,6 +141,8 @@ MG_API int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in,
                     const float* W, const float* a, int in_dim, int out_dim, int heads, int concat, float slope,
                     int nodes_per_graph, float dropout_p, uint64_t seed, const uint64_t* seed_dev, const float* den,
                     const float* z, const float* grad_out, float* grad_x, float* grad_W, float* grad_a, void* work,
+                    const void* fwd_work /* nullable: the work buffer mg_gat_forward used for the same call (its
+                                            attention scalars are then reused instead of recomputed) */,
                     mg_stream_t stream);
 
 /* Row softmax + argmax of the predictor logits — mincut_refinement.py:193 and

@@ -51,7 +51,7 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_edge_slot_map": (_i, [_p, _p, _i64, _p, _p, _p]),
     "mg_gat_backward_work_bytes": (_i64, [_i, _i64, _i, _i, _i, _i]),
     "mg_gat_backward": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i64, _p, _p, _i, _i, _i, _i, _f, _i, _f, C.c_uint64, _p,
-                             _p, _p, _p, _p, _p, _p, _p, _p]),
+                             _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mg_softmax_argmax": (_i, [_p, _i, _i, _p, _p, _p]),
     "mg_ncut_edge_weights": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
     "mg_ncut_work_bytes": (_i64, [_i, _i, _i]),

@@ -60,21 +60,21 @@ class _GATLayerFn(torch.autograd.Function):
     def forward(ctx, x, W, a, g: Graph, concat: bool, slope: float, att_dropout: float, out_dtype=None):
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if att_dropout > 0.0 else 0     # CPU generator: no device sync
         seed_dev = dropout_counter(x.device) if att_dropout > 0.0 else None
-        out, den, z = ops.gat_forward(x, g.rowptr_in, g.col_in, W, a, concat=concat, slope=slope,
-                                      nodes_per_graph=g.nodes_per_graph, save=True, dropout_p=att_dropout, seed=seed,
-                                      out_dtype=out_dtype, seed_dev=seed_dev)
-        ctx.save_for_backward(x, W, a, den, z)
+        out, den, z, work = ops.gat_forward(x, g.rowptr_in, g.col_in, W, a, concat=concat, slope=slope,
+                                            nodes_per_graph=g.nodes_per_graph, save=True, dropout_p=att_dropout, seed=seed,
+                                            out_dtype=out_dtype, seed_dev=seed_dev)
+        ctx.save_for_backward(x, W, a, den, z, work)       # work: the forward's attention scalars, reused by the backward
         ctx.g, ctx.concat, ctx.slope, ctx.p, ctx.seed, ctx.seed_dev = g, concat, slope, att_dropout, seed, seed_dev
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, W, a, den, z = ctx.saved_tensors
+        x, W, a, den, z, work = ctx.saved_tensors
         g = ctx.g
         g.need_backward_maps()
         gx, gW, ga = ops.gat_backward(x, g.rowptr_in, g.col_in, g.rowptr_out, g.col_out, g.slot_out2in, W, a, den, z,
                                       grad_out, concat=ctx.concat, slope=ctx.slope, nodes_per_graph=g.nodes_per_graph,
-                                      dropout_p=ctx.p, seed=ctx.seed, seed_dev=ctx.seed_dev)
+                                      dropout_p=ctx.p, seed=ctx.seed, seed_dev=ctx.seed_dev, fwd_work=work)
         return gx.to(x.dtype), gW.to(W.dtype), ga.to(a.dtype), None, None, None, None, None
 
 

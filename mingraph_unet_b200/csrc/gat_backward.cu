@@ -285,10 +285,16 @@ __global__ void __launch_bounds__(256) gat_bwd_u_kernel(const BwdArgs A) {
   const int nbeg = sp * chunk, nend = min(A.N, nbeg + chunk);
   for (int idx = threadIdx.x; idx < twoH * in_dim; idx += blockDim.x) {
     const int q = idx / in_dim, i = idx - q * in_dim;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int n = nbeg; n < nend; ++n) acc = fmaf(__ldg(A.gs + (size_t)n * twoH + q), to_f32<TX>(x[(size_t)n * in_dim + i]), acc);
-    A.partU[((size_t)sp * twoH + q) * in_dim + i] = acc;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;      // independent chains: the loads of four nodes are in flight together
+    int n = nbeg;
+    for (; n + 3 < nend; n += 4) {
+      acc0 = fmaf(__ldg(A.gs + (size_t)n * twoH + q), to_f32<TX>(x[(size_t)n * in_dim + i]), acc0);
+      acc1 = fmaf(__ldg(A.gs + (size_t)(n + 1) * twoH + q), to_f32<TX>(x[(size_t)(n + 1) * in_dim + i]), acc1);
+      acc2 = fmaf(__ldg(A.gs + (size_t)(n + 2) * twoH + q), to_f32<TX>(x[(size_t)(n + 2) * in_dim + i]), acc2);
+      acc3 = fmaf(__ldg(A.gs + (size_t)(n + 3) * twoH + q), to_f32<TX>(x[(size_t)(n + 3) * in_dim + i]), acc3);
+    }
+    for (; n < nend; ++n) acc0 = fmaf(__ldg(A.gs + (size_t)n * twoH + q), to_f32<TX>(x[(size_t)n * in_dim + i]), acc0);
+    A.partU[((size_t)sp * twoH + q) * in_dim + i] = (acc0 + acc1) + (acc2 + acc3);
   }
 }
 
@@ -339,7 +345,7 @@ struct BwdLayout { size_t s, gmax, u, gy, gz, c, ea, eg, gs, gmpart, gM, partW, 
 static BwdLayout bwd_layout(int N, int64_t E, int in_dim, int F, int heads, int G) {
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   BwdLayout L;
-  L.splits = std::max(1, std::min(kMaxSplits, ceil_div(N, 256)));
+  L.splits = std::max(1, std::min(kMaxSplits, ceil_div(N, 64)));      // 64-node chunks: enough blocks for a 4096-node shard
   size_t o = 0;
   L.s = o;     o = al(o + (size_t)N * 2 * heads * 4);
   L.gmax = o;  o = al(o + (size_t)G * heads * 4);
@@ -386,7 +392,7 @@ int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in, const 
                     const int32_t* col_out, const int32_t* slot_out2in, int N, int64_t E, const float* W, const float* a,
                     int in_dim, int out_dim, int heads, int concat, float slope, int nodes_per_graph, float dropout_p,
                     uint64_t seed, const uint64_t* seed_dev, const float* den, const float* z, const float* grad_out, float* grad_x, float* grad_W,
-                    float* grad_a, void* work, mg_stream_t stream) {
+                    float* grad_a, void* work, const void* fwd_work, mg_stream_t stream) {
   MG_REQUIRE(x && rowptr_in && col_in && rowptr_out && col_out && slot_out2in && W && a && den && z && grad_out && grad_x &&
                  grad_W && grad_a && work,
              MG_ERR_INVALID, "mg_gat_backward: null pointer");
@@ -403,9 +409,12 @@ int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in, const 
   cudaStream_t st = (cudaStream_t)stream;
   BwdArgs A;
   A.x = x; A.W = W; A.a = a; A.den = den; A.z = z; A.gout = grad_out;
-  A.u = reinterpret_cast<float*>(wb + L.u);
-  A.s = reinterpret_cast<float*>(wb + L.s);
-  A.gmax = reinterpret_cast<float*>(wb + L.gmax);
+  // attention scalars, per-graph maxima and u = W^T a: recomputed here, or taken from the forward's workspace of the same
+  // layer call (mg_gat_forward's work buffer starts with the same three segments: saves three launches per layer)
+  const unsigned char* sb = fwd_work ? reinterpret_cast<const unsigned char*>(fwd_work) : wb;
+  A.u = reinterpret_cast<float*>(const_cast<unsigned char*>(sb) + L.u);
+  A.s = reinterpret_cast<float*>(const_cast<unsigned char*>(sb) + L.s);
+  A.gmax = reinterpret_cast<float*>(const_cast<unsigned char*>(sb) + L.gmax);
   A.rowptr_in = rowptr_in; A.col_in = col_in; A.rowptr_out = rowptr_out; A.col_out = col_out; A.slot_out2in = slot_out2in;
   A.gy = reinterpret_cast<float*>(wb + L.gy); A.gz = reinterpret_cast<float*>(wb + L.gz);
   A.c = reinterpret_cast<float*>(wb + L.c); A.ea = reinterpret_cast<float*>(wb + L.ea);
@@ -419,7 +428,8 @@ int mg_gat_backward(const void* x, int x_dtype, const int32_t* rowptr_in, const 
   float* gu = reinterpret_cast<float*>(wb + L.gu);
   int rc;
   // recompute the attention scalars and the per-graph shift (cheaper than saving them)
-  if ((rc = gat_scores_and_max(x, x_dtype, rowptr_in, col_in, N, W, a, in_dim, out_dim, heads, nodes_per_graph,
+  if (!fwd_work &&
+      (rc = gat_scores_and_max(x, x_dtype, rowptr_in, col_in, N, W, a, in_dim, out_dim, heads, nodes_per_graph,
                                const_cast<float*>(A.s), const_cast<float*>(A.gmax), const_cast<float*>(A.u), st)))
     return rc;
   if (node_smem > 48 * 1024) cudaFuncSetAttribute(gat_bwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

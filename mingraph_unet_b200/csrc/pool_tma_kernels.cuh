@@ -248,6 +248,14 @@ __global__ void __launch_bounds__(kPtWarps * 32, 1) pool_patches_tma_kernel(cons
 #pragma unroll
           for (int j = 0; j < kPtUnroll; ++j) pt_acc16<TX>(q, u[j]);
         }
+        if (r + 4 <= nr) {                                      // chunks of 4 rows (2 KB rows: 1024-wide bf16 maps)
+          uint4 u[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) u[j] = a0[(r + j) * rv];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pt_acc16<TX>(q, u[j]);
+          r += 4;
+        }
         for (; r < nr; ++r) pt_acc16<TX>(q, a0[r * rv]);
         part = pt_fold2(q[0], q[1], q[2], q[3]);
 #else

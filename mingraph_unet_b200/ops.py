@@ -206,7 +206,8 @@ def gat_forward(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, W: tor
                 out_dtype: Optional[torch.dtype] = None, save: bool = False, dropout_p: float = 0.0, seed: int = 0,
                 seed_dev: Optional[torch.Tensor] = None):
     """Multi-head GAT layer forward (eval semantics).  ``x (N,in)`` f32|bf16, ``W (H,F,in)``,
-    ``a (H,2F)`` f32, in-CSR ``rowptr/col`` int32.  Returns ``out`` or ``(out, den, z)`` if ``save``."""
+    ``a (H,2F)`` f32, in-CSR ``rowptr/col`` int32.  Returns ``out`` or ``(out, den, z, work)`` if ``save`` (``work``: the
+    call's workspace, whose attention scalars ``gat_backward(fwd_work=...)`` reuses)."""
     _need_cuda(x, rowptr, col, W, a)
     if x.dim() != 2 or W.dim() != 3 or a.dim() != 2:
         raise ValueError("gat_forward expects x (N,in), W (H,F,in), a (H,2F)")
@@ -233,7 +234,7 @@ def gat_forward(x: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, W: tor
              W.data_ptr(), a.data_ptr(), in_dim, F, heads, int(concat), float(slope), int(nodes_per_graph),
              float(dropout_p), int(seed), _ptr(seed_dev), out.data_ptr(), _dtype_code(out_dtype), work.data_ptr(), _ptr(den),
              _ptr(z), _stream())
-    return (out, den, z) if save else out
+    return (out, den, z, work) if save else out
 
 
 def edge_slot_map(eid_in: torch.Tensor, eid_out: torch.Tensor) -> torch.Tensor:
@@ -249,8 +250,9 @@ def edge_slot_map(eid_in: torch.Tensor, eid_out: torch.Tensor) -> torch.Tensor:
 
 def gat_backward(x, rowptr_in, col_in, rowptr_out, col_out, slot_out2in, W, a, den, z, grad_out, concat: bool = False,
                  slope: float = 0.2, nodes_per_graph: int = 0, dropout_p: float = 0.0, seed: int = 0,
-                 seed_dev: Optional[torch.Tensor] = None):
-    """Backward of ``gat_forward``: returns ``grad_x (N,in) f32, grad_W (H,F,in), grad_a (H,2F)``."""
+                 seed_dev: Optional[torch.Tensor] = None, fwd_work: Optional[torch.Tensor] = None):
+    """Backward of ``gat_forward``: returns ``grad_x (N,in) f32, grad_W (H,F,in), grad_a (H,2F)``.  ``fwd_work``: the
+    forward call's workspace (``gat_forward(save=True)``): its scores / maxima are reused (3 launches fewer)."""
     _need_cuda(x, W, a, den, z, grad_out)
     N, in_dim = x.shape
     heads, F, _ = W.shape
@@ -270,7 +272,8 @@ def gat_backward(x, rowptr_in, col_in, rowptr_out, col_out, slot_out2in, W, a, d
         call("mg_gat_backward", x.data_ptr(), _dtype_code(x.dtype), rowptr_in.data_ptr(), col_in.data_ptr(),
              rowptr_out.data_ptr(), col_out.data_ptr(), slot_out2in.data_ptr(), N, E, W.data_ptr(), a.data_ptr(), in_dim, F,
              heads, int(concat), float(slope), int(nodes_per_graph), float(dropout_p), int(seed), _ptr(seed_dev), den.data_ptr(),
-             z.data_ptr(), grad_out.data_ptr(), gx.data_ptr(), gW.data_ptr(), ga.data_ptr(), work.data_ptr(), _stream())
+             z.data_ptr(), grad_out.data_ptr(), gx.data_ptr(), gW.data_ptr(), ga.data_ptr(), work.data_ptr(), _ptr(fwd_work),
+             _stream())
     return gx, gW, ga
 
 
