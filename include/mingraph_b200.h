@@ -288,6 +288,23 @@ MG_API int mg_block_forward_push(const void* x, int x_dtype, int B, int Hp, int 
                                  int H3, int K, float slope1, float slope2, float slope3, const float* prep, float* h,
                                  float* q_work, float* S, int32_t* labels, float* loss, float* region_in,
                                  float* region_out, const mg_peer_out_t* peer, mg_stream_t stream);
+/* mg_block_forward_ex: mg_block_forward_push plus FeatureConsistencyLoss folded into the kernel (scope row f4 — the loss
+ * of model/unet/feature_loss.py:103-123 between the U-Net patch features and the patch-GAT output h, evaluated while
+ * the rows of h are still in registers: no second pass over h).  floss (nullable): f_unet (B,N,D) f32, y (B,N) f32
+ * patch labels, margin; loss_per_image (B) receives the per-image sums over the patches (the reference's value is
+ * their batch mean, :124). */
+typedef struct mg_block_feature_loss {
+  const float* f_unet;
+  const float* y;
+  float margin;
+  float* loss_per_image;
+} mg_block_feature_loss_t;
+
+MG_API int mg_block_forward_ex(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3,
+                               int K, float slope1, float slope2, float slope3, const float* prep, float* h,
+                               float* q_work, float* S, int32_t* labels, float* loss, float* region_in,
+                               float* region_out, const mg_peer_out_t* peer, const mg_block_feature_loss_t* floss,
+                               mg_stream_t stream);
 MG_API int mg_peer_wait(const uint32_t* my_flags, int64_t first_flag, int world, const uint32_t* seq, int32_t* status,
                         mg_stream_t stream);
 MG_API int mg_peer_mem_alloc(int64_t nbytes, void** ptr_host, unsigned char* handle64_host);

@@ -74,6 +74,7 @@ PROTOTYPES: Dict[str, tuple] = {
     "mg_tv_loss_backward": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
     "mg_region_map_gather": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i64, _p]),
     "mg_block_forward_push": (_i, [_p] + [_i] * 10 + [_f] * 3 + [_p] * 10),
+    "mg_block_forward_ex": (_i, [_p] + [_i] * 10 + [_f] * 3 + [_p] * 11),
     "mg_peer_wait": (_i, [_p, _i64, _i, _p, _p, _p]),
     "mg_peer_mem_alloc": (_i, [_i64, _p, _p]),
     "mg_peer_mem_open": (_i, [_p, _p]),
@@ -87,6 +88,11 @@ class PeerOut(C.Structure):
     """``mg_peer_out_t`` of the header: one (pipeline slot, rank) of the fused peer exchange."""
     _fields_ = [("peer_bufs_dev", _p), ("peer_flags_dev", _p), ("world", C.c_int32), ("rank", C.c_int32),
                 ("slice_offset", _i64), ("parity_stride", _i64), ("flag_index", _i64), ("seq", _p), ("done", _p)]
+
+
+class BlockFeatureLoss(C.Structure):
+    """``mg_block_feature_loss_t`` of the header."""
+    _fields_ = [("f_unet", _p), ("y", _p), ("margin", C.c_float), ("loss_per_image", _p)]
 
 
 _lib = None

@@ -71,12 +71,16 @@ class GraphBlock(nn.Module):
         feature-consistency loss between them and the patch-GAT output (train_end_to_end.py:344,
         batch mean of the per-image sums).  ``_peer``: a ``distributed.PeerExchange.slot(i)`` descriptor — the block
         kernel then also pushes the small outputs to every rank (multi-GPU exchange fused into the launch)."""
-        res = self._forward(node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs, _after_block,
-                            _peer)
-        if f_unet_patches is None:
-            return res
-        if patch_labels_y is None:
+        if f_unet_patches is not None and patch_labels_y is None:
             raise ValueError("patch_labels_y is required with f_unet_patches")
+        fl_in = None
+        if f_unet_patches is not None and f_unet_patches.dtype == torch.float32 and f_unet_patches.is_cuda \
+                and not (torch.is_grad_enabled() and f_unet_patches.requires_grad):
+            fl_in = (f_unet_patches, patch_labels_y, float(feature_loss_margin))     # folded into the block kernel when it runs
+        res = self._forward(node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs, _after_block,
+                            _peer, fl_in)
+        if f_unet_patches is None or res.l_feature is not None:
+            return res
         if tuple(f_unet_patches.shape) != tuple(res.patch_features.shape):
             raise ValueError(f"f_unet ({f_unet_patches.shape}) and f_graph ({res.patch_features.shape}) must have "
                              f"same dimensions for this loss version.")
@@ -84,7 +88,7 @@ class GraphBlock(nn.Module):
                                                          float(feature_loss_margin)))
 
     def _forward(self, node_features, image_size, feature_map, out, out_dtype, want_dense, _block_outs,
-                 _after_block=None, _peer=None) -> GraphBlockOutput:
+                 _after_block=None, _peer=None, _feature_loss=None) -> GraphBlockOutput:
         if (node_features is None) == (feature_map is None):
             raise ValueError("pass exactly one of node_features / feature_map")
         if feature_map is not None:
@@ -128,9 +132,17 @@ class GraphBlock(nn.Module):
                                "use distributed.InlineGather otherwise")
         if use_fused:
             # ONE launch: patch GAT -> predictor GAT -> softmax/argmax -> N-cut -> region pool -> region GAT
-            h, S, labels, loss, _, G = ops.block_forward(
+            l_feature = None
+            if _feature_loss is not None and tuple(_feature_loss[0].shape) != (B, N, D):
+                raise ValueError(f"f_unet ({_feature_loss[0].shape}) and f_graph ({(B, N, D)}) must have "
+                                 f"same dimensions for this loss version.")
+            r = ops.block_forward(
                 node_features, nph, npw, self._prepared(), D, layers[0].num_heads, layers[1].num_heads,
-                layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers), outs=_block_outs, peer=_peer)
+                layers[2].num_heads, K, slopes=tuple(l.alpha for l in layers), outs=_block_outs, peer=_peer,
+                feature_loss=_feature_loss)
+            h, S, labels, loss, _, G = r[:6]
+            if _feature_loss is not None:
+                l_feature = r[6].mean()                 # batch mean of the per-image sums (feature_loss.py:124)
             if _after_block is not None:
                 _after_block()          # the small outputs are final here; the un-pool below only reads them
         elif needs_autograd or (self.training and any(l.dropout_rate > 0 for l in layers)):
@@ -166,7 +178,7 @@ class GraphBlock(nn.Module):
         f_g = None
         if want_dense:                                                                  # :403-421
             f_g = ops.unpool_nearest(G, labels, nph, npw, H, W, out=out, out_dtype=dense_dtype)
-        return GraphBlockOutput(f_g, loss, S, labels, h, G, (nph, npw))
+        return GraphBlockOutput(f_g, loss, S, labels, h, G, (nph, npw), l_feature if use_fused else None)
 
     def __setattr__(self, name, value):
         if isinstance(value, (nn.Module, nn.Parameter)):

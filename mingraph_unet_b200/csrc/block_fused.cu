@@ -62,7 +62,7 @@ __host__ __device__ inline PrepLayout prep_layout(const BlockShape& s) {
 
 // shared-memory layout of the main kernel (float offsets)
 struct SmemLayout {
-  int prepA, prepB, s1, alpha, zs, tmp, wts, deg, S, lab, red, cmax1, cmax2, exp_part, exp_rsum, exp_rcnt, region, total;
+  int prepA, prepB, s1, alpha, zs, tmp, wts, deg, S, lab, red, cmax1, cmax2, exp_part, exp_rsum, exp_rcnt, exp_fl, region, total;
 };
 __host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ inline SmemLayout smem_layout(const BlockShape& s) {
@@ -85,6 +85,7 @@ __host__ __device__ inline SmemLayout smem_layout(const BlockShape& s) {
   L.exp_part = o; o += round_up4(2 * s.K);
   L.exp_rsum = o; o += s.K * s.D;
   L.exp_rcnt = o; o += round_up4(s.K);
+  L.exp_fl = o;   o += 4;                        // this CTA's feature-consistency loss partial
   // rank-0 scratch of the region stage: R [K][D], s3 [K][2H3], a3 [K][H3][K], z3 [K][H3][D], y3 [K][H3][D]
   L.region = o;   o += s.K * s.D + round_up4(s.K * 2 * s.H3) + round_up4(s.K * s.H3 * s.K) + 2 * s.K * s.H3 * s.D;
   L.total = o;
@@ -118,6 +119,11 @@ struct BlockArgs {
   float* loss;              // (B)
   float* region_in;         // (B, K, D) or null
   float* region_out;        // (B, K, D)
+  // FeatureConsistencyLoss folded into the patch-GAT epilogue (model/unet/feature_loss.py:103-123): null = off
+  const float* fl_unet;     // (B, N, D) f32  U-Net patch features
+  const float* fl_y;        // (B, N)    f32  patch labels
+  float fl_margin;
+  float* fl_out;            // (B)       per-image sums over the patches
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -484,7 +490,9 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
     __syncthreads();
     // (c) h = mean_h ELU(W_h z_h); 4 nodes x 4 features per item; then the predictor scalars
     //     q[n][v] = h_n . vec_v  (vec = u2 rows, W2 rows) reduced over the FG lanes of a node quad
-    const int items = (kTileN / 4) * FG;
+    // node quads that hold real rows (a short last tile costs what it holds), rounded up to whole warps: the
+    // reduce-scatter below shuffles with the full mask, so a warp enters the loop with all its lanes or not at all
+    const int items = ((((tn + 3) / 4) * FG + 31) / 32) * 32;
     const float inv_h = 1.f / (float)H1;
     for (int it = tid; it < items; it += kBT) {
       const int ng = it / FG, fg = it - ng * FG;
@@ -531,6 +539,34 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
         for (int c = 0; c < 4; ++c) o[r][c] *= inv_h;
         if (q0 + r < tn)
           *reinterpret_cast<float4*>(A.h + (gb + n0 + tile + q0 + r) * D + f0) = make_float4(o[r][0], o[r][1], o[r][2], o[r][3]);
+      }
+      // feature-consistency loss (feature_loss.py:103-123) on the rows while they are in registers: squared distance
+      // to the U-Net patch features over the quad's FG lanes, then the per-patch contrastive term
+      if (A.fl_unet) {
+        float d2[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          d2[r] = 0.f;
+          if (q0 + r < tn) {
+            const float4 fu = __ldg(reinterpret_cast<const float4*>(A.fl_unet + (gb + n0 + tile + q0 + r) * D + f0));
+            const float e0 = fu.x - o[r][0], e1 = fu.y - o[r][1], e2 = fu.z - o[r][2], e3 = fu.w - o[r][3];
+            d2[r] = (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+          }
+        }
+        for (int off = FG >> 1; off > 0; off >>= 1) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) d2[r] += __shfl_xor_sync(kFull, d2[r], off);
+        }
+        if (fg == 0) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            if (q0 + r < tn) {
+              const float y = __ldg(A.fl_y + gb + n0 + tile + q0 + r);
+              const float hinge = fmaxf(A.fl_margin - sqrtf(d2[r] + 1e-8f), 0.f);                 // :116-118
+              deg[tile + q0 + r] = y * d2[r] + (1.f - y) * (hinge * hinge);                        // :110,119 (deg is free until P3)
+            }
+          }
+        }
       }
       // predictor scalars: 8 vectors x 4 nodes = 32 partial dot products per lane, summed over the node quad's
       // FG lanes with a reduce-scatter (30 shuffles instead of 128)
@@ -585,6 +621,12 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
       }
     }
     __syncthreads();
+  }
+  if (A.fl_unet && tid < 32) {                            // this CTA's patches, fixed order: strided per lane, then the shuffle tree
+    float acc = 0.f;
+    for (int t = lane; t < cnt; t += 32) acc += deg[t];
+    acc = warp_sum(acc);
+    if (lane == 0) (sm + L.exp_fl)[0] = acc;
   }
   cluster.sync();                                                                   // #2: h, q visible
 
@@ -800,6 +842,11 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
       }
       A.loss[b] = l;
       for (int p = 0; p < po.world; ++p) peer_slice(po, p, seq_now & 1u)[b] = l;
+      if (A.fl_out) {                                     // per-image sum over the patches, CTAs in rank order
+        float fl = 0.f;
+        for (int r = 0; r < s.cluster; ++r) fl += cluster.map_shared_rank(sm + L.exp_fl, r)[0];
+        A.fl_out[b] = fl;
+      }
     }
     for (int idx = tid; idx < K * D; idx += kBT) {
       const int c = idx / D;
@@ -947,7 +994,7 @@ static int plan_cluster(BlockShape* s) {
   // experiment / tuning override: MG_BLOCK_CLUSTER = 1, 2, 4 or 8 CTAs per image (fewer CTAs leave SMs to the HBM-bound
   // kernels of the neighbouring pipeline step)
   static const int forced = getenv("MG_BLOCK_CLUSTER") ? atoi(getenv("MG_BLOCK_CLUSTER")) : 0;
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
+  if (forced >= 1 && forced <= kMaxCluster) {
     s->cluster = forced;
     s->npc = ceil_div(s->N, forced);
     return forced;
@@ -1015,10 +1062,10 @@ int mg_block_prepare(const float* W1, const float* a1, const float* W2, const fl
   return check_launch("block_prepare_kernel");
 }
 
-int mg_block_forward_push(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K,
-                          float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work, float* S,
-                          int32_t* labels, float* loss, float* region_in, float* region_out, const mg_peer_out_t* peer,
-                          mg_stream_t stream) {
+int mg_block_forward_ex(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K,
+                        float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work, float* S,
+                        int32_t* labels, float* loss, float* region_in, float* region_out, const mg_peer_out_t* peer,
+                        const mg_block_feature_loss_t* floss, mg_stream_t stream) {
   MG_REQUIRE(x && prep && h && q_work && S && labels && loss && region_out, MG_ERR_INVALID, "mg_block_forward: null pointer");
   MG_REQUIRE(B > 0 && Hp > 0 && Wp > 0, MG_ERR_INVALID, "mg_block_forward: bad sizes");
   MG_REQUIRE(x_dtype == MG_F32 || x_dtype == MG_BF16, MG_ERR_INVALID, "mg_block_forward: x dtype");
@@ -1036,12 +1083,18 @@ int mg_block_forward_push(const void* x, int x_dtype, int B, int Hp, int Wp, int
   BlockArgs A;
   A.s = s; A.x = x; A.prep = prep; A.h = h; A.q = q_work; A.S = S; A.labels = labels; A.loss = loss;
   A.region_in = region_in; A.region_out = region_out;
+  A.fl_unet = nullptr; A.fl_y = nullptr; A.fl_out = nullptr; A.fl_margin = 0.f;
+  if (floss) {
+    MG_REQUIRE(floss->f_unet && floss->y && floss->loss_per_image, MG_ERR_INVALID, "mg_block_forward_ex: bad feature-loss descriptor");
+    MG_REQUIRE((uintptr_t)floss->f_unet % 16 == 0, MG_ERR_INVALID, "mg_block_forward_ex: f_unet must be 16-byte aligned");
+    A.fl_unet = floss->f_unet; A.fl_y = floss->y; A.fl_margin = floss->margin; A.fl_out = floss->loss_per_image;
+  }
   A.peer.world = 0;
   if (peer) {
     MG_REQUIRE(peer->peer_bufs_dev && peer->peer_flags_dev && peer->seq && peer->done && peer->world > 0 && peer->world <= 64,
-               MG_ERR_INVALID, "mg_block_forward_push: bad peer descriptor");
+               MG_ERR_INVALID, "mg_block_forward_ex: bad peer descriptor");
     MG_REQUIRE(peer->slice_offset >= 0 && peer->parity_stride >= 0 && peer->flag_index >= 0, MG_ERR_INVALID,
-               "mg_block_forward_push: negative peer offsets");
+               "mg_block_forward_ex: negative peer offsets");
     A.peer.bufs = reinterpret_cast<float* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer->peer_bufs_dev)));
     A.peer.flags = reinterpret_cast<uint32_t* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer->peer_flags_dev)));
     A.peer.world = peer->world;
@@ -1078,11 +1131,19 @@ int mg_block_forward_push(const void* x, int x_dtype, int B, int Hp, int Wp, int
   return check_launch("block_forward_kernel");
 }
 
+int mg_block_forward_push(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K,
+                          float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work, float* S,
+                          int32_t* labels, float* loss, float* region_in, float* region_out, const mg_peer_out_t* peer,
+                          mg_stream_t stream) {
+  return mg_block_forward_ex(x, x_dtype, B, Hp, Wp, in_dim, D, H1, H2, H3, K, slope1, slope2, slope3, prep, h, q_work, S,
+                             labels, loss, region_in, region_out, peer, nullptr, stream);
+}
+
 int mg_block_forward(const void* x, int x_dtype, int B, int Hp, int Wp, int in_dim, int D, int H1, int H2, int H3, int K,
                      float slope1, float slope2, float slope3, const float* prep, float* h, float* q_work, float* S,
                      int32_t* labels, float* loss, float* region_in, float* region_out, mg_stream_t stream) {
-  return mg_block_forward_push(x, x_dtype, B, Hp, Wp, in_dim, D, H1, H2, H3, K, slope1, slope2, slope3, prep, h, q_work, S,
-                               labels, loss, region_in, region_out, nullptr, stream);
+  return mg_block_forward_ex(x, x_dtype, B, Hp, Wp, in_dim, D, H1, H2, H3, K, slope1, slope2, slope3, prep, h, q_work, S,
+                             labels, loss, region_in, region_out, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -414,12 +414,14 @@ def block_prepare(W1, a1, W2, a2, W3, a3, out: Optional[torch.Tensor] = None) ->
 
 
 def block_forward(x: torch.Tensor, Hp: int, Wp: int, prep: torch.Tensor, D: int, H1: int, H2: int, H3: int, K: int,
-                  slopes=(0.2, 0.2, 0.2), want_region_in: bool = False, outs=None, peer=None):
+                  slopes=(0.2, 0.2, 0.2), want_region_in: bool = False, outs=None, peer=None, feature_loss=None):
     """One launch for the whole per-image pipeline.  ``x (B,N,in)`` f32|bf16.  Returns
     ``h (B,N,D), S (B,N,K), labels (B,N) int32, loss (B,), region_in|None, region_out (B,K,D)``.
     ``peer``: a ``_lib.PeerOut`` (``distributed.PeerExchange.slot(i)``) — the kernel then also stores
     ``loss | region_out | labels`` into every rank's gathered buffer over NVLink and publishes the step
-    (``mg_block_forward_push``)."""
+    (``mg_block_forward_push``).  ``feature_loss``: ``(f_unet (B,N,D) f32, y (B,N), margin)`` — FeatureConsistencyLoss
+    evaluated inside the kernel on the rows of ``h`` (``mg_block_forward_ex``); the per-image sums ``(B,)`` are
+    appended to the returned tuple."""
     _need_cuda(x, prep)
     x = x.contiguous()
     B, N, in_dim = x.shape
@@ -440,11 +442,22 @@ def block_forward(x: torch.Tensor, Hp: int, Wp: int, prep: torch.Tensor, D: int,
         rout = torch.empty((B, K, D), **f32)
     q = torch.empty((B, N, 2 * H2 + H2 * K), **f32)
     rin = torch.empty((B, K, D), **f32) if want_region_in else None
+    fl = fl_out = None
+    if feature_loss is not None:
+        fu, y, margin = feature_loss
+        _need_cuda(fu, y)
+        if fu.dtype != torch.float32 or tuple(fu.shape) != (B, N, D) or tuple(y.shape) != (B, N):
+            raise ValueError("block_forward: feature_loss needs f_unet (B,N,D) float32 and y (B,N)")
+        fu, y = fu.contiguous(), y.to(torch.float32).contiguous()
+        fl_out = torch.empty(B, **f32)
+        fl = _lib.BlockFeatureLoss(fu.data_ptr(), y.data_ptr(), float(margin), fl_out.data_ptr())
     with torch.cuda.device(dev):
-        call("mg_block_forward_push", x.data_ptr(), _dtype_code(x.dtype), B, Hp, Wp, in_dim, D, H1, H2, H3, K,
+        call("mg_block_forward_ex", x.data_ptr(), _dtype_code(x.dtype), B, Hp, Wp, in_dim, D, H1, H2, H3, K,
              float(slopes[0]), float(slopes[1]), float(slopes[2]), prep.data_ptr(), h.data_ptr(), q.data_ptr(),
              S.data_ptr(), labels.data_ptr(), loss.data_ptr(), _ptr(rin), rout.data_ptr(),
-             None if peer is None else C.addressof(peer), _stream())
+             None if peer is None else C.addressof(peer), None if fl is None else C.addressof(fl), _stream())
+    if feature_loss is not None:
+        return h, S, labels, loss, rin, rout, fl_out
     return h, S, labels, loss, rin, rout
 
 

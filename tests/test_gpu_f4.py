@@ -168,6 +168,26 @@ def test_block_feature_loss(M, train):
         out = blk(x, (H, W), f_unet_patches=fu, patch_labels_y=y, want_dense=False)
     want = O.feature_consistency_loss(fu.detach().cpu(), out.patch_features.detach().cpu(), y.cpu())
     assert float(out.l_feature.detach()) == pytest.approx(float(want), rel=5e-6)
+    if not train:
+        # inference: the loss is evaluated INSIDE the one-launch block kernel (rows of h still in registers) — the step
+        # launches exactly as many kernels of the library as without the loss, and agrees with the stand-alone kernel
+        from mingraph_unet_b200 import _lib
+        with torch.no_grad():
+            n0 = _lib.launch_count(); blk(x, (H, W), want_dense=False)
+            n1 = _lib.launch_count(); blk(x, (H, W), f_unet_patches=fu, patch_labels_y=y, want_dense=False)
+            n2 = _lib.launch_count()
+        assert n2 - n1 == n1 - n0 == 1
+        alone = M.FeatureConsistencyLoss()(fu, out.patch_features, y)
+        assert float(out.l_feature) == pytest.approx(float(alone), rel=2e-6)
+        # other margins / label dtypes, a padded grid and K = 3
+        blk3 = M.GraphBlock(node_feature_dim=12, num_segments=3, dropout_rate=0.0).cuda().eval()
+        x3 = torch.randn(2, 5 * 5, 12, device="cuda")
+        fu3 = 0.5 * torch.randn(2, 25, 64, device="cuda")
+        y3 = torch.randint(0, 2, (2, 25), device="cuda").float()
+        with torch.no_grad():
+            o3 = blk3(x3, (70, 75), f_unet_patches=fu3, patch_labels_y=y3, feature_loss_margin=0.7, want_dense=False)
+        w3 = O.feature_consistency_loss(fu3.cpu(), o3.patch_features.cpu(), y3.cpu(), margin=0.7)
+        assert float(o3.l_feature) == pytest.approx(float(w3), rel=5e-6)
     if train:
         (out.l_feature + out.l_partition.mean()).backward()
         assert fu.grad is not None and torch.isfinite(fu.grad).all()
