@@ -43,6 +43,12 @@ struct GatTcArgs {
   float slope;
 };
 
+// ---- programmatic dependent launch: the four kernels of a layer are chained on one stream; each lets its successor
+// start (prologue + loads of the layer's INPUTS) while it is still running, and the successor waits for its
+// predecessor's outputs right before it first reads them -------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- PTX helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint32_t bar, int count) {
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(256) tc_u_kernel(const float* __restrict__ W, 
   constexpr int FP = 256 / IN;
   __shared__ float u_part[FP][2 * IN];
   const int h = blockIdx.x;
+  pdl_launch_dependents();
   {
     const int i = threadIdx.x % IN, fp = threadIdx.x / IN;
     const float* Wh = W + (size_t)h * F * IN + i;
@@ -237,6 +244,23 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
   constexpr int CH = IN / 32;                                  // 16-byte chunks per lane per row
   constexpr int STEPS = IN / 16;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  pdl_launch_dependents();
+  // the first step's rows of x (an INPUT of the layer) are requested before this kernel waits for u (its predecessor's
+  // output): the DRAM round trip overlaps the tail of tc_u_kernel and the fragment set-up below
+  uint4 x0[CH], x1[CH];
+  {
+    const int base = wid * 16;
+    if (base < N) {
+      const int r0 = min(base + g, N - 1), r1 = min(base + g + 8, N - 1);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        x0[c] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r0 * IN) + c * 4 + t);
+        x1[c] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r1 * IN) + c * 4 + t);
+      }
+    }
+  }
+  pdl_wait_prior_grid();
   uint32_t bhi[STEPS][2], blo[STEPS][2];
 #pragma unroll
   for (int m = 0; m < STEPS; ++m)
@@ -250,14 +274,14 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
       bhi[m][r] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
       blo[m][r] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int base = wid * 16; base < N; base += nw * 16) {
-    const int r0 = min(base + g, N - 1), r1 = min(base + g + 8, N - 1);
-    uint4 x0[CH], x1[CH];
+    if (base != wid * 16) {                                    // (the first step's rows are already in flight)
+      const int r0 = min(base + g, N - 1), r1 = min(base + g + 8, N - 1);
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      x0[c] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r0 * IN) + c * 4 + t);
-      x1[c] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r1 * IN) + c * 4 + t);
+      for (int c = 0; c < CH; ++c) {
+        x0[c] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r0 * IN) + c * 4 + t);
+        x1[c] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r1 * IN) + c * 4 + t);
+      }
     }
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
@@ -294,6 +318,8 @@ __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restr
   __shared__ int red_g[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();                                       // s comes from tc_scores_kernel
   // running maxima of the warp for graph g_run (flushed with one atomic per head when the graph changes / at the end:
   // atomics on the same four addresses serialise in L2, so there must be few of them)
   float m_run[NH];
@@ -433,6 +459,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait_prior_grid();                                       // s, gmax of the pre-pass are read from here on
 
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N=F, M=128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
@@ -833,6 +860,9 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // everything above (barriers, TMEM allocation, W -> bf16 B operand) ran beside the tail of the edge-max pre-pass;
+  // its outputs (s, gmax) are read from here on
+  pdl_wait_prior_grid();
 
   // instruction descriptor: D = f32, A = B = bf16, both K-major, N = F, M = 128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
@@ -1181,6 +1211,23 @@ static bool ag_mma_supported(int in_dim, int F, int heads, int concat, int out_b
   return ag_smem_layout(F, out_bf16 && !concat).total <= 227 * 1024;
 }
 
+// launch with programmatic stream serialisation: the kernel may start while its predecessor on the stream is still
+// running; it calls griddepcontrol.wait before it reads the predecessor's outputs
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int NH, int LPN>
 static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, float* u, size_t smem, int grid,
                      cudaStream_t st) {
@@ -1195,23 +1242,23 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
   const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)A.N * 2, 256), (int64_t)num_sms() * 8);   // 16 nodes per warp step
   tc_u_kernel<NH, LPN><<<NH, 256, 0, st>>>(A.W, a, A.F, G, u, gmax);
   if ((rc = check_launch("tc_u_kernel"))) return rc;
-  tc_scores_kernel<NH, LPN><<<sgrid, 256, 0, st>>>(A.x, A.N, u, s);
+  launch_pdl(tc_scores_kernel<NH, LPN>, dim3(sgrid), dim3(256), 0, st, A.x, A.N, (const float*)u, s);
   if ((rc = check_launch("tc_scores_kernel"))) return rc;
   const int mgrid = std::min(ceil_div(A.N, 256), num_sms() * 6);
   if (A.E > (int64_t)A.N * 12)      // high in-degree: more gathers in flight per destination
-    tc_edge_max_kernel<NH, 8><<<mgrid, 256, 0, st>>>(A.rowptr, A.col, s, A.N, A.nodes_per_graph, gmax);
+    launch_pdl(tc_edge_max_kernel<NH, 8>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax);
   else
-    tc_edge_max_kernel<NH, 4><<<mgrid, 256, 0, st>>>(A.rowptr, A.col, s, A.N, A.nodes_per_graph, gmax);
+    launch_pdl(tc_edge_max_kernel<NH, 4>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax);
   if ((rc = check_launch("tc_edge_max_kernel"))) return rc;
   if (NH == kAgNH && LPN * 8 == kAgIn && ag_mma_supported(LPN * 8, A.F, NH, A.concat, A.out_bf16)) {
     if (cudaFuncSetAttribute(gat_agg_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("gat_agg_mma_kernel: cannot raise dynamic shared memory");
       return MG_ERR_CUDA;
     }
-    gat_agg_mma_kernel<<<grid, kAgThreads, (size_t)ag_smem_layout(A.F, A.out_bf16 && !A.concat).total, st>>>(A);
+    launch_pdl(gat_agg_mma_kernel, dim3(grid), dim3(kAgThreads), (size_t)ag_smem_layout(A.F, A.out_bf16 && !A.concat).total, st, A);
     return check_launch("gat_agg_mma_kernel");
   }
-  k<<<grid, kTcThreads, smem, st>>>(A);
+  launch_pdl(k, dim3(grid), dim3(kTcThreads), smem, st, A);
   return check_launch("gat_tc_kernel");
 }
 
