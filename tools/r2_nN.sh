@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 port=29610
 for m in $modes; do
   port=$((port + 1))
-  timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
     tools/check_exchange.py --mode $m 2>&1 | grep -E "exchange world|rror|Traceback" | tail -3
   port=$((port + 1))
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
