@@ -200,7 +200,8 @@ __host__ __device__ inline TcSmem tc_smem_layout(int heads, int in_dim, int F, b
 // u_src[h] = W_h^T a_h[:F], u_tgt[h] = W_h^T a_h[F:] come from a one-block kernel (which also resets the per-graph maxima).
 template <int NH, int LPN>
 __global__ void __launch_bounds__(256) tc_u_kernel(const float* __restrict__ W, const float* __restrict__ a, int F,
-                                                   int num_graphs, float* __restrict__ u, float* __restrict__ gmax) {
+                                                   int num_graphs, float* __restrict__ u, float* __restrict__ gmax,
+                                                   float* __restrict__ gsrc /* (NH) or null: max_i s_src[i][h] */) {
   // one block per head: thread = (f-partition, input column); all of a thread's loads are independent
   constexpr int IN = LPN * 8;
   constexpr int FP = 256 / IN;
@@ -221,8 +222,10 @@ __global__ void __launch_bounds__(256) tc_u_kernel(const float* __restrict__ W, 
     u_part[fp][i] = acc0;
     u_part[fp][IN + i] = acc1;
   }
-  if (h == 0)
+  if (h == 0) {
     for (int i = threadIdx.x; i < num_graphs * NH; i += blockDim.x) gmax[i] = -INFINITY;
+    if (gsrc && threadIdx.x < NH) gsrc[threadIdx.x] = -INFINITY;
+  }
   __syncthreads();
   for (int idx = threadIdx.x; idx < 2 * IN; idx += blockDim.x) {
     float v = 0.f;
@@ -235,7 +238,8 @@ __global__ void __launch_bounds__(256) tc_u_kernel(const float* __restrict__ W, 
 
 template <int NH, int LPN>
 __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __restrict__ x, int N,
-                                                        const float* __restrict__ u, float* __restrict__ s) {
+                                                        const float* __restrict__ u, float* __restrict__ s,
+                                                        float* __restrict__ gsrc /* nullable */) {
   constexpr int IN = LPN * 8, NQ = 2 * NH;
   const float* u_s = u;                                        // (2*NH, IN) fp32, 2 KB at most: L1/L2 resident
   // s = X U^T on mma.sync m16n8k16 (bf16 x bf16 -> f32): a warp takes 16 nodes per step.  x is bf16 already; u is split
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
       bhi[m][r] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
       blo[m][r] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
+  float ms0 = -INFINITY, ms1 = -INFINITY;                       // running max of this lane's two score columns (rows it owns)
   for (int base = wid * 16; base < N; base += nw * 16) {
     if (base != wid * 16) {                                    // (the first step's rows are already in flight)
       const int r0 = min(base + g, N - 1), r1 = min(base + g + 8, N - 1);
@@ -297,9 +302,84 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(blo[m][0]), "r"(blo[m][1]));
     }
     if (2 * t < NQ) {
-      if (base + g < N) *reinterpret_cast<float2*>(s + (size_t)(base + g) * NQ + 2 * t) = make_float2(c0, c1);
-      if (base + g + 8 < N) *reinterpret_cast<float2*>(s + (size_t)(base + g + 8) * NQ + 2 * t) = make_float2(c2, c3);
+      if (base + g < N) {
+        *reinterpret_cast<float2*>(s + (size_t)(base + g) * NQ + 2 * t) = make_float2(c0, c1);
+        ms0 = fmaxf(ms0, c0); ms1 = fmaxf(ms1, c1);
+      }
+      if (base + g + 8 < N) {
+        *reinterpret_cast<float2*>(s + (size_t)(base + g + 8) * NQ + 2 * t) = make_float2(c2, c3);
+        ms0 = fmaxf(ms0, c2); ms1 = fmaxf(ms1, c3);
+      }
     }
+  }
+  // max_i s_src[i][h] (columns 0 .. NH-1 of s): the bound the edge-max pre-pass prunes with.  Lanes with equal t hold
+  // the same two columns; one atomic per column and BLOCK (atomics on four addresses serialise in L2).
+  if (gsrc) {
+    __shared__ float red[8][NQ];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      ms0 = fmaxf(ms0, __shfl_xor_sync(kFull, ms0, o));
+      ms1 = fmaxf(ms1, __shfl_xor_sync(kFull, ms1, o));
+    }
+    const int warp = threadIdx.x >> 5;
+    if (g == 0 && 2 * t < NQ) { red[warp][2 * t] = ms0; red[warp][2 * t + 1] = ms1; }
+    __syncthreads();
+    if (threadIdx.x < NH) {
+      float v = red[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w][threadIdx.x]);
+      if (v > -INFINITY) atomic_max_f32(gsrc + threadIdx.x, v);
+    }
+  }
+}
+
+// ---- pre-pass 2a (single graph): a LOWER bound of the edge maximum from every destination's first in-edge.  Together
+// with gsrc it lets the full scan below skip every destination whose best possible edge, s_tgt[j] + max_i s_src[i],
+// cannot exceed it: fp32 addition is monotone, so the bound holds bit for bit and the result stays the exact maximum.
+template <int NH>
+__global__ void __launch_bounds__(256) tc_edge_first_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                         const float* __restrict__ s, int N, float* __restrict__ gmax) {
+  constexpr int NQ = 2 * NH;
+  __shared__ float red[8][NH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  float m[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) m[h] = -INFINITY;
+  const int stride = gridDim.x * blockDim.x;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int beg = 0, end = 0, c0 = -1;
+  if (j < N) {                                                 // inputs of the layer: requested before the wait
+    beg = __ldg(rowptr + j); end = __ldg(rowptr + j + 1);
+    if (beg < end) c0 = __ldg(col + beg);
+  }
+  pdl_wait_prior_grid();                                       // s comes from tc_scores_kernel
+  for (; j < N; j += stride) {
+    if (c0 >= 0) {
+      float sv[NH], st[NH];
+      load_scores<NH>(s + (size_t)c0 * NQ, sv);
+      load_scores<NH>(s + (size_t)j * NQ + NH, st);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) m[h] = fmaxf(m[h], sv[h] + st[h]);
+    }
+    const int jn = j + stride;
+    c0 = -1;
+    if (jn < N) {
+      beg = __ldg(rowptr + jn); end = __ldg(rowptr + jn + 1);
+      if (beg < end) c0 = __ldg(col + beg);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const float v = warp_max(m[h]);
+    if (lane == 0) red[warp][h] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NH) {
+    float v = red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w][threadIdx.x]);
+    if (v > -INFINITY) atomic_max_f32(gmax + threadIdx.x, v);
   }
 }
 
@@ -312,7 +392,7 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
 template <int NH, int UN>
 __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                        const float* __restrict__ s, int N, int nodes_per_graph,
-                                                       float* __restrict__ gmax) {
+                                                       float* __restrict__ gmax, const float* __restrict__ gsrc /* nullable */) {
   constexpr int NQ = 2 * NH;
   __shared__ float red[8][NH];
   __shared__ int red_g[8];
@@ -320,6 +400,14 @@ __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restr
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   pdl_launch_dependents();
   pdl_wait_prior_grid();                                       // s comes from tc_scores_kernel
+  // single graph: what a destination must beat to matter, and the best any source can contribute (see
+  // tc_edge_first_kernel).  gmax only grows while this kernel runs; a stale read merely prunes less.
+  float lowb[NH], gs[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    lowb[h] = gsrc ? __ldcg(gmax + h) : -INFINITY;
+    gs[h] = gsrc ? __ldcg(gsrc + h) : INFINITY;
+  }
   // running maxima of the warp for graph g_run (flushed with one atomic per head when the graph changes / at the end:
   // atomics on the same four addresses serialise in L2, so there must be few of them)
   float m_run[NH];
@@ -332,7 +420,20 @@ __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restr
     float m[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) m[h] = -INFINITY;
+    float st[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) st[h] = 0.f;
+    bool scan = ok;
     if (ok) {
+      load_scores<NH>(s + (size_t)j * NQ + NH, st);
+      if (gsrc) {                                              // can any edge into j exceed the lower bound?
+        bool may = false;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) may = may || (st[h] + gs[h] > lowb[h]);
+        scan = may;
+      }
+    }
+    if (scan) {
       const int beg = __ldg(rowptr + j), end = __ldg(rowptr + j + 1);
       for (int k = beg; k < end; k += UN) {                    // UN column loads, then UN score gathers, all in flight
         int c[UN];
@@ -350,8 +451,6 @@ __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restr
 #pragma unroll
           for (int h = 0; h < NH; ++h) m[h] = fmaxf(m[h], sv[e][h]);
       }
-      float st[NH];
-      load_scores<NH>(s + (size_t)j * NQ + NH, st);
 #pragma unroll
       for (int h = 0; h < NH; ++h) m[h] += st[h];                                 // -inf stays -inf for isolated nodes
     }
@@ -400,6 +499,81 @@ __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restr
       for (int h = 0; h < NH; ++h)
         if (red[lane][h] > -INFINITY) atomic_max_f32(gmax + (size_t)gw * NH + h, red[lane][h]);
     }
+  }
+}
+
+// ---- pre-pass 2b (single graph, pruned): only destinations that can still raise the maximum are scanned, and they are
+// scanned by whole warps.  A block takes 256 consecutive destinations: every thread tests its destination against the
+// bound (s_tgt[j] + max_i s_src[i] > lower bound, any head), the survivors are compacted into a shared-memory list, and
+// each warp then walks the in-edges of one survivor at a time, 32 edges per pass (coalesced column load, 32 score gathers
+// in flight).  A thread-per-destination scan gains nothing from pruning: one surviving lane keeps its warp in the loop.
+template <int NH>
+__global__ void __launch_bounds__(256) tc_edge_max_pruned_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                              const float* __restrict__ s, int N, float* __restrict__ gmax,
+                                                              const float* __restrict__ gsrc) {
+  constexpr int NQ = 2 * NH;
+  __shared__ int list[256];
+  __shared__ int wcount[8];
+  __shared__ float red[8][NH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();                                       // s, gsrc, the first-edge lower bound in gmax
+  float lowb[NH], gs[NH], run[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    lowb[h] = __ldcg(gmax + h);                                // gmax only grows while this kernel runs: a stale read prunes less
+    gs[h] = __ldcg(gsrc + h);
+    run[h] = -INFINITY;
+  }
+  for (int base = blockIdx.x * 256; base < N; base += gridDim.x * 256) {
+    const int j = base + threadIdx.x;
+    bool may = false;
+    if (j < N) {
+      float st[NH];
+      load_scores<NH>(s + (size_t)j * NQ + NH, st);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) may = may || (st[h] + gs[h] > lowb[h]);
+    }
+    const unsigned bal = __ballot_sync(kFull, may);
+    if (lane == 0) wcount[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) off += wcount[w];
+      total += wcount[w];
+    }
+    if (may) list[off + __popc(bal & ((1u << lane) - 1u))] = j;
+    __syncthreads();
+    for (int idx = warp; idx < total; idx += 8) {              // warp-uniform trip count
+      const int jj = list[idx];
+      const int beg = __ldg(rowptr + jj), end = __ldg(rowptr + jj + 1);
+      float m[NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) m[h] = -INFINITY;
+      for (int k = beg + lane; k < end; k += 32) {
+        float sv[NH];
+        load_scores<NH>(s + (size_t)__ldg(col + k) * NQ, sv);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) m[h] = fmaxf(m[h], sv[h]);
+      }
+      float st[NH];
+      load_scores<NH>(s + (size_t)jj * NQ + NH, st);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) run[h] = fmaxf(run[h], warp_max(m[h]) + st[h]);    // -inf stays -inf for isolated nodes
+    }
+    __syncthreads();                                           // the list is reused by the next chunk
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h) red[warp][h] = run[h];
+  }
+  __syncthreads();
+  if (threadIdx.x < NH) {
+    float v = red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w][threadIdx.x]);
+    if (v > -INFINITY) atomic_max_f32(gmax + threadIdx.x, v);
   }
 }
 
@@ -1240,15 +1414,26 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
   const int G = A.nodes_per_graph > 0 ? A.N / A.nodes_per_graph : 1;
   int rc;
   const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)A.N * 2, 256), (int64_t)num_sms() * 8);   // 16 nodes per warp step
-  tc_u_kernel<NH, LPN><<<NH, 256, 0, st>>>(A.W, a, A.F, G, u, gmax);
+  // single graph with enough edges per node: prune the edge-max scan (gsrc sits in the slack of the 256-byte gmax segment)
+  static const int prune_env = getenv("MG_GAT_PRUNE") ? atoi(getenv("MG_GAT_PRUNE")) : 1;
+  float* gsrc = (prune_env && G == 1 && A.E >= (int64_t)A.N * 12) ? gmax + 16 : nullptr;
+  tc_u_kernel<NH, LPN><<<NH, 256, 0, st>>>(A.W, a, A.F, G, u, gmax, gsrc);
   if ((rc = check_launch("tc_u_kernel"))) return rc;
-  launch_pdl(tc_scores_kernel<NH, LPN>, dim3(sgrid), dim3(256), 0, st, A.x, A.N, (const float*)u, s);
+  launch_pdl(tc_scores_kernel<NH, LPN>, dim3(sgrid), dim3(256), 0, st, A.x, A.N, (const float*)u, s, gsrc);
   if ((rc = check_launch("tc_scores_kernel"))) return rc;
   const int mgrid = std::min(ceil_div(A.N, 256), num_sms() * 6);
-  if (A.E > (int64_t)A.N * 12)      // high in-degree: more gathers in flight per destination
-    launch_pdl(tc_edge_max_kernel<NH, 8>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax);
+  if (gsrc) {
+    launch_pdl(tc_edge_first_kernel<NH>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, gmax);
+    if ((rc = check_launch("tc_edge_first_kernel"))) return rc;
+    launch_pdl(tc_edge_max_pruned_kernel<NH>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, gmax,
+               (const float*)gsrc);
+    if ((rc = check_launch("tc_edge_max_pruned_kernel"))) return rc;
+  } else if (A.E > (int64_t)A.N * 12)      // high in-degree: more gathers in flight per destination
+    launch_pdl(tc_edge_max_kernel<NH, 8>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax,
+               (const float*)gsrc);
   else
-    launch_pdl(tc_edge_max_kernel<NH, 4>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax);
+    launch_pdl(tc_edge_max_kernel<NH, 4>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax,
+               (const float*)gsrc);
   if ((rc = check_launch("tc_edge_max_kernel"))) return rc;
   if (NH == kAgNH && LPN * 8 == kAgIn && ag_mma_supported(LPN * 8, A.F, NH, A.concat, A.out_bf16)) {
     if (cudaFuncSetAttribute(gat_agg_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
