@@ -928,10 +928,13 @@ constexpr int kAgIn = 64, kAgNH = 4;
 constexpr int kAgRowBytes = kAgIn * 2;                      // 128
 constexpr int kAgStageBytes = 32 * kAgRowBytes;             // 4 KB: 4 destinations x 8 edge slots
 constexpr int kAgStages = 2;
-constexpr int kAgStepsPerTile = kTcTile / 4;                // 32
+constexpr int kAgTile = kTcTile;                            // destinations per tile (96 = two steps per warp was measured: slower, the epilogue warps become the limit)
+constexpr int kAgStepsPerTile = kAgTile / 4;                // 32
 
+constexpr int kAgAttDst = 144;                              // bytes per destination in the attention scratch: 8 slots x 4 heads + 16 pad (bank shift)
+constexpr int kAgAttBytes = 4 * kAgAttDst;                  // per warp
 struct AgSmem {
-  int a_off, b_off, ring_off, stage_off, total;
+  int a_off, b_off, ring_off, att_off, stage_off, total;
 };
 __host__ __device__ inline AgSmem ag_smem_layout(int F, bool staged) {
   AgSmem L;
@@ -939,14 +942,44 @@ __host__ __device__ inline AgSmem ag_smem_layout(int F, bool staged) {
   L.a_off = o;     o += kAgNH * kTcTile * 128;              // 4 head blocks of 128 rows x 64 bf16
   L.b_off = o;     o += kAgNH * F * 128;
   L.ring_off = o;  o += kAgWarps * kAgStages * kAgStageBytes;
+  L.att_off = o;   o += kAgWarps * kAgAttBytes;
   o = (o + 1023) & ~1023;
-  L.stage_off = o; o += staged ? kTcTile * F * 2 : 0;
+  L.stage_off = o; o += staged ? kAgTile * F * 2 : 0;
   L.total = o + 1024;
   return L;
 }
 
 __device__ __forceinline__ void ag_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// base + row * 128 as ONE 64-bit multiply-add (left to itself the compiler splits it into a multiply, an OR and a two-instruction add)
+__device__ __forceinline__ const char* ag_row_ptr(const char* lane_base, int row) {
+  unsigned long long p;
+  asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(p) : "r"((unsigned)row), "l"((unsigned long long)lane_base));
+  return reinterpret_cast<const char*>(p);
+}
+__device__ __forceinline__ float ag_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// acc += ELU(a), ELU(b) on a packed pair: ELU(v) = max(v, exp(min(v, 0)) - 1) (for v > 0 the second term is 0; for v <= 0 it is
+// >= v), the scale by log2(e), the -1 and the sum each one packed instruction for the two lanes
+__device__ __forceinline__ void ag_elu2_acc(unsigned long long& acc, uint32_t a, uint32_t b) {
+  asm("{\n.reg .b64 m, t;\n.reg .f32 ml, mh, tl, th;\n"
+      "mov.b64 m, {%1, %2};\n"
+      "mul.f32x2 m, m, %3;\n"
+      "mov.b64 {ml, mh}, m;\n"
+      "min.f32 ml, ml, 0f00000000;\nmin.f32 mh, mh, 0f00000000;\n"
+      "ex2.approx.ftz.f32 tl, ml;\nex2.approx.ftz.f32 th, mh;\n"
+      "mov.b64 t, {tl, th};\n"
+      "add.f32x2 t, t, %4;\n"
+      "mov.b64 {tl, th}, t;\n"
+      "max.f32 tl, tl, %1;\nmax.f32 th, th, %2;\n"
+      "mov.b64 t, {tl, th};\n"
+      "add.f32x2 %0, %0, t;\n}"
+      : "+l"(acc)
+      : "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "l"(0x3fb8aa3b3fb8aa3bull), "l"(0xbf800000bf800000ull));
 }
 __device__ __forceinline__ void ag_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -999,7 +1032,7 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int F = A.F;
-  const int ntiles = ceil_div(A.N, kTcTile);
+  const int ntiles = ceil_div(A.N, kAgTile);
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
@@ -1069,8 +1102,8 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
     constexpr float kLog2e = 1.4426950408889634f;
     const float slope = A.slope;
     const int npg = A.nodes_per_graph;
-    const int tile_stride = (int)gridDim.x * kTcTile;
-    const int n_end = ntiles * kTcTile;                       // a cursor is exhausted once its tile base reaches this
+    const int tile_stride = (int)gridDim.x * kAgTile;
+    const int n_end = ntiles * kAgTile;                       // a cursor is exhausted once its tile base reaches this
     // lane constants
     const uint32_t cp_off_even = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ r4) << 4));          // rows 8m + r4
     const uint32_t cp_off_odd = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ (r4 | 4)) << 4));      // rows 8m + 4 + r4
@@ -1084,10 +1117,12 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
     const uint32_t mask_d0 = dsel == 0 ? 0xffffffffu : 0u, mask_d1 = ~mask_d0;
     const uint32_t z_lane = tc_smem_u32(As) + (uint32_t)(hd * kTcTile * 128 + dsel * 128 + t4 * 4);
     const int slotA = dsel * 8 + 2 * t4, slotB = slotA + 16;  // the lane's (destination, edge) slots: A rows 0-7, B rows 8-15
+    float* att_w = reinterpret_cast<float*>(sm + L.att_off + warp * kAgAttBytes + r4 * kAgAttDst + ch8 * 16);          // slot (r4, ch8), heads 0..3
+    const float* att_r = reinterpret_cast<const float*>(sm + L.att_off + warp * kAgAttBytes + dsel * kAgAttDst + t4 * 32 + hd * 4);
     const float M_single = npg > 0 ? 0.f : leaky_relu(__ldg(A.gmax + hd), slope);     // one graph: the shift is a lane constant
 
     // ---- cursor over the warp's steps (warp-uniform), loader-lane row ranges ----
-    int cur_tb = (int)blockIdx.x * kTcTile, cur_step = warp, cur_it = 0;     // tile base node, step in tile, tile ordinal
+    int cur_tb = (int)blockIdx.x * kAgTile, cur_step = warp, cur_it = 0;     // tile base node, step in tile, tile ordinal
     int cur_c = 0, cur_nch = 1, cur_beg = 0, cur_end = 0, nxt_beg = 0, nxt_end = 0;
 #define AG_NEXT_STEP(tb, st, it)  \
   do {                            \
@@ -1098,14 +1133,16 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
       ++it;                       \
     }                             \
   } while (0)
-#define AG_FETCH_RP(tb, st, b, e)                       \
-  do {                                                  \
-    b = 0; e = 0;                                       \
-    const int j_ = tb + st * 4 + r4;                    \
-    if (tb < n_end && j_ < A.N) {                       \
-      b = __ldg(A.rowptr + j_);                         \
-      e = __ldg(A.rowptr + j_ + 1);                     \
-    }                                                   \
+    // the loads write the pipeline registers themselves: a copy out of a temporary would wait for the data one
+    // instruction after the request (measured: 7 % of the aggregation warps' time in that move)
+#define AG_FETCH_RP(tb, st, b, e)                                                                  \
+  do {                                                                                             \
+    b = 0; e = 0;                                                                                  \
+    const int j_ = tb + st * 4 + r4;                                                               \
+    const int ok_ = (tb < n_end && j_ < A.N) ? 1 : 0;                                              \
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p ld.global.nc.b32 %0, [%3];\n"        \
+                 "@p ld.global.nc.b32 %1, [%3+4];\n}"                                              \
+                 : "+r"(b), "+r"(e) : "r"(ok_), "l"(A.rowptr + (ok_ ? j_ : 0)));                   \
   } while (0)
     AG_FETCH_RP(cur_tb, cur_step, cur_beg, cur_end);
     {
@@ -1115,17 +1152,27 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
     }
     cur_nch = max(1, __reduce_max_sync(kFull, (cur_end - cur_beg + 7) >> 3));
     // advance the cursor by one item; rowptr of the step after the next one is prefetched
-#define AG_ADVANCE()                                                            \
-  do {                                                                          \
-    if (++cur_c >= cur_nch) {                                                   \
-      AG_NEXT_STEP(cur_tb, cur_step, cur_it);                                   \
-      cur_beg = nxt_beg; cur_end = nxt_end;                                     \
-      int tb = cur_tb, st = cur_step, it = cur_it;                              \
-      AG_NEXT_STEP(tb, st, it);                                                 \
-      AG_FETCH_RP(tb, st, nxt_beg, nxt_end);                                    \
-      cur_c = 0;                                                                \
-      cur_nch = max(1, __reduce_max_sync(kFull, (cur_end - cur_beg + 7) >> 3)); \
-    }                                                                           \
+    // branch-free on the load: the prefetched row pointers are written by a predicated load straight into nxt_beg / nxt_end
+    // (tied asm operands), so nothing waits for them before the next step reads them
+#define AG_ADVANCE()                                                                                               \
+  do {                                                                                                             \
+    const bool adv_ = ++cur_c >= cur_nch;                                                                          \
+    if (adv_) {                                                                                                    \
+      AG_NEXT_STEP(cur_tb, cur_step, cur_it);                                                                      \
+      cur_c = 0;                                                                                                   \
+    }                                                                                                              \
+    cur_beg = adv_ ? nxt_beg : cur_beg;                                                                            \
+    cur_end = adv_ ? nxt_end : cur_end;                                                                            \
+    {                                                                                                              \
+      int tb = cur_tb, st = cur_step, it = cur_it;                                                                 \
+      AG_NEXT_STEP(tb, st, it);                                                                                    \
+      /* past the last node both loads read rowptr[N]: an empty range, no zeroing (a select would wait for the load) */ \
+      const int j_ = tb < n_end ? min(tb + st * 4 + r4, A.N) : A.N;                                                \
+      asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p ld.global.nc.b32 %0, [%3];\n@p ld.global.nc.b32 %1, [%4];\n}" \
+                   : "+r"(nxt_beg), "+r"(nxt_end)                                                                  \
+                   : "r"(adv_ ? 1 : 0), "l"(A.rowptr + j_), "l"(A.rowptr + min(j_ + 1, A.N)));                     \
+    }                                                                                                              \
+    if (adv_) cur_nch = max(1, __reduce_max_sync(kFull, (cur_end - cur_beg + 7) >> 3));                            \
   } while (0)
     // loader lane: source node of its slot in the cursor's item (-1: no edge)
 #define AG_LOAD_SRC(dst)                                             \
@@ -1140,18 +1187,12 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
     _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) {                                                 \
       const int sn_ = __shfl_sync(kFull, src, i_ * 4 + r4);                                            \
       ag_cp_async16(sb_ + (uint32_t)(i_ * 4 * kAgRowBytes) + ((i_ & 1) ? cp_off_odd : cp_off_even),   \
-                    x_lane + (size_t)(unsigned)max(sn_, 0) * kAgRowBytes, sn_ >= 0 ? 16u : 0u);        \
+                    ag_row_ptr(x_lane, max(sn_, 0)), sn_ >= 0 ? 16u : 0u);                              \
     }                                                                                                 \
   } while (0)
     // attention scalars of an item: s_src of the lane's 4 slots (-inf: empty), s_tgt and shift of its two destinations
-#define AG_LOAD_ATT(src, node0, sv, st2, M2)                                                           \
+#define AG_LOAD_TGT(node0, st2, M2)                                                                    \
   do {                                                                                                 \
-    const int n0_ = __shfl_sync(kFull, src, slotA), n1_ = __shfl_sync(kFull, src, slotA + 1);           \
-    const int n2_ = __shfl_sync(kFull, src, slotB), n3_ = __shfl_sync(kFull, src, slotB + 1);           \
-    sv[0] = n0_ >= 0 ? __ldg(s_src_lane + (size_t)(unsigned)n0_ * (2 * NH)) : -INFINITY;                 \
-    sv[1] = n1_ >= 0 ? __ldg(s_src_lane + (size_t)(unsigned)n1_ * (2 * NH)) : -INFINITY;                 \
-    sv[2] = n2_ >= 0 ? __ldg(s_src_lane + (size_t)(unsigned)n2_ * (2 * NH)) : -INFINITY;                 \
-    sv[3] = n3_ >= 0 ? __ldg(s_src_lane + (size_t)(unsigned)n3_ * (2 * NH)) : -INFINITY;                 \
     const int ja_ = node0 + dsel, jb_ = ja_ + 2;                                                        \
     const bool va_ = node0 >= 0 && ja_ < A.N, vb_ = node0 >= 0 && jb_ < A.N;                             \
     st2[0] = va_ ? __ldg(s_tgt_lane + (size_t)(unsigned)ja_ * (2 * NH)) : 0.f;                           \
@@ -1161,6 +1202,17 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
       M2[0] = va_ ? leaky_relu(__ldg(A.gmax + (size_t)(ja_ / npg) * NH + hd), slope) : 0.f;              \
       M2[1] = vb_ ? leaky_relu(__ldg(A.gmax + (size_t)(jb_ / npg) * NH + hd), slope) : 0.f;              \
     }                                                                                                   \
+  } while (0)
+    // loader role: the lane's OWN slot, all four heads in one 16-byte gather (a quarter of the L1 requests of four 4-byte
+    // gathers per fragment lane); the fragment lanes pick their values up from the warp's scratch in step E
+#define AG_LOAD_ATT(src, node0, sv, st2, M2)                                                           \
+  do {                                                                                                 \
+    sv[0] = sv[1] = sv[2] = sv[3] = -INFINITY;                                                           \
+    if (src >= 0) {                                                                                     \
+      const float4 v_ = __ldg(reinterpret_cast<const float4*>(A.s + (size_t)(unsigned)src * (2 * NH))); \
+      sv[0] = v_.x; sv[1] = v_.y; sv[2] = v_.z; sv[3] = v_.w;                                            \
+    }                                                                                                   \
+    AG_LOAD_TGT(node0, st2, M2);                                                                        \
   } while (0)
 
     // ---- software pipeline: item n on the tensor cores, rows + scalars of item n+1 and columns of item n+2 in flight ----
@@ -1203,10 +1255,15 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
         den0 = den1 = 0.f;
       }
       // E. attention numerators (graph_attention.py:61-65,86) and the block-diagonal A fragments
+      float sq[4];
+      *reinterpret_cast<float4*>(att_w) = make_float4(sv0[0], sv0[1], sv0[2], sv0[3]);
+      __syncwarp();
+      sq[0] = att_r[0]; sq[1] = att_r[4]; sq[2] = att_r[2 * kAgAttDst / 4]; sq[3] = att_r[2 * kAgAttDst / 4 + 4];
+      // (the scratch is rewritten one iteration later, behind the __syncwarp() that follows the MMAs)
       float p[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float e = sv0[i] + st0[i >> 1];
+        const float e = sq[i] + st0[i >> 1];
         p[i] = tc_ex2((fmaxf(e, e * slope) - M0[i >> 1]) * kLog2e);                 // LeakyReLU (0 <= slope <= 1); empty slot: ex2(-inf) = 0
       }
       den0 += p[0] + p[1];
@@ -1245,8 +1302,8 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
         float d0 = den0, d1 = den1;
         d0 += __shfl_xor_sync(kFull, d0, 1); d1 += __shfl_xor_sync(kFull, d1, 1);
         d0 += __shfl_xor_sync(kFull, d0, 2); d1 += __shfl_xor_sync(kFull, d1, 2);
-        const float inv0 = 1.f / (d0 + 1e-10f), inv1 = 1.f / (d1 + 1e-10f);           // graph_attention.py:96
-        if (it_0 > 0) tc_mbar_wait(bar_a_empty, (uint32_t)((it_0 - 1) & 1));           // previous tile's MMAs have read A
+        const float inv0 = ag_rcp(d0 + 1e-10f), inv1 = ag_rcp(d1 + 1e-10f);           // graph_attention.py:96
+        if (it_0 > 0 && row0_0 < 4 * kAgWarps) tc_mbar_wait(bar_a_empty, (uint32_t)((it_0 - 1) & 1));   // (the warp's first step of the tile)
         // rows qa = row0 + dsel and qa + 2; chunk nt of a row sits at ((nt ^ (row & 7)) << 4)
         const uint32_t za = z_lane + (uint32_t)row0_0 * 128u;
         const uint32_t xa = (uint32_t)(((row0_0 + dsel) & 7) << 4), xb = xa ^ 0x20u;   // (row + 2) & 7 = (row & 7) ^ 2 (row & 3 = dsel < 2)
@@ -1257,15 +1314,18 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(za + ((uint32_t)(nt << 4) ^ xa)), "r"(va) : "memory");
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(za + 256u + ((uint32_t)(nt << 4) ^ xb)), "r"(vb) : "memory");
         }
-        tc_fence_async_smem();                                // generic-proxy writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence_block();
-          const bool last = atomicAdd(arrive_cnt, 1) == kAgStepsPerTile * (it_0 + 1) - 1;
-          __threadfence_block();
-          if (last) issue_mma(it_0);                          // the LAST step of the tile to arrive issues its MMAs
+        // the warp's last step of the tile (steps warp, warp + 12, ...): one fence and one arrival for all its z rows
+        if (row0_0 + 4 * kAgWarps >= kAgTile) {
+          tc_fence_async_smem();                              // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence_block();
+            const bool last = atomicAdd(arrive_cnt, 1) == kAgWarps * (it_0 + 1) - 1;
+            __threadfence_block();
+            if (last) issue_mma(it_0);                        // the LAST warp to finish the tile issues its MMAs
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       // rotate the pipeline
       node0_0 = node0_1; row0_0 = row0_1; it_0 = it_1; first_0 = first_1; last_0 = last_1; src0 = src1;
@@ -1282,6 +1342,7 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
 #undef AG_LOAD_SRC
 #undef AG_ISSUE_ROWS
 #undef AG_LOAD_ATT
+#undef AG_LOAD_TGT
   } else {
     // ============ epilogue warps: TMEM -> ELU -> head mean / concat -> global (as in gat_tc_kernel) ============
     const int ew = warp & 3;                                  // TMEM lane quarter this warp may access
@@ -1291,10 +1352,11 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
     const int out_w = A.concat ? NH * F : F;
     const int cpr = F / 8;                                    // 16-byte chunks per staged bf16 row
     const int swz_mask = ((cpr & (cpr - 1)) == 0) ? (min(cpr, 8) - 1) : 0;
+    const int cpr_sh = ((cpr & (cpr - 1)) == 0) ? __ffs(cpr) - 1 : -1;       // power of two: row = idx >> cpr_sh (no runtime division)
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int stg = it & 1, nn = it >> 1;
-      const int tile_base = tile * kTcTile;
+      const int tile_base = tile * kAgTile;
       const int node = tile_base + row;
       tc_mbar_wait_relaxed(bar_t_full0 + 8 * stg, (uint32_t)(nn & 1));
       tc_fence_after();
@@ -1303,6 +1365,9 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
         float oacc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) oacc[i] = 0.f;
+        unsigned long long oacc2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) oacc2[i] = 0ull;
 #pragma unroll
         for (int h0 = 0; h0 < NH; h0 += 2) {
           uint32_t v[2][16];
@@ -1311,6 +1376,11 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
           tc_tmem_wait_ld();
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
+            if (!A.concat) {                                   // ELU per head (:118) and the head sum (:158) on packed pairs
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ag_elu2_acc(oacc2[i], v[hh][2 * i], v[hh][2 * i + 1]);
+              continue;
+            }
             float e16[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) e16[i] = tc_elu(__uint_as_float(v[hh][i]));          // ELU per head (:118)
@@ -1337,6 +1407,8 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
           }
         }
         if (!A.concat) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tc_unpack2(oacc2[i], oacc[2 * i], oacc[2 * i + 1]);
           if (staged) {
             uint4 pk[2];
             unsigned* pw = reinterpret_cast<unsigned*>(pk);
@@ -1359,11 +1431,11 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
       if (lane == 0) tc_mbar_arrive(bar_t_empty0 + 8 * stg);
       if (staged) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int valid_rows = min(kTcTile, A.N - tile_base);
+        const int valid_rows = min(kAgTile, A.N - tile_base);
         const int nchunks = valid_rows * cpr;
         uint4* gdst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + (size_t)tile_base * F);
         for (int idx = et; idx < nchunks; idx += 128) {
-          const int r = idx / cpr, c = idx - r * cpr;
+          const int r = cpr_sh >= 0 ? idx >> cpr_sh : idx / cpr, c = idx - r * cpr;
           gdst[idx] = *reinterpret_cast<const uint4*>(Ss + (size_t)r * F * 2 + ((c ^ (r & swz_mask)) << 4));
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1416,7 +1488,8 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
   const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)A.N * 2, 256), (int64_t)num_sms() * 8);   // 16 nodes per warp step
   // single graph with enough edges per node: prune the edge-max scan (gsrc sits in the slack of the 256-byte gmax segment)
   static const int prune_env = getenv("MG_GAT_PRUNE") ? atoi(getenv("MG_GAT_PRUNE")) : 1;
-  float* gsrc = (prune_env && G == 1 && A.E >= (int64_t)A.N * 12) ? gmax + 16 : nullptr;
+  static const int prune_deg = getenv("MG_GAT_PRUNE_MIN_DEG") ? atoi(getenv("MG_GAT_PRUNE_MIN_DEG")) : 12;
+  float* gsrc = (prune_env && G == 1 && A.E >= (int64_t)A.N * prune_deg) ? gmax + 16 : nullptr;
   tc_u_kernel<NH, LPN><<<NH, 256, 0, st>>>(A.W, a, A.F, G, u, gmax, gsrc);
   if ((rc = check_launch("tc_u_kernel"))) return rc;
   launch_pdl(tc_scores_kernel<NH, LPN>, dim3(sgrid), dim3(256), 0, st, A.x, A.N, (const float*)u, s, gsrc);
@@ -1440,7 +1513,8 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
       set_error("gat_agg_mma_kernel: cannot raise dynamic shared memory");
       return MG_ERR_CUDA;
     }
-    launch_pdl(gat_agg_mma_kernel, dim3(grid), dim3(kAgThreads), (size_t)ag_smem_layout(A.F, A.out_bf16 && !A.concat).total, st, A);
+    const int ag_grid = std::min(ceil_div(A.N, kAgTile), num_sms());
+    launch_pdl(gat_agg_mma_kernel, dim3(ag_grid), dim3(kAgThreads), (size_t)ag_smem_layout(A.F, A.out_bf16 && !A.concat).total, st, A);
     return check_launch("gat_agg_mma_kernel");
   }
   launch_pdl(k, dim3(grid), dim3(kTcThreads), smem, st, A);
