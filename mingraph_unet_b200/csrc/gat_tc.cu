@@ -437,8 +437,18 @@ __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restr
       const int beg = __ldg(rowptr + j), end = __ldg(rowptr + j + 1);
       for (int k = beg; k < end; k += UN) {                    // UN column loads, then UN score gathers, all in flight
         int c[UN];
+        // whole 16-byte groups of a row when it is aligned (fixed in-degree 4 / 8 / ...): a thread's 4 column ids in one load, and a
+        // warp's 32 loads cover 8 lines of 128 bytes instead of 32 (the pre-pass is bound by L1 wavefronts, not by bytes)
+        if (((reinterpret_cast<uintptr_t>(col + k) & 15) == 0) && k + UN <= end) {
 #pragma unroll
-        for (int e = 0; e < UN; ++e) c[e] = k + e < end ? __ldg(col + k + e) : -1;
+          for (int e = 0; e < UN; e += 4) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(col + k + e));
+            c[e] = v.x; c[e + 1] = v.y; c[e + 2] = v.z; c[e + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < UN; ++e) c[e] = k + e < end ? __ldg(col + k + e) : -1;
+        }
         float sv[UN][NH];
 #pragma unroll
         for (int e = 0; e < UN; ++e) {
@@ -1033,7 +1043,6 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int F = A.F;
   const int ntiles = ceil_div(A.N, kAgTile);
-  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
     *arrive_cnt = 0;
@@ -1108,7 +1117,6 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
     const uint32_t cp_off_even = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ r4) << 4));          // rows 8m + r4
     const uint32_t cp_off_odd = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ (r4 | 4)) << 4));      // rows 8m + 4 + r4
     const char* x_lane = reinterpret_cast<const char*>(A.x) + ch8 * 16;
-    const float* s_src_lane = A.s + hd;                       // + node * 8
     const float* s_tgt_lane = A.s + NH + hd;
     uint32_t ld_off[4];                                       // ldmatrix.x4.trans lane addresses for the 4 feature pairs (k-step 0)
 #pragma unroll
@@ -1116,9 +1124,9 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
       ld_off[np] = (uint32_t)((((r4 & 1) * 8 + ch8) * kAgRowBytes) + ((((np << 1) | (r4 >> 1)) ^ ch8) << 4));
     const uint32_t mask_d0 = dsel == 0 ? 0xffffffffu : 0u, mask_d1 = ~mask_d0;
     const uint32_t z_lane = tc_smem_u32(As) + (uint32_t)(hd * kTcTile * 128 + dsel * 128 + t4 * 4);
-    const int slotA = dsel * 8 + 2 * t4, slotB = slotA + 16;  // the lane's (destination, edge) slots: A rows 0-7, B rows 8-15
-    float* att_w = reinterpret_cast<float*>(sm + L.att_off + warp * kAgAttBytes + r4 * kAgAttDst + ch8 * 16);          // slot (r4, ch8), heads 0..3
-    const float* att_r = reinterpret_cast<const float*>(sm + L.att_off + warp * kAgAttBytes + dsel * kAgAttDst + t4 * 32 + hd * 4);
+        // (shared-space addresses: through generic pointers the compiler emits LD.E / ST.E, tracked on the long scoreboard)
+    const uint32_t att_w = tc_smem_u32(sm + L.att_off + warp * kAgAttBytes + r4 * kAgAttDst + ch8 * 16);                 // slot (r4, ch8), heads 0..3
+    const uint32_t att_r = tc_smem_u32(sm + L.att_off + warp * kAgAttBytes + dsel * kAgAttDst + t4 * 32 + hd * 4);
     const float M_single = npg > 0 ? 0.f : leaky_relu(__ldg(A.gmax + hd), slope);     // one graph: the shift is a lane constant
 
     // ---- cursor over the warp's steps (warp-uniform), loader-lane row ranges ----
@@ -1256,9 +1264,11 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
       }
       // E. attention numerators (graph_attention.py:61-65,86) and the block-diagonal A fragments
       float sq[4];
-      *reinterpret_cast<float4*>(att_w) = make_float4(sv0[0], sv0[1], sv0[2], sv0[3]);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(att_w), "f"(sv0[0]), "f"(sv0[1]), "f"(sv0[2]), "f"(sv0[3]) : "memory");
       __syncwarp();
-      sq[0] = att_r[0]; sq[1] = att_r[4]; sq[2] = att_r[2 * kAgAttDst / 4]; sq[3] = att_r[2 * kAgAttDst / 4 + 4];
+      asm volatile("ld.shared.f32 %0, [%4];\nld.shared.f32 %1, [%4+16];\nld.shared.f32 %2, [%4+288];\nld.shared.f32 %3, [%4+304];"
+                   : "=f"(sq[0]), "=f"(sq[1]), "=f"(sq[2]), "=f"(sq[3]) : "r"(att_r) : "memory");
+      static_assert(2 * kAgAttDst == 288, "slot B = slot A + 2 destinations");
       // (the scratch is rewritten one iteration later, behind the __syncwarp() that follows the MMAs)
       float p[4];
 #pragma unroll
@@ -1320,7 +1330,9 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
           __syncwarp();
           if (lane == 0) {
             __threadfence_block();
-            const bool last = atomicAdd(arrive_cnt, 1) == kAgWarps * (it_0 + 1) - 1;
+            int prev;                                         // (shared-space atomic: atomicAdd on the generic pointer compiles to ATOM.E)
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(tc_smem_u32(arrive_cnt)) : "memory");
+            const bool last = prev == kAgWarps * (it_0 + 1) - 1;
             __threadfence_block();
             if (last) issue_mma(it_0);                        // the LAST warp to finish the tile issues its MMAs
           }
@@ -1501,7 +1513,7 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
     launch_pdl(tc_edge_max_pruned_kernel<NH>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, gmax,
                (const float*)gsrc);
     if ((rc = check_launch("tc_edge_max_pruned_kernel"))) return rc;
-  } else if (A.E > (int64_t)A.N * 12)      // high in-degree: more gathers in flight per destination
+  } else if (A.E > (int64_t)A.N * 12)      // high in-degree: more gathers in flight per destination (at k = 8 both widths take 18-19 us: the pass is bound by ~0.5 L1-miss sectors per clock and SM, not by its dependent round trips)
     launch_pdl(tc_edge_max_kernel<NH, 8>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax,
                (const float*)gsrc);
   else
