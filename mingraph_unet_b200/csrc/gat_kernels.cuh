@@ -17,6 +17,10 @@ bool gat_transform_tc_supported(int N, int in_dim, int F, int heads, int passes)
 int gat_transform_tc_launch(const float* z, const float* W, int N, int in_dim, int F, int heads, int concat, void* out,
                             int out_bf16, int passes, cudaStream_t st);
 
+// bf16 score pre-pass on mma.sync (gat_tc.cu): u, s and the exact per-graph edge maximum for heads 1/2/4, in 32..256
+bool gat_tc_prepass_supported(int N, int in_dim, int heads);
+int gat_tc_prepass(const void* x, const int32_t* rowptr, const int32_t* col, int N, int64_t E, const float* W, const float* a, int in_dim,
+                   int F, int heads, int nodes_per_graph, float* s, float* gmax, float* u, cudaStream_t st);
 // persistent TMA-fed bf16 tensor-pipe transform (gat_tma_gemm.cu): z spilled as bf16, W converted to bf16 into w_bf16
 bool gat_transform_tma_supported(int N, int in_dim, int F, int heads);
 int64_t gat_transform_tma_wbytes(int in_dim, int F, int heads);

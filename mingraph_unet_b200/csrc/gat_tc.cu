@@ -47,7 +47,28 @@ struct GatTcArgs {
 // start (prologue + loads of the layer's INPUTS) while it is still running, and the successor waits for its
 // predecessor's outputs right before it first reads them -------------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// RULE: whatever the predecessor grid wrote (u, s, gmax, gsrc) is read with COHERENT loads (ld_pre below), never
+// with __ldg.  ptxas treats ld.global.nc as a load of immutable data and schedules it above griddepcontrol.wait (ACQBULK) —
+// seen in the SASS of tc_scores_kernel<4,32>, whose loads of u sat right behind PREEXIT and raced with tc_u_kernel (wrong
+// scores whenever tc_u_kernel ran long enough); a data dependency through the inline asm does not help, the wait has no operands.
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (asm volatile: ordered behind the wait by the front end; ld.global.ca: an ordinary weak load, which ptxas keeps behind ACQBULK.
+//  No line of these buffers is in this SM's L1 before the wait, so the L1-cached form is as safe as .cg and schedules like __ldg.)
+__device__ __forceinline__ float ld_pre(const float* p) {
+  float v;
+  asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ld_pre(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.ca.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_pre(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 
 // ---- PTX helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -165,15 +186,15 @@ __device__ __forceinline__ float tc_elu(float v) {
 template <int NH>
 __device__ __forceinline__ void load_scores(const float* p, float (&o)[NH]);
 template <>
-__device__ __forceinline__ void load_scores<1>(const float* p, float (&o)[1]) { o[0] = __ldg(p); }
+__device__ __forceinline__ void load_scores<1>(const float* p, float (&o)[1]) { o[0] = ld_pre(p); }
 template <>
 __device__ __forceinline__ void load_scores<2>(const float* p, float (&o)[2]) {
-  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  const float2 v = ld_pre(reinterpret_cast<const float2*>(p));
   o[0] = v.x; o[1] = v.y;
 }
 template <>
 __device__ __forceinline__ void load_scores<4>(const float* p, float (&o)[4]) {
-  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 v = ld_pre(reinterpret_cast<const float4*>(p));
   o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
 }
 
@@ -241,7 +262,7 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ u, float* __restrict__ s,
                                                         float* __restrict__ gsrc /* nullable */) {
   constexpr int IN = LPN * 8, NQ = 2 * NH;
-  const float* u_s = u;                                        // (2*NH, IN) fp32, 2 KB at most: L1/L2 resident
+  const float* u_s = u;                                        // (2*NH, IN) fp32, 2 KB at most: L1/L2 resident (read after the wait)
   // s = X U^T on mma.sync m16n8k16 (bf16 x bf16 -> f32): a warp takes 16 nodes per step.  x is bf16 already; u is split
   // into bf16 hi + lo parts (two MMAs), so the products carry ~16 mantissa bits of u and the sums are fp32.  The k index
   // of the MMA is a permutation of the feature index chosen so that every lane feeds whole 16-byte row chunks.
@@ -264,7 +285,7 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
       }
     }
   }
-  pdl_wait_prior_grid();
+  pdl_wait_prior_grid();                                       // u comes from tc_u_kernel: read it with ld_pre
   uint32_t bhi[STEPS][2], blo[STEPS][2];
 #pragma unroll
   for (int m = 0; m < STEPS; ++m)
@@ -272,7 +293,7 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
     for (int r = 0; r < 2; ++r) {
       const int jj = 2 * m + r;                                // pair register jj of this lane: chunk (jj/4)*4 + t, pair jj%4
       const int k = ((jj >> 2) * 4 + t) * 8 + 2 * (jj & 3);
-      const float u0 = g < NQ ? __ldg(u_s + g * IN + k) : 0.f, u1 = g < NQ ? __ldg(u_s + g * IN + k + 1) : 0.f;
+      const float u0 = g < NQ ? ld_pre(u_s + g * IN + k) : 0.f, u1 = g < NQ ? ld_pre(u_s + g * IN + k + 1) : 0.f;
       const __nv_bfloat16 h0 = __float2bfloat16_rn(u0), h1 = __float2bfloat16_rn(u1);
       const __nv_bfloat16 l0 = __float2bfloat16_rn(u0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(u1 - __bfloat162float(h1));
       bhi[m][r] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
@@ -338,8 +359,9 @@ __global__ void __launch_bounds__(256) tc_scores_kernel(const __nv_bfloat16* __r
 // cannot exceed it: fp32 addition is monotone, so the bound holds bit for bit and the result stays the exact maximum.
 template <int NH>
 __global__ void __launch_bounds__(256) tc_edge_first_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                         const float* __restrict__ s, int N, float* __restrict__ gmax) {
+                                                         const float* s_arg, int N, float* __restrict__ gmax) {
   constexpr int NQ = 2 * NH;
+  const float* s = s_arg;                                      // (laundered by the wait below)
   __shared__ float red[8][NH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_launch_dependents();
@@ -391,15 +413,17 @@ __global__ void __launch_bounds__(256) tc_edge_first_kernel(const int32_t* __res
 // reduction + one atomic max per (warp, graph, head) is deterministic.
 template <int NH, int UN>
 __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                       const float* __restrict__ s, int N, int nodes_per_graph,
-                                                       float* __restrict__ gmax, const float* __restrict__ gsrc /* nullable */) {
+                                                       const float* s_arg, int N, int nodes_per_graph,
+                                                       float* __restrict__ gmax, const float* gsrc_arg /* nullable */) {
   constexpr int NQ = 2 * NH;
+  const float* s = s_arg;                                      // (both laundered by the wait below)
+  const float* gsrc = gsrc_arg;
   __shared__ float red[8][NH];
   __shared__ int red_g[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   pdl_launch_dependents();
-  pdl_wait_prior_grid();                                       // s comes from tc_scores_kernel
+  pdl_wait_prior_grid();                                       // s, gsrc come from tc_scores_kernel
   // single graph: what a destination must beat to matter, and the best any source can contribute (see
   // tc_edge_first_kernel).  gmax only grows while this kernel runs; a stale read merely prunes less.
   float lowb[NH], gs[NH];
@@ -519,9 +543,11 @@ __global__ void __launch_bounds__(256) tc_edge_max_kernel(const int32_t* __restr
 // in flight).  A thread-per-destination scan gains nothing from pruning: one surviving lane keeps its warp in the loop.
 template <int NH>
 __global__ void __launch_bounds__(256) tc_edge_max_pruned_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                              const float* __restrict__ s, int N, float* __restrict__ gmax,
-                                                              const float* __restrict__ gsrc) {
+                                                              const float* s_arg, int N, float* __restrict__ gmax,
+                                                              const float* gsrc_arg) {
   constexpr int NQ = 2 * NH;
+  const float* s = s_arg;                                      // (both laundered by the wait below)
+  const float* gsrc = gsrc_arg;
   __shared__ int list[256];
   __shared__ int wcount[8];
   __shared__ float red[8][NH];
@@ -643,7 +669,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
-  pdl_wait_prior_grid();                                       // s, gmax of the pre-pass are read from here on
+  const float* s_in = A.s;
+  const float* gmax_in = A.gmax;
+  pdl_wait_prior_grid();                                       // s, gmax of the pre-pass are read from here on (ld_pre)
 
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N=F, M=128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
@@ -714,8 +742,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
           stgt[h] = 0.f; Mh[h] = 0.f; den[h] = 0.f;
         }
         if (node_ok && gl < EPI) {
-          load_scores<NH>(A.s + (size_t)j * two_h + NH, stgt);
-          load_scores<NH>(A.gmax + (size_t)g * NH, Mh);
+          load_scores<NH>(s_in + (size_t)j * two_h + NH, stgt);
+          load_scores<NH>(gmax_in + (size_t)g * NH, Mh);
 #pragma unroll
           for (int h = 0; h < NH; ++h) Mh[h] = leaky_relu(Mh[h], A.slope);
         }
@@ -742,7 +770,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
           float pv[NH];
           {
             float ssrc[NH];
-            load_scores<NH>(A.s + (size_t)srcn * two_h, ssrc);
+            load_scores<NH>(s_in + (size_t)srcn * two_h, ssrc);
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
               const float e = leaky_relu(ssrc[h] + stgt[h], A.slope);
@@ -799,7 +827,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gat_tc_kernel(const GatTcArgs A
       int last = 0;
       if (lane == 0) {
         __threadfence_block();
-        last = atomicAdd(arrive_cnt, 1) == kTcGatherWarps * (it + 1) - 1;
+        int prev;                                             // (shared-space atomic: atomicAdd on the generic pointer compiles to ATOM.E)
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(tc_smem_u32(arrive_cnt)) : "memory");
+        last = prev == kTcGatherWarps * (it + 1) - 1;
         __threadfence_block();
         if (last) issue_mma(it);
       }
@@ -1077,7 +1107,9 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   // everything above (barriers, TMEM allocation, W -> bf16 B operand) ran beside the tail of the edge-max pre-pass;
-  // its outputs (s, gmax) are read from here on
+  // its outputs (s, gmax) are read from here on, through these pointers
+  const float* s_in = A.s;
+  const float* gmax_in = A.gmax;
   pdl_wait_prior_grid();
 
   // instruction descriptor: D = f32, A = B = bf16, both K-major, N = F, M = 128
@@ -1117,7 +1149,7 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
     const uint32_t cp_off_even = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ r4) << 4));          // rows 8m + r4
     const uint32_t cp_off_odd = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ (r4 | 4)) << 4));      // rows 8m + 4 + r4
     const char* x_lane = reinterpret_cast<const char*>(A.x) + ch8 * 16;
-    const float* s_tgt_lane = A.s + NH + hd;
+    const float* s_tgt_lane = s_in + NH + hd;
     uint32_t ld_off[4];                                       // ldmatrix.x4.trans lane addresses for the 4 feature pairs (k-step 0)
 #pragma unroll
     for (int np = 0; np < 4; ++np)
@@ -1127,7 +1159,7 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
         // (shared-space addresses: through generic pointers the compiler emits LD.E / ST.E, tracked on the long scoreboard)
     const uint32_t att_w = tc_smem_u32(sm + L.att_off + warp * kAgAttBytes + r4 * kAgAttDst + ch8 * 16);                 // slot (r4, ch8), heads 0..3
     const uint32_t att_r = tc_smem_u32(sm + L.att_off + warp * kAgAttBytes + dsel * kAgAttDst + t4 * 32 + hd * 4);
-    const float M_single = npg > 0 ? 0.f : leaky_relu(__ldg(A.gmax + hd), slope);     // one graph: the shift is a lane constant
+    const float M_single = npg > 0 ? 0.f : leaky_relu(ld_pre(gmax_in + hd), slope);   // one graph: the shift is a lane constant
 
     // ---- cursor over the warp's steps (warp-uniform), loader-lane row ranges ----
     int cur_tb = (int)blockIdx.x * kAgTile, cur_step = warp, cur_it = 0;     // tile base node, step in tile, tile ordinal
@@ -1203,12 +1235,12 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
   do {                                                                                                 \
     const int ja_ = node0 + dsel, jb_ = ja_ + 2;                                                        \
     const bool va_ = node0 >= 0 && ja_ < A.N, vb_ = node0 >= 0 && jb_ < A.N;                             \
-    st2[0] = va_ ? __ldg(s_tgt_lane + (size_t)(unsigned)ja_ * (2 * NH)) : 0.f;                           \
-    st2[1] = vb_ ? __ldg(s_tgt_lane + (size_t)(unsigned)jb_ * (2 * NH)) : 0.f;                           \
+    st2[0] = va_ ? ld_pre(s_tgt_lane + (size_t)(unsigned)ja_ * (2 * NH)) : 0.f;                          \
+    st2[1] = vb_ ? ld_pre(s_tgt_lane + (size_t)(unsigned)jb_ * (2 * NH)) : 0.f;                          \
     M2[0] = M_single; M2[1] = M_single;                                                                 \
     if (npg > 0) {                                                                                      \
-      M2[0] = va_ ? leaky_relu(__ldg(A.gmax + (size_t)(ja_ / npg) * NH + hd), slope) : 0.f;              \
-      M2[1] = vb_ ? leaky_relu(__ldg(A.gmax + (size_t)(jb_ / npg) * NH + hd), slope) : 0.f;              \
+      M2[0] = va_ ? leaky_relu(ld_pre(gmax_in + (size_t)(ja_ / npg) * NH + hd), slope) : 0.f;              \
+      M2[1] = vb_ ? leaky_relu(ld_pre(gmax_in + (size_t)(jb_ / npg) * NH + hd), slope) : 0.f;              \
     }                                                                                                   \
   } while (0)
     // loader role: the lane's OWN slot, all four heads in one 16-byte gather (a quarter of the L1 requests of four 4-byte
@@ -1217,7 +1249,7 @@ __global__ void __launch_bounds__(kAgThreads, 1) gat_agg_mma_kernel(const GatTcA
   do {                                                                                                 \
     sv[0] = sv[1] = sv[2] = sv[3] = -INFINITY;                                                           \
     if (src >= 0) {                                                                                     \
-      const float4 v_ = __ldg(reinterpret_cast<const float4*>(A.s + (size_t)(unsigned)src * (2 * NH))); \
+      const float4 v_ = ld_pre(reinterpret_cast<const float4*>(s_in + (size_t)(unsigned)src * (2 * NH))); \
       sv[0] = v_.x; sv[1] = v_.y; sv[2] = v_.z; sv[3] = v_.w;                                            \
     }                                                                                                   \
     AG_LOAD_TGT(node0, st2, M2);                                                                        \
@@ -1480,10 +1512,43 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const int pdl_env = getenv("MG_GAT_PDL") ? atoi(getenv("MG_GAT_PDL")) : 1;      // 0: plain stream order (debugging)
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_env ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// The score pre-pass of a layer on bf16 node features (also used in front of the spilled-z path of gat_forward.cu):
+// u = W^T a (one block per head), s = X U^T on mma.sync, the exact per-graph edge maximum.  Chained with programmatic
+// dependent launch; the caller's next kernel follows in stream order.
+template <int NH, int LPN>
+static int launch_prepass(const __nv_bfloat16* x, const int32_t* rowptr, const int32_t* col, int N, int64_t E, const float* W,
+                          const float* a, int F, int nodes_per_graph, float* s, float* gmax, float* u, cudaStream_t st) {
+  const int G = nodes_per_graph > 0 ? N / nodes_per_graph : 1;
+  int rc;
+  const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)N * 2, 256), (int64_t)num_sms() * 8);   // 16 nodes per warp step
+  // single graph with enough edges per node: prune the edge-max scan (gsrc sits in the slack of the 256-byte gmax segment)
+  static const int prune_env = getenv("MG_GAT_PRUNE") ? atoi(getenv("MG_GAT_PRUNE")) : 1;
+  float* gsrc = (prune_env && G == 1 && NH <= 4 && E >= (int64_t)N * 12) ? gmax + 16 : nullptr;
+  tc_u_kernel<NH, LPN><<<NH, 256, 0, st>>>(W, a, F, G, u, gmax, gsrc);
+  if ((rc = check_launch("tc_u_kernel"))) return rc;
+  launch_pdl(tc_scores_kernel<NH, LPN>, dim3(sgrid), dim3(256), 0, st, x, N, (const float*)u, s, gsrc);
+  if ((rc = check_launch("tc_scores_kernel"))) return rc;
+  const int mgrid = std::min(ceil_div(N, 256), num_sms() * 6);
+  if (gsrc) {
+    launch_pdl(tc_edge_first_kernel<NH>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, gmax);
+    if ((rc = check_launch("tc_edge_first_kernel"))) return rc;
+    launch_pdl(tc_edge_max_pruned_kernel<NH>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, gmax,
+               (const float*)gsrc);
+    if ((rc = check_launch("tc_edge_max_pruned_kernel"))) return rc;
+  } else if (E > (int64_t)N * 12)      // high in-degree: more gathers in flight per destination (at k = 8 both widths take 18-19 us: the pass is bound by ~0.5 L1-miss sectors per clock and SM, not by its dependent round trips)
+    launch_pdl(tc_edge_max_kernel<NH, 8>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, nodes_per_graph, gmax,
+               (const float*)gsrc);
+  else
+    launch_pdl(tc_edge_max_kernel<NH, 4>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, nodes_per_graph, gmax,
+               (const float*)gsrc);
+  return check_launch("tc_edge_max_kernel");
 }
 
 template <int NH, int LPN>
@@ -1495,31 +1560,8 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
     set_error("gat_tc_kernel: cannot raise dynamic shared memory");
     return MG_ERR_CUDA;
   }
-  const int G = A.nodes_per_graph > 0 ? A.N / A.nodes_per_graph : 1;
   int rc;
-  const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)A.N * 2, 256), (int64_t)num_sms() * 8);   // 16 nodes per warp step
-  // single graph with enough edges per node: prune the edge-max scan (gsrc sits in the slack of the 256-byte gmax segment)
-  static const int prune_env = getenv("MG_GAT_PRUNE") ? atoi(getenv("MG_GAT_PRUNE")) : 1;
-  static const int prune_deg = getenv("MG_GAT_PRUNE_MIN_DEG") ? atoi(getenv("MG_GAT_PRUNE_MIN_DEG")) : 12;
-  float* gsrc = (prune_env && G == 1 && A.E >= (int64_t)A.N * prune_deg) ? gmax + 16 : nullptr;
-  tc_u_kernel<NH, LPN><<<NH, 256, 0, st>>>(A.W, a, A.F, G, u, gmax, gsrc);
-  if ((rc = check_launch("tc_u_kernel"))) return rc;
-  launch_pdl(tc_scores_kernel<NH, LPN>, dim3(sgrid), dim3(256), 0, st, A.x, A.N, (const float*)u, s, gsrc);
-  if ((rc = check_launch("tc_scores_kernel"))) return rc;
-  const int mgrid = std::min(ceil_div(A.N, 256), num_sms() * 6);
-  if (gsrc) {
-    launch_pdl(tc_edge_first_kernel<NH>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, gmax);
-    if ((rc = check_launch("tc_edge_first_kernel"))) return rc;
-    launch_pdl(tc_edge_max_pruned_kernel<NH>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, gmax,
-               (const float*)gsrc);
-    if ((rc = check_launch("tc_edge_max_pruned_kernel"))) return rc;
-  } else if (A.E > (int64_t)A.N * 12)      // high in-degree: more gathers in flight per destination (at k = 8 both widths take 18-19 us: the pass is bound by ~0.5 L1-miss sectors per clock and SM, not by its dependent round trips)
-    launch_pdl(tc_edge_max_kernel<NH, 8>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax,
-               (const float*)gsrc);
-  else
-    launch_pdl(tc_edge_max_kernel<NH, 4>, dim3(mgrid), dim3(256), 0, st, A.rowptr, A.col, (const float*)s, A.N, A.nodes_per_graph, gmax,
-               (const float*)gsrc);
-  if ((rc = check_launch("tc_edge_max_kernel"))) return rc;
+  if ((rc = launch_prepass<NH, LPN>(A.x, A.rowptr, A.col, A.N, A.E, A.W, a, A.F, A.nodes_per_graph, s, gmax, u, st))) return rc;
   if (NH == kAgNH && LPN * 8 == kAgIn && ag_mma_supported(LPN * 8, A.F, NH, A.concat, A.out_bf16)) {
     if (cudaFuncSetAttribute(gat_agg_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("gat_agg_mma_kernel: cannot raise dynamic shared memory");
@@ -1531,6 +1573,25 @@ static int launch_tc(const GatTcArgs& A, const float* a, float* s, float* gmax, 
   }
   launch_pdl(k, dim3(grid), dim3(kTcThreads), smem, st, A);
   return check_launch("gat_tc_kernel");
+}
+
+// bf16 score pre-pass for layers that do not run on gat_tc_kernel / gat_agg_mma_kernel (spilled z, FP32-pipe fused kernel)
+bool gat_tc_prepass_supported(int N, int in_dim, int heads) {
+  static const int enabled = getenv("MG_GAT_TC_PREPASS") ? atoi(getenv("MG_GAT_TC_PREPASS")) : 1;
+  if (!enabled || N < 4096) return false;
+  return (heads == 1 || heads == 2 || heads == 4) && (in_dim == 32 || in_dim == 64 || in_dim == 128 || in_dim == 256);
+}
+int gat_tc_prepass(const void* x, const int32_t* rowptr, const int32_t* col, int N, int64_t E, const float* W, const float* a, int in_dim,
+                   int F, int heads, int nodes_per_graph, float* s, float* gmax, float* u, cudaStream_t st) {
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  const int lpn = in_dim / 8;
+#define MG_PRE(NHH, LL) \
+  if (heads == NHH && lpn == LL) return launch_prepass<NHH, LL>(xb, rowptr, col, N, E, W, a, F, nodes_per_graph, s, gmax, u, st);
+  MG_PRE(4, 4) MG_PRE(4, 8) MG_PRE(4, 16) MG_PRE(4, 32) MG_PRE(2, 4) MG_PRE(2, 8) MG_PRE(2, 16) MG_PRE(2, 32)
+  MG_PRE(1, 4) MG_PRE(1, 8) MG_PRE(1, 16) MG_PRE(1, 32)
+#undef MG_PRE
+  set_error("gat_tc_prepass: no variant for heads=%d in=%d", heads, in_dim);
+  return MG_ERR_UNSUPPORTED;
 }
 
 // Shapes the tensor-pipe kernel takes (everything else stays on the FP32-pipe kernels).

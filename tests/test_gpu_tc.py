@@ -91,6 +91,27 @@ def test_tensor_core_aggregation_vs_oracle(mg, N, kmin, kmax, fout, concat, out_
     assert float(y.float().cpu()[deg == 0].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("fin,heads,fout", [(128, 4, 256), (256, 4, 256), (256, 4, 192), (256, 2, 256), (128, 4, 64), (32, 2, 48)])
+def test_bf16_prepass_in_front_of_the_spilled_path(mg, fin, heads, fout):
+    """bf16 layers that do not fit the fused tensor-pipe kernels still take the mma.sync score pre-pass (u, s, edge maximum chained
+    with programmatic dependent launch) in front of the aggregate + GEMM kernels.  Regression: __ldg loads of the predecessor's
+    outputs were scheduled above griddepcontrol.wait (in = 256 read u before tc_u_kernel had written it: errors ~1)."""
+    N = 5000
+    gen = torch.Generator().manual_seed(7)
+    deg = torch.randint(1, 9, (N,), generator=gen)
+    tgt = torch.arange(N).repeat_interleave(deg)
+    src = torch.randint(0, N, (int(deg.sum()),), generator=gen)
+    ei = torch.stack([src, tgt])
+    x = (torch.randn(N, fin, generator=gen) * 0.5).to(torch.bfloat16)
+    Ws, As = O.init_gat_params(fin, fout, heads, gen)
+    ref = O.gat_layer(x.float(), ei, Ws, As, 0.2, concat=False)
+    rowptr, col, _ = mg.ops.csr_from_coo(ei.cuda(), N, by_target=True)
+    for _ in range(3):                                           # back to back: the next call's pre-pass follows this call's tail
+        y = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), concat=False, slope=0.2, out_dtype=torch.float32)
+        torch.cuda.synchronize()
+        assert float((y.cpu() - ref).abs().max()) <= 8e-3
+
+
 def test_tc_batched_grid_per_graph_max(mg):
     """Block-diagonal batch of grid graphs: the softmax shift is per graph (graph_attention.py:86 per image)."""
     B, hp, wp, fin, fout, heads = 6, 32, 32, 64, 64, 4
