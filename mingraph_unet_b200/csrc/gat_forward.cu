@@ -466,7 +466,9 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   DimCfg dagg = d;
   if (in_dim > 256 && in_dim % 256 == 0) { dagg = DimCfg{4, 2}; ag.dim_parts = in_dim / 256; }
   const int grid = (int)std::min<int64_t>(ceil_div64((int64_t)N * ag.dim_parts * 32, 256), (int64_t)num_sms() * 16);
-  if (x_dtype == MG_F32) rc = gat_launch_agg_f32(ag, NH, dagg, z, save_den, grid, st);
+  if (tma_gemm && !save_den && dropout_p == 0.f && gat_agg_spill_supported(N, in_dim, heads))
+    rc = gat_agg_spill_launch(x, rowptr, col, s, gmax, z, N, in_dim, slope, nodes_per_graph, st);      // mma.sync aggregation warps
+  else if (x_dtype == MG_F32) rc = gat_launch_agg_f32(ag, NH, dagg, z, save_den, grid, st);
   else rc = gat_launch_agg_bf16(ag, NH, dagg, z, save_den, grid, st);
   if (rc) return rc;
   if (tma_gemm)

@@ -21,6 +21,10 @@ int gat_transform_tc_launch(const float* z, const float* W, int N, int in_dim, i
 bool gat_tc_prepass_supported(int N, int in_dim, int heads);
 int gat_tc_prepass(const void* x, const int32_t* rowptr, const int32_t* col, int N, int64_t E, const float* W, const float* a, int in_dim,
                    int F, int heads, int nodes_per_graph, float* s, float* gmax, float* u, cudaStream_t st);
+// tensor-core aggregation with z spilled to HBM as bf16 (gat_tc.cu): heads 4, in a multiple of 64; needs s / gmax of the pre-pass
+bool gat_agg_spill_supported(int N, int in_dim, int heads);
+int gat_agg_spill_launch(const void* x, const int32_t* rowptr, const int32_t* col, const float* s, const float* gmax, void* z_bf16, int N,
+                         int in_dim, float slope, int nodes_per_graph, cudaStream_t st);
 // persistent TMA-fed bf16 tensor-pipe transform (gat_tma_gemm.cu): z spilled as bf16, W converted to bf16 into w_bf16
 bool gat_transform_tma_supported(int N, int in_dim, int F, int heads);
 int64_t gat_transform_tma_wbytes(int in_dim, int F, int heads);

@@ -1519,6 +1519,267 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// =====================================================================================================================
+// The same tensor-core aggregation for WIDE rows (heads 4, in = 64 * nsl, bf16 storage) in front of the TMA-fed transform
+// (gat_tma_gemm.cu): z does not fit an SM's shared memory as a UMMA operand, so it is spilled to HBM as bf16 (N, heads, in)
+// — but by mma.sync warps instead of the FP32-pipe gat_aggregate_kernel.  A source row is walked in 128-byte slabs of 64
+// features: sub-item (step of 4 destinations, slab, chunk of 8 in-edges) runs the item pipeline of gat_agg_mma_kernel
+// (cp.async-staged rows, ldmatrix.trans, block-diagonal attention fragments).  With one chunk per step (in-degree <= 8)
+// the column ids, the attention scalars and the numerator fragments of a step are computed once and reused for every
+// slab.  No tiles, no TMEM: 16 aggregation warps per SM, steps dealt round-robin over all warps of the grid.
+// =====================================================================================================================
+constexpr int kSpWarps = 16;
+constexpr int kSpThreads = kSpWarps * 32;
+
+struct GatSpillArgs {
+  const __nv_bfloat16* x;
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* s;          // (N, 8)
+  const float* gmax;       // (G, 4)
+  __nv_bfloat16* z;        // (N, 4, in)
+  int N, in_dim, nodes_per_graph;
+  float slope;
+};
+
+__host__ __device__ inline int sp_smem_bytes() { return kSpWarps * (kAgStages * kAgStageBytes + kAgAttBytes) + 1024; }
+
+__device__ __forceinline__ const char* sp_row_ptr(const char* lane_base, int row, unsigned row_bytes) {
+  unsigned long long p;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"((unsigned)row), "r"(row_bytes), "l"((unsigned long long)lane_base));
+  return reinterpret_cast<const char*>(p);
+}
+
+__global__ void __launch_bounds__(kSpThreads, 1) gat_agg_spill_kernel(const GatSpillArgs A) {
+  constexpr int NH = kAgNH;
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g8 = lane >> 2, t4 = lane & 3;                    // MMA fragment coordinates
+  const int hd = g8 & 3, dsel = g8 >> 2;                      // fragment row g8 = (destination dsel, head hd); row g8 + 8 = (dsel + 2, hd)
+  const int r4 = lane >> 3, ch8 = lane & 7;                   // loader role: destination of the step, 16-byte chunk / edge slot
+  const uint32_t ring0 = tc_smem_u32(sm + (size_t)warp * kAgStages * kAgStageBytes);
+  const uint32_t att0 = tc_smem_u32(sm + (size_t)kSpWarps * kAgStages * kAgStageBytes + (size_t)warp * kAgAttBytes);
+  const uint32_t att_w = att0 + (uint32_t)(r4 * kAgAttDst + ch8 * 16);
+  const uint32_t att_r = att0 + (uint32_t)(dsel * kAgAttDst + t4 * 32 + hd * 4);
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float slope = A.slope;
+  const int npg = A.nodes_per_graph, N = A.N, in_dim = A.in_dim, nsl = in_dim >> 6;
+  const unsigned row_bytes = (unsigned)in_dim * 2u;
+  const int gw = (int)blockIdx.x * kSpWarps + warp, nw = (int)gridDim.x * kSpWarps;
+  const int nsteps = (N + 3) >> 2;
+  const uint32_t cp_off_even = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ r4) << 4));
+  const uint32_t cp_off_odd = (uint32_t)(r4 * kAgRowBytes + ((ch8 ^ (r4 | 4)) << 4));
+  const char* x_lane = reinterpret_cast<const char*>(A.x) + ch8 * 16;
+  uint32_t ld_off[4];
+#pragma unroll
+  for (int np = 0; np < 4; ++np)
+    ld_off[np] = (uint32_t)((((r4 & 1) * 8 + ch8) * kAgRowBytes) + ((((np << 1) | (r4 >> 1)) ^ ch8) << 4));
+  const uint32_t mask_d0 = dsel == 0 ? 0xffffffffu : 0u, mask_d1 = ~mask_d0;
+
+  pdl_launch_dependents();
+  const float* s_in = A.s;
+  const float* gmax_in = A.gmax;
+  pdl_wait_prior_grid();                                      // s, gmax of the pre-pass: read with ld_pre from here on
+  const float* s_tgt_lane = s_in + NH + hd;
+  const float M_single = npg > 0 ? 0.f : leaky_relu(ld_pre(gmax_in + hd), slope);
+
+  // ---- cursor over (step, slab, chunk); row pointers of the step after the next one prefetched in place ----
+  int cur_step = gw, cur_sl = 0, cur_c = 0, cur_nch = 1, cur_beg = 0, cur_end = 0, nxt_beg = 0, nxt_end = 0;
+  auto fetch_rp = [&](int step, int& b, int& e, bool doit) {
+    const int j = step < nsteps ? min(step * 4 + r4, N) : N;  // past the last node: rowptr[N] twice, an empty range
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p ld.global.nc.b32 %0, [%3];\n@p ld.global.nc.b32 %1, [%4];\n}"
+                 : "+r"(b), "+r"(e)
+                 : "r"(doit ? 1 : 0), "l"(A.rowptr + j), "l"(A.rowptr + min(j + 1, N)));
+  };
+  fetch_rp(cur_step, cur_beg, cur_end, true);
+  fetch_rp(cur_step + nw, nxt_beg, nxt_end, true);
+  cur_nch = max(1, __reduce_max_sync(kFull, (cur_end - cur_beg + 7) >> 3));
+  auto advance = [&]() {
+    bool adv_step = false;
+    if (++cur_c >= cur_nch) {
+      cur_c = 0;
+      if (++cur_sl >= nsl) {
+        cur_sl = 0;
+        cur_step += nw;
+        adv_step = true;
+      }
+    }
+    cur_beg = adv_step ? nxt_beg : cur_beg;
+    cur_end = adv_step ? nxt_end : cur_end;
+    fetch_rp(cur_step + nw, nxt_beg, nxt_end, adv_step);
+    if (adv_step) cur_nch = max(1, __reduce_max_sync(kFull, (cur_end - cur_beg + 7) >> 3));
+  };
+  auto load_src = [&]() -> int {                              // loader lane: source node of its slot (-1: no edge)
+    const int k = cur_beg + 8 * cur_c + ch8;
+    return (cur_step < nsteps && k < cur_end) ? __ldg(A.col + k) : -1;
+  };
+  auto issue_rows = [&](int src, int sl, uint32_t stg) {      // 32 slab rows of 128 B into ring stage stg (zero-filled where empty)
+    const uint32_t sb = ring0 + stg * kAgStageBytes;
+    const char* xs = x_lane + sl * 128;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int sn = __shfl_sync(kFull, src, i * 4 + r4);
+      ag_cp_async16(sb + (uint32_t)(i * 4 * kAgRowBytes) + ((i & 1) ? cp_off_odd : cp_off_even), sp_row_ptr(xs, max(sn, 0), row_bytes),
+                    sn >= 0 ? 16u : 0u);
+    }
+  };
+  auto load_att = [&](int src, int node0, float (&sv)[4], float (&st2)[2], float (&M2)[2]) {
+    sv[0] = sv[1] = sv[2] = sv[3] = -INFINITY;
+    if (src >= 0) {
+      const float4 v = ld_pre(reinterpret_cast<const float4*>(s_in + (size_t)(unsigned)src * (2 * NH)));
+      sv[0] = v.x; sv[1] = v.y; sv[2] = v.z; sv[3] = v.w;
+    }
+    const int ja = node0 + dsel, jb = ja + 2;
+    const bool va = node0 >= 0 && ja < N, vb = node0 >= 0 && jb < N;
+    st2[0] = va ? ld_pre(s_tgt_lane + (size_t)(unsigned)ja * (2 * NH)) : 0.f;
+    st2[1] = vb ? ld_pre(s_tgt_lane + (size_t)(unsigned)jb * (2 * NH)) : 0.f;
+    M2[0] = M_single; M2[1] = M_single;
+    if (npg > 0) {
+      M2[0] = va ? leaky_relu(ld_pre(gmax_in + (size_t)(ja / npg) * NH + hd), slope) : 0.f;
+      M2[1] = vb ? leaky_relu(ld_pre(gmax_in + (size_t)(jb / npg) * NH + hd), slope) : 0.f;
+    }
+  };
+
+  // ---- software pipeline: sub-item n on the tensor cores, rows + scalars of n+1 and column ids of n+2 in flight ----
+  int node0_0 = cur_step < nsteps ? cur_step * 4 : -1, sl_0 = 0;
+  bool first_0 = true, last_0 = cur_nch == 1, reuse_0 = false;
+  int src0 = load_src();
+  float sv0[4], st0[2], M0[2];
+  load_att(src0, node0_0, sv0, st0, M0);
+  if (node0_0 >= 0) issue_rows(src0, sl_0, 0u);
+  ag_cp_commit();
+  advance();
+  int node0_1 = cur_step < nsteps ? cur_step * 4 : -1, sl_1 = cur_sl;
+  bool first_1 = cur_c == 0, last_1 = cur_c == cur_nch - 1, reuse_1 = cur_nch == 1 && cur_sl > 0;
+  int src1 = reuse_1 ? src0 : load_src();
+  float acc[8][4];
+  float den0 = 0.f, den1 = 0.f, psum0 = 0.f, psum1 = 0.f;
+  uint32_t hiA = 0, loA = 0, hiB = 0, loB = 0;                // numerator fragments of the step's chunk (kept across slabs)
+  uint32_t stage = 0;
+  while (node0_0 >= 0) {
+    // A. rows of sub-item n+1
+    if (node0_1 >= 0) issue_rows(src1, sl_1, stage ^ 1u);
+    ag_cp_commit();
+    // B. column ids of sub-item n+2
+    advance();
+    const int node0_2 = cur_step < nsteps ? cur_step * 4 : -1, sl_2 = cur_sl;
+    const bool first_2 = cur_c == 0, last_2 = cur_c == cur_nch - 1, reuse_2 = cur_nch == 1 && cur_sl > 0;
+    const int src2 = reuse_2 ? src1 : load_src();
+    // C. attention scalars of sub-item n+1 (the same as sub-item n's when it is another slab of the same chunk)
+    float sv1[4], st1[2], M1[2];
+    if (reuse_1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sv1[i] = sv0[i];
+      st1[0] = st0[0]; st1[1] = st0[1]; M1[0] = M0[0]; M1[1] = M0[1];
+    } else {
+      load_att(src1, node0_1, sv1, st1, M1);
+    }
+    // D. rows of sub-item n have landed
+    ag_cp_wait<1>();
+    __syncwarp();
+    if (first_0) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+      den0 = den1 = 0.f;
+    }
+    // E. attention numerators (graph_attention.py:61-65,86) and the block-diagonal A fragments
+    if (!reuse_0) {
+      float sq[4];
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(att_w), "f"(sv0[0]), "f"(sv0[1]), "f"(sv0[2]), "f"(sv0[3]) : "memory");
+      __syncwarp();
+      asm volatile("ld.shared.f32 %0, [%4];\nld.shared.f32 %1, [%4+16];\nld.shared.f32 %2, [%4+288];\nld.shared.f32 %3, [%4+304];"
+                   : "=f"(sq[0]), "=f"(sq[1]), "=f"(sq[2]), "=f"(sq[3]) : "r"(att_r) : "memory");
+      float p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float e = sq[i] + st0[i >> 1];
+        p[i] = tc_ex2((fmaxf(e, e * slope) - M0[i >> 1]) * kLog2e);                   // LeakyReLU (0 <= slope <= 1); empty slot: ex2(-inf) = 0
+      }
+      psum0 = p[0] + p[1];
+      psum1 = p[2] + p[3];
+      ag_split(p[0], p[1], hiA, loA);
+      ag_split(p[2], p[3], hiB, loB);
+    }
+    den0 += psum0;
+    den1 += psum1;
+    const uint32_t sb = ring0 + stage * kAgStageBytes;
+    {
+      const uint32_t a0h = hiA & mask_d0, a0l = loA & mask_d0, a2h = hiA & mask_d1, a2l = loA & mask_d1;
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        ag_ldmatrix_x4_trans(sb + ld_off[np], b);
+        ag_mma_bf16(acc[2 * np], a0h, 0u, a2h, 0u, b[0], b[1]);
+        ag_mma_bf16(acc[2 * np], a0l, 0u, a2l, 0u, b[0], b[1]);
+        ag_mma_bf16(acc[2 * np + 1], a0h, 0u, a2h, 0u, b[2], b[3]);
+        ag_mma_bf16(acc[2 * np + 1], a0l, 0u, a2l, 0u, b[2], b[3]);
+      }
+      const uint32_t a1h = hiB & mask_d0, a1l = loB & mask_d0, a3h = hiB & mask_d1, a3l = loB & mask_d1;
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        ag_ldmatrix_x4_trans(sb + 16 * kAgRowBytes + ld_off[np], b);
+        ag_mma_bf16(acc[2 * np], 0u, a1h, 0u, a3h, b[0], b[1]);
+        ag_mma_bf16(acc[2 * np], 0u, a1l, 0u, a3l, b[0], b[1]);
+        ag_mma_bf16(acc[2 * np + 1], 0u, a1h, 0u, a3h, b[2], b[3]);
+        ag_mma_bf16(acc[2 * np + 1], 0u, a1l, 0u, a3l, b[2], b[3]);
+      }
+    }
+    __syncwarp();                                             // every lane has read the stage: the next issue may refill it
+    // F. last chunk of the (step, slab): softmax denominators, the slab's 64 columns of z -> HBM (bf16)
+    if (last_0) {
+      float d0 = den0, d1 = den1;
+      d0 += __shfl_xor_sync(kFull, d0, 1); d1 += __shfl_xor_sync(kFull, d1, 1);
+      d0 += __shfl_xor_sync(kFull, d0, 2); d1 += __shfl_xor_sync(kFull, d1, 2);
+      const float inv0 = ag_rcp(d0 + 1e-10f), inv1 = ag_rcp(d1 + 1e-10f);             // graph_attention.py:96
+      const int na = node0_0 + dsel, nb = na + 2;
+      char* za = reinterpret_cast<char*>(A.z) + (((size_t)na * NH + hd) * in_dim + sl_0 * 64 + 2 * t4) * 2;
+      char* zb = za + (size_t)2 * NH * in_dim * 2;
+      if (na < N) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          *reinterpret_cast<uint32_t*>(za + nt * 16) = ag_pack_bf16(acc[nt][0] * inv0, acc[nt][1] * inv0);
+      }
+      if (nb < N) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          *reinterpret_cast<uint32_t*>(zb + nt * 16) = ag_pack_bf16(acc[nt][2] * inv1, acc[nt][3] * inv1);
+      }
+    }
+    // rotate the pipeline
+    node0_0 = node0_1; sl_0 = sl_1; first_0 = first_1; last_0 = last_1; reuse_0 = reuse_1; src0 = src1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sv0[i] = sv1[i];
+    st0[0] = st1[0]; st0[1] = st1[1]; M0[0] = M1[0]; M0[1] = M1[1];
+    node0_1 = node0_2; sl_1 = sl_2; first_1 = first_2; last_1 = last_2; reuse_1 = reuse_2; src1 = src2;
+    stage ^= 1u;
+  }
+  ag_cp_wait<0>();
+}
+
+bool gat_agg_spill_supported(int N, int in_dim, int heads) {
+  static const int enabled = getenv("MG_GAT_AGG_SPILL_MMA") ? atoi(getenv("MG_GAT_AGG_SPILL_MMA")) : 1;
+  return enabled && heads == kAgNH && in_dim >= 64 && in_dim % 64 == 0 && in_dim <= 1024 && N >= 4096;
+}
+
+// z (N, 4, in) bf16 <- attention-weighted neighbour sums; s, gmax from the pre-pass launched before on the same stream
+int gat_agg_spill_launch(const void* x, const int32_t* rowptr, const int32_t* col, const float* s, const float* gmax, void* z_bf16, int N,
+                         int in_dim, float slope, int nodes_per_graph, cudaStream_t st) {
+  GatSpillArgs A;
+  A.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  A.rowptr = rowptr; A.col = col; A.s = s; A.gmax = gmax; A.z = reinterpret_cast<__nv_bfloat16*>(z_bf16);
+  A.N = N; A.in_dim = in_dim; A.nodes_per_graph = nodes_per_graph; A.slope = slope;
+  if (cudaFuncSetAttribute(gat_agg_spill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    set_error("gat_agg_spill_kernel: cannot raise dynamic shared memory");
+    return MG_ERR_CUDA;
+  }
+  const int grid = std::min(ceil_div(ceil_div(N, 4), kSpWarps), num_sms());
+  launch_pdl(gat_agg_spill_kernel, dim3(grid), dim3(kSpThreads), (size_t)sp_smem_bytes(), st, A);
+  return check_launch("gat_agg_spill_kernel");
+}
+
+
 // The score pre-pass of a layer on bf16 node features (also used in front of the spilled-z path of gat_forward.cu):
 // u = W^T a (one block per head), s = X U^T on mma.sync, the exact per-graph edge maximum.  Chained with programmatic
 // dependent launch; the caller's next kernel follows in stream order.

@@ -112,6 +112,43 @@ def test_bf16_prepass_in_front_of_the_spilled_path(mg, fin, heads, fout):
         assert float((y.cpu() - ref).abs().max()) <= 8e-3
 
 
+@pytest.mark.parametrize("N,kmin,kmax,fin,fout,G", [
+    (5000, 0, 20, 128, 256, 1),                                # up to 3 chunks of 8 edges x 2 slabs of 64 features, isolated nodes
+    (4099, 8, 8, 256, 128, 1),                                 # one chunk per step: numerators reused across the 4 slabs; ragged last step
+    (9000, 1, 3, 512, 64, 1),                                  # 8 slabs, mostly empty slots (generic score pre-pass: in = 512)
+    (4096, 17, 33, 256, 128, 1),
+    (8000, 0, 9, 64, 256, 1),                                  # a single slab with a wide transform
+    (8192, 4, 4, 128, 128, 2),                                 # two graphs with different logit scales: per-graph softmax shift
+    (5003, 0, 40, 192, 256, 1),                                # 3 slabs
+])
+def test_wide_row_tensor_core_aggregation_vs_oracle(mg, N, kmin, kmax, fin, fout, G):
+    """gat_agg_spill_kernel (heads 4, in a multiple of 64, bf16): mma.sync aggregation warps spill z (N, heads, in) as bf16 for the
+    TMA-fed transform.  Every case has 2 N in F heads >= 1e9, the threshold below which the layer stays on the FP32-pipe kernels."""
+    assert 2.0 * N * fin * fout * 4 >= 1e9
+    gen = torch.Generator().manual_seed(N + kmax + fin)
+    deg = torch.randint(kmin, kmax + 1, (N,), generator=gen)
+    deg[::13] = 0
+    tgt = torch.arange(N).repeat_interleave(deg)
+    npg = N // G
+    src = torch.randint(0, npg, (int(deg.sum()),), generator=gen) + (tgt // npg) * npg        # edges stay inside their graph
+    ei = torch.stack([src, tgt])
+    x = torch.randn(N, fin, generator=gen) * 0.5
+    if G > 1:
+        x[npg:] *= 3.0
+    x = x.to(torch.bfloat16)
+    Ws, As = O.init_gat_params(fin, fout, 4, gen)
+    rowptr, col, _ = mg.ops.csr_from_coo(ei.cuda(), N, by_target=True)
+    y = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), concat=False, slope=0.2, out_dtype=torch.float32,
+                           nodes_per_graph=(npg if G > 1 else 0)).cpu()
+    if G == 1:
+        ref = O.gat_layer(x.float(), ei, Ws, As, 0.2, concat=False)
+    else:
+        ref = torch.cat([O.gat_layer(x[g * npg:(g + 1) * npg].float(), ei[:, (tgt // npg) == g] - g * npg, Ws, As, 0.2, concat=False)
+                         for g in range(G)])
+    assert float((y - ref).abs().max()) <= TOL_BF16
+    assert float(y[deg == 0].abs().max()) == 0.0
+
+
 def test_tc_batched_grid_per_graph_max(mg):
     """Block-diagonal batch of grid graphs: the softmax shift is per graph (graph_attention.py:86 per image)."""
     B, hp, wp, fin, fout, heads = 6, 32, 32, 64, 64, 4

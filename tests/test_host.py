@@ -307,3 +307,21 @@ def test_numa_binding_never_raises():
     if msg.startswith("not bound"):
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def test_pdl_kernels_read_predecessor_outputs_with_ordinary_loads():
+    """Source lint for csrc/gat_tc.cu, the only file that chains kernels with programmatic dependent launch: ``__ldg`` (ld.global.nc)
+    may be scheduled above ``griddepcontrol.wait`` by ptxas, so it is reserved for the layer's inputs; everything a predecessor
+    grid wrote (u, s, gmax, gsrc) goes through ``ld_pre``.  (The ordering itself is checked on the GPU by
+    tests/test_gpu_tc.py::test_bf16_prepass_in_front_of_the_spilled_path.)"""
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "mingraph_unet_b200", "csrc", "gat_tc.cu")).read()
+    src = re.sub(r"//[^\n]*", "", src)                                       # comments mention __ldg too
+    allowed = ("x +", "x_lane", "A.x", "rowptr", "col +", "A.col", "Wh +", "ah +", "A.W")
+    calls = re.findall(r"__ldg\(([^;]*?)\)\s*[;:,)]", src)
+    assert len(calls) >= 20
+    for arg in calls:
+        assert any(tok in arg for tok in allowed), f"__ldg on something that is not a layer input: {arg!r}"
+        for bad in ("u_s", "s_in", "gmax", "gsrc", "s_tgt_lane", "A.s", "(s +"):
+            assert bad not in arg, f"__ldg on a predecessor grid's output: {arg!r}"
+    assert src.count("ld_pre(") >= 10
