@@ -7,7 +7,7 @@ import mingraph_unet_b200 as mg
 cases = [  # N, kmin, kmax, in, F, graphs
     # (all with 2 N in F heads >= 1e9, the TMA-GEMM threshold: below it the layer takes the FP32-pipe kernels)
     (5000, 0, 20, 128, 256, 1), (4099, 8, 8, 256, 128, 1), (9000, 1, 3, 512, 64, 1), (4096, 17, 33, 256, 128, 1), (8000, 0, 9, 64, 256, 1),
-    (4096 * 2, 4, 4, 128, 128, 2), (5003, 0, 40, 192, 256, 1), (4097, 9, 9, 128, 256, 1)]
+    (4096 * 2, 4, 4, 128, 128, 2), (5003, 0, 40, 192, 256, 1), (4097, 9, 9, 128, 256, 1), (8192, 2, 6, 512, 64, 2)]
 for N, kmin, kmax, fin, fout, G in cases:
     gen = torch.Generator().manual_seed(N + kmax + fin)
     deg = torch.randint(kmin, kmax + 1, (N,), generator=gen); deg[::13] = 0
