@@ -149,6 +149,25 @@ def test_wide_row_tensor_core_aggregation_vs_oracle(mg, N, kmin, kmax, fin, fout
     assert float(y[deg == 0].abs().max()) == 0.0
 
 
+def test_wide_row_aggregation_concat_and_bf16_output(mg):
+    """Same path with concatenated heads and bf16 output (the transform's epilogue variants behind the spilled z)."""
+    N, fin, fout = 6000, 256, 128
+    gen = torch.Generator().manual_seed(11)
+    deg = torch.randint(0, 12, (N,), generator=gen)
+    tgt = torch.arange(N).repeat_interleave(deg)
+    src = torch.randint(0, N, (int(deg.sum()),), generator=gen)
+    ei = torch.stack([src, tgt])
+    x = (torch.randn(N, fin, generator=gen) * 0.5).to(torch.bfloat16)
+    Ws, As = O.init_gat_params(fin, fout, 4, gen)
+    assert 2.0 * N * fin * fout * 4 >= 1e9
+    rowptr, col, _ = mg.ops.csr_from_coo(ei.cuda(), N, by_target=True)
+    for concat, out_dtype in ((True, torch.float32), (True, torch.bfloat16), (False, torch.bfloat16)):
+        ref = O.gat_layer(x.float(), ei, Ws, As, 0.2, concat=concat)
+        y = mg.ops.gat_forward(x.cuda(), rowptr, col, Ws.cuda(), As.cuda(), concat=concat, slope=0.2, out_dtype=out_dtype).float().cpu()
+        assert float((y - ref).abs().max()) <= TOL_BF16, (concat, out_dtype)
+        assert float(y[deg == 0].abs().max()) == 0.0
+
+
 def test_tc_batched_grid_per_graph_max(mg):
     """Block-diagonal batch of grid graphs: the softmax shift is per graph (graph_attention.py:86 per image)."""
     B, hp, wp, fin, fout, heads = 6, 32, 32, 64, 64, 4
