@@ -1791,7 +1791,8 @@ static int launch_prepass(const __nv_bfloat16* x, const int32_t* rowptr, const i
   const int sgrid = (int)std::min<int64_t>(ceil_div64((int64_t)N * 2, 256), (int64_t)num_sms() * 8);   // 16 nodes per warp step
   // single graph with enough edges per node: prune the edge-max scan (gsrc sits in the slack of the 256-byte gmax segment)
   static const int prune_env = getenv("MG_GAT_PRUNE") ? atoi(getenv("MG_GAT_PRUNE")) : 1;
-  float* gsrc = (prune_env && G == 1 && NH <= 4 && E >= (int64_t)N * 12) ? gmax + 16 : nullptr;
+  static const int prune_deg = getenv("MG_GAT_PRUNE_MIN_DEG") ? atoi(getenv("MG_GAT_PRUNE_MIN_DEG")) : 12;
+  float* gsrc = (prune_env && G == 1 && NH <= 4 && E >= (int64_t)N * prune_deg) ? gmax + 16 : nullptr;
   tc_u_kernel<NH, LPN><<<NH, 256, 0, st>>>(W, a, F, G, u, gmax, gsrc);
   if ((rc = check_launch("tc_u_kernel"))) return rc;
   launch_pdl(tc_scores_kernel<NH, LPN>, dim3(sgrid), dim3(256), 0, st, x, N, (const float*)u, s, gsrc);
@@ -1800,8 +1801,12 @@ static int launch_prepass(const __nv_bfloat16* x, const int32_t* rowptr, const i
   if (gsrc) {
     launch_pdl(tc_edge_first_kernel<NH>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, gmax);
     if ((rc = check_launch("tc_edge_first_kernel"))) return rc;
-    launch_pdl(tc_edge_max_pruned_kernel<NH>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, gmax,
-               (const float*)gsrc);
+    if (E >= (int64_t)N * 12)          // many in-edges: survivors compacted per block and scanned by whole warps
+      launch_pdl(tc_edge_max_pruned_kernel<NH>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, gmax,
+                 (const float*)gsrc);
+    else                               // few in-edges: a surviving thread scans its own 8 edges in one round of loads
+      launch_pdl(tc_edge_max_kernel<NH, 8>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, nodes_per_graph, gmax,
+                 (const float*)gsrc);
     if ((rc = check_launch("tc_edge_max_pruned_kernel"))) return rc;
   } else if (E > (int64_t)N * 12)      // high in-degree: more gathers in flight per destination (at k = 8 both widths take 18-19 us: the pass is bound by ~0.5 L1-miss sectors per clock and SM, not by its dependent round trips)
     launch_pdl(tc_edge_max_kernel<NH, 8>, dim3(mgrid), dim3(256), 0, st, rowptr, col, (const float*)s, N, nodes_per_graph, gmax,
