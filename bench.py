@@ -17,6 +17,9 @@ The same invocation also measures, as `extra` keys of the same JSON line, the tw
               the whole batch on rank 0 alone, measured in the same run);
   extra.cfg5  configs[4]: training step (forward + backward scatter + NCCL gradient all-reduce + Adam) at 512x512,
               4 images per GPU (= batch 32 on 8 GPUs; weak scaling; efficiency against rank 0 alone without all-reduce).
+  extra.cfg4  configs[3]: a few points of the graph-layer micro-benchmark sweep (N = 262 144 nodes, k = 8 / 32, F = 64 / 128,
+              4 heads, bf16; one GAT layer through the C ABI, L2 flushed before every timed launch) on rank 0: ms, edges/s,
+              SpMM gather-model GB/s and its fraction of the measured HBM peak (the full sweep: tools/sweep.py).
 
 Prints ONE JSON line (rank 0).  ``--impl reference`` times the UNTOUCHED reference classes on the host cores
 (oracle/_ref, copied there by __graft_entry__.build(); falls back to the oracle port oracle/restate.py, labelled, when
@@ -634,8 +637,59 @@ def solo_on_rank0(ctx, fn):
     return out
 
 
+CFG4_POINTS = ((262144, 8, 64), (262144, 32, 64), (262144, 8, 128), (262144, 32, 128))     # (nodes, in-degree, in = out features)
+
+
+def gat_layer_points(dev, iters=8):
+    """configs[3] points: one multi-head GAT layer (4 heads averaged, in = out = F, bf16 storage) on a random graph with fixed
+    in-degree, timed with CUDA events on the launching stream after warm-up, L2 flushed (256 MB write) before every launch.
+    Same generator and byte models as tools/sweep.py."""
+    import torch
+    from mingraph_unet_b200 import _lib, ops
+    peak, _ = measured_peak()
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    rows = []
+    for N, k, F in CFG4_POINTS:
+        gen = torch.Generator().manual_seed(0)
+        tgt = torch.arange(N).repeat_interleave(k)
+        src = torch.randint(0, N, (N * k,), generator=gen)
+        rowptr, col, _ = ops.csr_from_coo(torch.stack([src, tgt]).to(dev), N, by_target=True)
+        gen = torch.Generator().manual_seed(1)
+        x = torch.randn(N, F, generator=gen).to(dev).to(torch.bfloat16)
+        bound = 1.414 * (6.0 / (F + F)) ** 0.5
+        W = ((torch.rand(4, F, F, generator=gen) * 2 - 1) * bound).to(dev)
+        bound_a = 1.414 * (6.0 / (2 * F + 1)) ** 0.5
+        a = ((torch.rand(4, 2 * F, generator=gen) * 2 - 1) * bound_a).to(dev)
+        fn = lambda: ops.gat_forward(x, rowptr, col, W, a, concat=False, slope=0.2, out_dtype=torch.bfloat16)  # noqa: E731
+        for _ in range(3):
+            fn()
+        launches0 = _lib.launch_count()
+        ts = []
+        for _ in range(iters):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = statistics.median(ts)
+        E = N * k
+        comp = 2 * N * F * 2 + 4 * (E + N + 1) + 8 * 4 * N
+        gath = E * F * 2 + N * F * 2 + 4 * (E + N + 1)
+        rows.append({"N": N, "k": k, "F": F, "heads": 4, "E": E, "ms": ms, "edges_per_s": E / (ms * 1e-3),
+                     "compulsory_gbs": comp / (ms * 1e-3) / 1e9, "compulsory_frac_of_hbm_peak": comp / (ms * 1e-3) / 1e9 / peak,
+                     "gather_model_gbs": gath / (ms * 1e-3) / 1e9, "gather_model_frac_of_hbm_peak": gath / (ms * 1e-3) / 1e9 / peak,
+                     "gpu_launches_per_layer": (_lib.launch_count() - launches0) // iters})
+        del x, W, a, rowptr, col
+    del flush
+    torch.cuda.empty_cache()
+    return rows
+
+
 def extras(ctx, steps, warmup):
-    """extra.cfg3 (configs[2], strong scaling) and extra.cfg5 (configs[4], training step) of the same invocation."""
+    """extra.cfg3 (configs[2], strong scaling), extra.cfg5 (configs[4], training step) and extra.cfg4 (configs[3] points) of the
+    same invocation."""
     import gc
     import torch
     world = ctx.world
@@ -674,6 +728,14 @@ def extras(ctx, steps, warmup):
             "efficiency": t["images_per_s"] / (world * one["images_per_s"]),
             "unpool_backward_ms": t["bwd_ms"], "unpool_backward_frac_of_hbm_peak": bwd_bytes / (t["bwd_ms"] * 1e-3) / 1e9 / peak,
             "gpu_launches": int(t["launches"]), "kernels_per_step": t["trainer_launches"],
+        }
+    gc.collect(); torch.cuda.empty_cache()
+    pts = solo_on_rank0(ctx, lambda: gat_layer_points(ctx.dev))
+    if ctx.rank == 0:
+        out["cfg4"] = {
+            "workload": "configs[3] points: one GAT layer (4 heads averaged, in = out = F, bf16 storage, random graph of fixed in-degree k) "
+                        "on one GPU; median of 8 launches, L2 flushed before each; bytes as in tools/sweep.py",
+            "hbm_peak_gbs": measured_peak()[0], "points": pts,
         }
     gc.collect(); torch.cuda.empty_cache()
     return out
