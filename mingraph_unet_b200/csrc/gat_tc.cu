@@ -1035,6 +1035,12 @@ __device__ __forceinline__ void ag_mma_bf16(float (&c)[4], uint32_t a0, uint32_t
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// same, accumulators start from zero (the first MMA of a single-chunk step: no zeroing pass over the 32 accumulators)
+__device__ __forceinline__ void ag_mma_bf16_zero(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
 __device__ __forceinline__ uint32_t ag_pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -1044,6 +1050,40 @@ __device__ __forceinline__ void ag_split(float a, float b, uint32_t& hi, uint32_
   const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
   hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
   lo = ag_pack_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
+}
+// The 32 HMMAs of an item: the stage's 32 source rows (B operand through ldmatrix.trans) times the block-diagonal attention
+// fragments (A operand, bf16 hi + lo parts).  k-step 0: slots of destinations 0 (k 0-7) and 1 (k 8-15) feed fragment rows 0-7
+// only; k-step 1: destinations 2, 3 feed rows 8-15.  ZERO: the accumulators start from 0 (single-chunk step).
+template <bool ZERO>
+__device__ __forceinline__ void ag_item_mma(float (&acc)[8][4], uint32_t sb, const uint32_t (&ld_off)[4], uint32_t hiA, uint32_t loA,
+                                            uint32_t hiB, uint32_t loB, uint32_t mask_d0, uint32_t mask_d1) {
+  const uint32_t a0h = hiA & mask_d0, a0l = loA & mask_d0, a2h = hiA & mask_d1, a2l = loA & mask_d1;
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    uint32_t b[4];
+    ag_ldmatrix_x4_trans(sb + ld_off[np], b);
+    if (ZERO) ag_mma_bf16_zero(acc[2 * np], a0h, 0u, a2h, 0u, b[0], b[1]);
+    else ag_mma_bf16(acc[2 * np], a0h, 0u, a2h, 0u, b[0], b[1]);
+    ag_mma_bf16(acc[2 * np], a0l, 0u, a2l, 0u, b[0], b[1]);
+    if (ZERO) ag_mma_bf16_zero(acc[2 * np + 1], a0h, 0u, a2h, 0u, b[2], b[3]);
+    else ag_mma_bf16(acc[2 * np + 1], a0h, 0u, a2h, 0u, b[2], b[3]);
+    ag_mma_bf16(acc[2 * np + 1], a0l, 0u, a2l, 0u, b[2], b[3]);
+  }
+  const uint32_t a1h = hiB & mask_d0, a1l = loB & mask_d0, a3h = hiB & mask_d1, a3l = loB & mask_d1;
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    uint32_t b[4];
+    ag_ldmatrix_x4_trans(sb + 16 * kAgRowBytes + ld_off[np], b);
+    ag_mma_bf16(acc[2 * np], 0u, a1h, 0u, a3h, b[0], b[1]);
+    ag_mma_bf16(acc[2 * np], 0u, a1l, 0u, a3l, b[0], b[1]);
+    ag_mma_bf16(acc[2 * np + 1], 0u, a1h, 0u, a3h, b[2], b[3]);
+    ag_mma_bf16(acc[2 * np + 1], 0u, a1l, 0u, a3l, b[2], b[3]);
+  }
+}
+// softmax denominators of the lane's two destinations over the 8 slots each (the 4 lanes of a fragment row hold 2 slots each)
+__device__ __forceinline__ void ag_quad_sum(float& d0, float& d1) {
+  d0 += __shfl_xor_sync(kFull, d0, 1); d1 += __shfl_xor_sync(kFull, d1, 1);
+  d0 += __shfl_xor_sync(kFull, d0, 2); d1 += __shfl_xor_sync(kFull, d1, 2);
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -1678,7 +1718,9 @@ __global__ void __launch_bounds__(kSpThreads, 1) gat_agg_spill_kernel(const GatS
     // D. rows of sub-item n have landed
     ag_cp_wait<1>();
     __syncwarp();
-    if (first_0) {
+    // single-chunk steps (every in-degree <= 8): numerators normalised once, accumulators start from zero (see gat_agg_mma_kernel)
+    const bool single = first_0 && last_0;
+    if (first_0 && !single) {
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
       den0 = den1 = 0.f;
@@ -1698,53 +1740,52 @@ __global__ void __launch_bounds__(kSpThreads, 1) gat_agg_spill_kernel(const GatS
       }
       psum0 = p[0] + p[1];
       psum1 = p[2] + p[3];
+      if (single) {                                           // (a reused fragment belongs to a single-chunk step too)
+        float d0 = psum0, d1 = psum1;
+        ag_quad_sum(d0, d1);
+        const float i0 = ag_rcp(d0 + 1e-10f), i1 = ag_rcp(d1 + 1e-10f);              // graph_attention.py:96
+        p[0] *= i0; p[1] *= i0; p[2] *= i1; p[3] *= i1;
+      }
       ag_split(p[0], p[1], hiA, loA);
       ag_split(p[2], p[3], hiB, loB);
     }
     den0 += psum0;
     den1 += psum1;
     const uint32_t sb = ring0 + stage * kAgStageBytes;
-    {
-      const uint32_t a0h = hiA & mask_d0, a0l = loA & mask_d0, a2h = hiA & mask_d1, a2l = loA & mask_d1;
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t b[4];
-        ag_ldmatrix_x4_trans(sb + ld_off[np], b);
-        ag_mma_bf16(acc[2 * np], a0h, 0u, a2h, 0u, b[0], b[1]);
-        ag_mma_bf16(acc[2 * np], a0l, 0u, a2l, 0u, b[0], b[1]);
-        ag_mma_bf16(acc[2 * np + 1], a0h, 0u, a2h, 0u, b[2], b[3]);
-        ag_mma_bf16(acc[2 * np + 1], a0l, 0u, a2l, 0u, b[2], b[3]);
-      }
-      const uint32_t a1h = hiB & mask_d0, a1l = loB & mask_d0, a3h = hiB & mask_d1, a3l = loB & mask_d1;
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t b[4];
-        ag_ldmatrix_x4_trans(sb + 16 * kAgRowBytes + ld_off[np], b);
-        ag_mma_bf16(acc[2 * np], 0u, a1h, 0u, a3h, b[0], b[1]);
-        ag_mma_bf16(acc[2 * np], 0u, a1l, 0u, a3l, b[0], b[1]);
-        ag_mma_bf16(acc[2 * np + 1], 0u, a1h, 0u, a3h, b[2], b[3]);
-        ag_mma_bf16(acc[2 * np + 1], 0u, a1l, 0u, a3l, b[2], b[3]);
-      }
-    }
+    if (single) ag_item_mma<true>(acc, sb, ld_off, hiA, loA, hiB, loB, mask_d0, mask_d1);
+    else ag_item_mma<false>(acc, sb, ld_off, hiA, loA, hiB, loB, mask_d0, mask_d1);
     __syncwarp();                                             // every lane has read the stage: the next issue may refill it
     // F. last chunk of the (step, slab): softmax denominators, the slab's 64 columns of z -> HBM (bf16)
     if (last_0) {
-      float d0 = den0, d1 = den1;
-      d0 += __shfl_xor_sync(kFull, d0, 1); d1 += __shfl_xor_sync(kFull, d1, 1);
-      d0 += __shfl_xor_sync(kFull, d0, 2); d1 += __shfl_xor_sync(kFull, d1, 2);
-      const float inv0 = ag_rcp(d0 + 1e-10f), inv1 = ag_rcp(d1 + 1e-10f);             // graph_attention.py:96
+      float inv0 = 1.f, inv1 = 1.f;
+      if (!single) {
+        float d0 = den0, d1 = den1;
+        ag_quad_sum(d0, d1);
+        inv0 = ag_rcp(d0 + 1e-10f); inv1 = ag_rcp(d1 + 1e-10f);                       // graph_attention.py:96
+      }
       const int na = node0_0 + dsel, nb = na + 2;
       char* za = reinterpret_cast<char*>(A.z) + (((size_t)na * NH + hd) * in_dim + sl_0 * 64 + 2 * t4) * 2;
       char* zb = za + (size_t)2 * NH * in_dim * 2;
-      if (na < N) {
+      if (single) {
+        if (na < N) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-          *reinterpret_cast<uint32_t*>(za + nt * 16) = ag_pack_bf16(acc[nt][0] * inv0, acc[nt][1] * inv0);
-      }
-      if (nb < N) {
+          for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(za + nt * 16) = ag_pack_bf16(acc[nt][0], acc[nt][1]);
+        }
+        if (nb < N) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-          *reinterpret_cast<uint32_t*>(zb + nt * 16) = ag_pack_bf16(acc[nt][2] * inv1, acc[nt][3] * inv1);
+          for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(zb + nt * 16) = ag_pack_bf16(acc[nt][2], acc[nt][3]);
+        }
+      } else {
+        if (na < N) {
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(za + nt * 16) = ag_pack_bf16(acc[nt][0] * inv0, acc[nt][1] * inv0);
+        }
+        if (nb < N) {
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(zb + nt * 16) = ag_pack_bf16(acc[nt][2] * inv1, acc[nt][3] * inv1);
+        }
       }
     }
     // rotate the pipeline
