@@ -503,11 +503,11 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
 #pragma unroll
         for (int c = 0; c < 4; ++c) o[r][c] = 0.f;
       for (int h = 0; h < H1; ++h) {
-        float acc[4][4];
+        // acc[r][c] += z[r][i] * W[i][c] on packed fp32 pairs (FFMA2: the same IEEE fmaf per element — labels stay bit-exact — in
+        // half the instructions of the phase that is bound by issue slots)
+        unsigned long long acc2[4][2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        for (int r = 0; r < 4; ++r) acc2[r][0] = acc2[r][1] = 0ull;
         const float* wh = w1t + (size_t)h * in_pad * D + f0;
         const float* zh = zs + (size_t)q0 * zs_stride + h * in_pad;
 #pragma unroll 1
@@ -518,15 +518,21 @@ __global__ void __launch_bounds__(kBT, 1) block_forward_kernel(const BlockArgs A
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii) {
             const float4 wv = *reinterpret_cast<const float4*>(wh + (size_t)(i + ii) * D);
+            const unsigned long long w01 = f32x2_pack(wv.x, wv.y), w23 = f32x2_pack(wv.z, wv.w);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const float zz = ii == 0 ? zv[r].x : (ii == 1 ? zv[r].y : (ii == 2 ? zv[r].z : zv[r].w));
-              acc[r][0] = fmaf(zz, wv.x, acc[r][0]);
-              acc[r][1] = fmaf(zz, wv.y, acc[r][1]);
-              acc[r][2] = fmaf(zz, wv.z, acc[r][2]);
-              acc[r][3] = fmaf(zz, wv.w, acc[r][3]);
+              const unsigned long long z2 = f32x2_pack(zz, zz);
+              f32x2_fma(acc2[r][0], z2, w01);
+              f32x2_fma(acc2[r][1], z2, w23);
             }
           }
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          f32x2_unpack(acc2[r][0], acc[r][0], acc[r][1]);
+          f32x2_unpack(acc2[r][1], acc[r][2], acc[r][3]);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r)

@@ -118,6 +118,24 @@ __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
 __device__ __forceinline__ float leaky_relu(float v, float slope) { return v > 0.f ? v : v * slope; }
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 
+// Packed fp32x2 FMA (sm_100 FFMA2): two independent IEEE fmaf results per instruction, bit-identical to the scalar form.
+// A pair built from the same scalar twice is folded by ptxas into the instruction's scalar-broadcast operand.
+#ifndef MG_HOST_EMULATION
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
+  unsigned a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  lo = __uint_as_float(a); hi = __uint_as_float(b);
+}
+__device__ __forceinline__ void f32x2_fma(unsigned long long& d, unsigned long long a, unsigned long long b) {      // d = a * b + d, per lane
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+#endif
+
 // Streaming (evict-first) 16-byte store for write-once outputs.
 #ifndef MG_HOST_EMULATION
 __device__ __forceinline__ void st_cs_v4(void* p, uint4 v) {

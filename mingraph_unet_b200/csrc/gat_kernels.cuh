@@ -71,11 +71,10 @@ __device__ __forceinline__ void transform_tile(const GatFusedArgs& A, const floa
 #pragma unroll
       for (int c = 0; c < 4; ++c) oacc[r][c] = 0.f;
     for (int h = 0; h < heads; ++h) {
-      float acc[RN][4];
+      // acc[r][c] += z[r][i] * W[i][c] on packed fp32 pairs (FFMA2: the same IEEE fmaf per element, half the instructions)
+      unsigned long long acc2[RN][2];
 #pragma unroll
-      for (int r = 0; r < RN; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      for (int r = 0; r < RN; ++r) acc2[r][0] = acc2[r][1] = 0ull;
       const float* wh = Wt + (size_t)h * A.in_pad * A.f_pad + fg * 4;
       const float* zh = Zs + (size_t)n0 * zs_stride + h * A.in_pad;
       for (int i = 0; i < A.in_pad; i += 4) {
@@ -85,15 +84,21 @@ __device__ __forceinline__ void transform_tile(const GatFusedArgs& A, const floa
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
           const float4 wv = *reinterpret_cast<const float4*>(wh + (size_t)(i + ii) * A.f_pad);
+          const unsigned long long w01 = f32x2_pack(wv.x, wv.y), w23 = f32x2_pack(wv.z, wv.w);
 #pragma unroll
           for (int r = 0; r < RN; ++r) {
             const float zz = ii == 0 ? zv[r].x : (ii == 1 ? zv[r].y : (ii == 2 ? zv[r].z : zv[r].w));
-            acc[r][0] = fmaf(zz, wv.x, acc[r][0]);
-            acc[r][1] = fmaf(zz, wv.y, acc[r][1]);
-            acc[r][2] = fmaf(zz, wv.z, acc[r][2]);
-            acc[r][3] = fmaf(zz, wv.w, acc[r][3]);
+            const unsigned long long z2 = f32x2_pack(zz, zz);
+            f32x2_fma(acc2[r][0], z2, w01);
+            f32x2_fma(acc2[r][1], z2, w23);
           }
         }
+      }
+      float acc[RN][4];
+#pragma unroll
+      for (int r = 0; r < RN; ++r) {
+        f32x2_unpack(acc2[r][0], acc[r][0], acc[r][1]);
+        f32x2_unpack(acc2[r][1], acc[r][2], acc[r][3]);
       }
       // per-head epilogue: ELU, then concat store or running head mean
 #pragma unroll
