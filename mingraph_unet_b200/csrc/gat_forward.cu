@@ -330,7 +330,7 @@ static int launch_scores(const void* x, int N, int in_dim, const float* W, const
 // scores s (N, 2*heads) = [s_src | s_tgt] and the per-graph raw edge maxima gmax (G, heads); shared with backward
 int gat_scores_and_max(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, const float* W,
                        const float* a, int in_dim, int out_dim, int heads, int nodes_per_graph, float* s, float* gmax,
-                       float* u, cudaStream_t st) {
+                       float* u, cudaStream_t st, int64_t E) {
   DimCfg d;
   if (!pick_dims(in_dim, &d)) {
     set_error("gat: in_dim=%d unsupported", in_dim);
@@ -350,6 +350,8 @@ int gat_scores_and_max(const void* x, int x_dtype, const int32_t* rowptr, const 
   else
     rc = launch_scores<__nv_bfloat16>(x, N, in_dim, W, a, u_global, out_dim, heads, G, s, gmax, d, st);
   if (rc) return rc;
+  if (E >= 0 && N >= 4096 && gat_tc_edge_max_supported(heads))        // several gathers in flight per destination (gat_tc.cu)
+    return gat_tc_edge_max(rowptr, col, s, N, E, heads, nodes_per_graph, gmax, st);
   gat_edge_max_kernel<<<ceil_div(N, 256), 256, 0, st>>>(rowptr, col, s, N, heads, nodes_per_graph, gmax);
   return check_launch("gat_edge_max_kernel");
 }
@@ -437,7 +439,7 @@ int mg_gat_forward(const void* x, int x_dtype, const int32_t* rowptr, const int3
   if (x_dtype == MG_BF16 && gat_tc_prepass_supported(N, in_dim, heads))
     rc = gat_tc_prepass(x, rowptr, col, N, E, W, a, in_dim, out_dim, heads, nodes_per_graph, s, gmax, u, st);
   else
-    rc = gat_scores_and_max(x, x_dtype, rowptr, col, N, W, a, in_dim, out_dim, heads, nodes_per_graph, s, gmax, u, st);
+    rc = gat_scores_and_max(x, x_dtype, rowptr, col, N, W, a, in_dim, out_dim, heads, nodes_per_graph, s, gmax, u, st, E);
   if (rc) return rc;
 
   GatAggArgs ag;

@@ -9,7 +9,7 @@ struct DimCfg { int V, T; };
 
 int gat_scores_and_max(const void* x, int x_dtype, const int32_t* rowptr, const int32_t* col, int N, const float* W,
                        const float* a, int in_dim, int out_dim, int heads, int nodes_per_graph, float* s, float* gmax,
-                       float* u, cudaStream_t st);
+                       float* u, cudaStream_t st, int64_t E = -1);      // E >= 0: the caller knows the edge count (faster edge-max kernel)
 static constexpr int64_t kSmemBudget = 200 * 1024;
 
 // tensor-pipe node transform for spilled z (gat_tc_gemm.cu): passes = 1 (tf32, bf16-storage path) or 3 (3xTF32, fp32 path)
@@ -21,6 +21,10 @@ int gat_transform_tc_launch(const float* z, const float* W, int N, int in_dim, i
 bool gat_tc_prepass_supported(int N, int in_dim, int heads);
 int gat_tc_prepass(const void* x, const int32_t* rowptr, const int32_t* col, int N, int64_t E, const float* W, const float* a, int in_dim,
                    int F, int heads, int nodes_per_graph, float* s, float* gmax, float* u, cudaStream_t st);
+// exact per-graph edge maximum alone (gat_tc.cu), for heads 1/2/4 behind any score kernel that reset gmax
+bool gat_tc_edge_max_supported(int heads);
+int gat_tc_edge_max(const int32_t* rowptr, const int32_t* col, const float* s, int N, int64_t E, int heads, int nodes_per_graph, float* gmax,
+                    cudaStream_t st);
 // tensor-core aggregation with z spilled to HBM as bf16 (gat_tc.cu): heads 4, in a multiple of 64; needs s / gmax of the pre-pass
 bool gat_agg_spill_supported(int N, int in_dim, int heads);
 int gat_agg_spill_launch(const void* x, const int32_t* rowptr, const int32_t* col, const float* s, const float* gmax, void* z_bf16, int N,
